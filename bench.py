@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py -- SpGEMM + SSpMM throughput of the MaxK-GNN aggregation hot path.
+
+One "step" = one layer's aggregation forward (row-wise-product SpGEMM over the CBSR table) plus
+its backward (sampled SSpMM that emits the CBSR gradient) on a synthetic graph of one of the
+BASELINE.json shapes, D = 256, k = 32, SAGE-mean edge weights, fp32.  Default workload:
+BASELINE.json configs[1], the Reddit-shaped graph (232,965 nodes, ~114M stored entries).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+`value` = edge traversals per second of the whole job = 2 * E / (time per step), inputs resident
+in HBM.  `e2e` = the same through the reference-facing entry points with HOST buffers: every step
+copies that step's activations X and dY from pinned host memory, runs maxk_forward_cbsr ->
+spgemm_forward -> spgemm_backward, and copies both results back.  `--impl reference` times the
+reference's own formulation (dense masked features, CSR SpMM forward + transposed backward through
+autograd; torch.sparse.mm in the place of DGL, which is not in the image) on the host cores, on a
+bounded row sample of the same workload.
+
+N > 1 (torchrun): the same graph, 1-D row partition, CBSR all-gather forward and CBSR-gradient
+reduce-scatter backward over NCCL inside the timed step ("scaling": "strong").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "SpGEMM+SSpMM edge traversals per second (fwd+bwd of one aggregation layer, k=32, dim 256)"
+UNIT = "edges/s"
+
+
+# ---------------------------------------------------------------------------------------
+# bookkeeping helpers
+# ---------------------------------------------------------------------------------------
+def algorithmic_bytes(n_rows, n_src, e, p, k, d, w):
+    """SURVEY.md section 8d / DESIGN.md: bytes one launch has to touch, per kernel."""
+    fwd = e * (4 + 4 + k * (4 + w)) + n_rows * d * 4 + (n_rows + 1) * 4 + p * 16
+    bwd = e * (4 + 4 + k * w + k * 4) + n_rows * d * 4 + n_src * k * 4 + (n_rows + 1) * 4 + p * 16
+    return fwd, bwd
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel, workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        return t.get(workload, {}).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """SM clock and throttle reasons during the timed region (NVML, 20 ms period)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        if not self.samples:
+            return None
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def workload_config(args, world, n, e):
+    return {"workload": f"{args.workload}-shaped synthetic graph, {n} nodes, {e} stored entries "
+                        f"(symmetric, self-loops, seed 97), dim_origin {args.dim}, k {args.k}, "
+                        f"SAGE-mean weights, fp32",
+            "graph": args.workload, "nodes": n, "edges": e, "dim_origin": args.dim, "k": args.k,
+            "scale": args.scale,
+            "parallelism": "1 GPU" if world == 1 else f"1-D row partition over {world} GPUs, "
+                           "CBSR all-gather fwd + CBSR-grad reduce-scatter bwd (NCCL)",
+            "l2": "no explicit flush: every step streams inputs larger than L2 "
+                  "(edge arrays 8 B/entry + dense rows); the CBSR table is re-used inside one "
+                  "launch by construction"}
+
+
+# ---------------------------------------------------------------------------------------
+# the reference's CPU formulation (oracle port) -- cpu_baseline and --impl reference
+# ---------------------------------------------------------------------------------------
+def cpu_reference(args, graph_cpu_rows, x_cpu, steps, warmup):
+    """Dense-feature SpMM forward + backward through autograd on the host cores, on the row
+    sample `graph_cpu_rows` = (indptr, indices, val, n_src).  Returns (edges/s, ms/step, cores)."""
+    from oracle import ref_torch
+    indptr, indices, val, n_src = graph_cpu_rows
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    adj = ref_torch.csr_matrix(indptr, indices, val, n_src)
+    rows = indptr.numel() - 1
+    e = indices.numel()
+    with torch.no_grad():
+        xm = ref_torch.RefMaxK.apply(x_cpu, args.k)      # masked dense features (resident input)
+    gen = torch.Generator().manual_seed(98)
+    dy = torch.randn(rows, x_cpu.shape[1], generator=gen)
+    times = []
+    for it in range(warmup + steps):
+        xin = xm.detach().requires_grad_(True)
+        t0 = time.perf_counter()
+        y = ref_torch.aggregate(adj, xin)
+        y.backward(dy)
+        t1 = time.perf_counter()
+        if it >= warmup:
+            times.append(t1 - t0)
+    t = statistics.median(times)
+    return 2.0 * e / t, t * 1e3, cores, e, rows
+
+
+def cpu_sample_of(g, val, frac_rows):
+    n = g.num_nodes()
+    rows = max(int(n * frac_rows), 1)
+    hi = int(g.indptr[rows])
+    return (g.indptr[: rows + 1].cpu(), g.indices[:hi].cpu(), val[:hi].cpu(), g.num_src), rows, hi
+
+
+# ---------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="reddit",
+                    choices=["reddit", "flickr", "yelp", "ogbn-products", "ogbn-proteins"])
+    ap.add_argument("--k", type=int, default=32)
+    ap.add_argument("--dim", type=int, default=256)
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debug only)")
+    ap.add_argument("--max-nz", type=int, default=None)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-rows", type=float, default=1.0 / 32, help="row fraction of the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from spgemm_gnn_b200.graph import shaped_graph
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        g = shaped_graph(args.workload, scale=args.scale, device=dev)
+        n, e = g.num_nodes(), g.num_edges()
+        val = g.edge_weights("mean")
+        sample, rows, e_s = cpu_sample_of(g, val, args.cpu_rows)
+        x_cpu = torch.randn(g.num_src, args.dim, generator=torch.Generator().manual_seed(97))
+        v, ms, cores, e_s, rows = cpu_reference(args, sample, x_cpu, args.steps, args.warmup)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, world, n, e),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"rows [0,{rows}) of the workload graph ({e_s} stored entries, "
+                                       f"all {g.num_src} columns): masked-dense CSR SpMM forward + "
+                                       "transposed backward via torch autograd (torch.sparse.mm "
+                                       "stands in for DGL's CPU SpMM, absent from the image)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the hot path has no CPU fallback"}))
+        return 2
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    import maxk_kernels as mk
+    from spgemm_gnn_b200 import _lib
+    from spgemm_gnn_b200 import dist as mdist
+    if _lib.lib().mk_device_ok() != 0:
+        print(json.dumps({"error": "device is not sm_100"}))
+        return 2
+    if args.max_nz:
+        mk.set_max_nz(args.max_nz)
+
+    g = shaped_graph(args.workload, scale=args.scale, device=device)
+    n, e = g.num_nodes(), g.num_edges()
+    k, d = args.k, args.dim
+    w = 1 if d <= 256 else 2
+    val_full = g.edge_weights("mean")
+    if world > 1:
+        local, r0, r1 = mdist.shard_graph(g, rank, world)
+        val = mdist.shard_edge_weights(g, local, r0, r1, "mean")
+        n_rows, n_src = local.num_nodes(), local.num_src
+    else:
+        local, val, r0, r1 = g, val_full, 0, n
+        n_rows, n_src = n, n
+    e_local = local.num_edges()
+    gen = torch.Generator(device=device).manual_seed(97 + rank)
+    x_local = torch.randn(n_rows, d, device=device, generator=gen)
+    dy = torch.randn(n_rows, d, device=device, generator=gen)
+    sp_data, sp_index = mk.maxk_forward_cbsr(x_local, k)
+    part = mk.partition(local.indptr, n_rows)
+    ptr, idx = local.indptr, local.indices
+
+    def step():
+        if world > 1:
+            fd, fi = mdist.allgather_cbsr(sp_data, sp_index)
+        else:
+            fd, fi = sp_data, sp_index
+        out, _ = mk.spgemm_forward(ptr, idx, val, fd, fi, n_rows, e_local, k, d)
+        mid.record()
+        dxs = mk.spgemm_backward(ptr, idx, val, dy, fi, n_rows, e_local, k, d)
+        if world > 1:
+            dxs = mdist.reduce_scatter_rows(dxs)
+        return out, dxs
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    mid = torch.cuda.Event(enable_timing=True)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching (current) stream
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    clocks = ClockSampler(local_rank)
+    launches0 = mk.launch_count()
+    clocks.start()
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_stop = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        mid = ev[i][1]
+        ev[i][0].record()
+        step()
+        ev[i][2].record()
+    t_stop.record()
+    barrier()
+    clk = clocks.stop()
+    launches = mk.launch_count() - launches0
+    total_ms = t_start.elapsed_time(t_stop)
+    if world > 1:
+        tt = torch.tensor([total_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    ms_step = total_ms / args.steps
+    fwd_ms = statistics.mean(a.elapsed_time(b) for a, b, _ in ev)
+    bwd_ms = statistics.mean(b.elapsed_time(c) for _, b, c in ev)
+    value = 2.0 * e / (ms_step * 1e-3)
+
+    # ---- separate timings of the other kernels of the path (not part of the step)
+    def time_op(fn, reps=10):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    topk_ms = time_op(lambda: mk.maxk_forward_cbsr(x_local, k))
+    dxs_probe = torch.randn(n_rows, k, device=device)
+    scatter_ms = time_op(lambda: mk.cbsr_scatter(dxs_probe, sp_index, d))
+
+    # ---- roofline of the dominant kernel
+    peak, peak_src = measured_peak()
+    bf, bb = algorithmic_bytes(n_rows, n_src, e_local, part.num_parts, k, d, w)
+    dom = "spgemm_fwd" if fwd_ms >= bwd_ms else "sspmm_bwd"
+    dom_ms, dom_bytes = (fwd_ms, bf) if dom == "spgemm_fwd" else (bwd_ms, bb)
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(dom, args.workload),
+                "peak_source": peak_src, "algorithmic_bytes": dom_bytes, "launch_ms": dom_ms,
+                "compulsory_bytes": e_local * 8 + n_src * k * (4 + w) + n_rows * d * 4,
+                "note": "algorithmic bytes count every CBSR row gather; the CBSR table itself is "
+                        "L2-resident for this shape, so achieved GB/s is L2+HBM traffic over time"}
+    kernels = {
+        "spgemm_fwd_ms": fwd_ms, "sspmm_bwd_ms": bwd_ms,
+        "spgemm_fwd_alg_GBps": bf / (fwd_ms * 1e-3) / 1e9, "sspmm_bwd_alg_GBps": bb / (bwd_ms * 1e-3) / 1e9,
+        "spgemm_fwd_frac_of_peak": bf / (fwd_ms * 1e-3) / 1e9 / peak,
+        "sspmm_bwd_frac_of_peak": bb / (bwd_ms * 1e-3) / 1e9 / peak,
+        "maxk_topk_cbsr_ms": topk_ms, "maxk_alg_GBps": (n_rows * d * 4 + n_rows * k * (4 + w)) / (topk_ms * 1e-3) / 1e9,
+        "cbsr_scatter_ms": scatter_ms,
+        "scatter_alg_GBps": (n_rows * k * (4 + w) + n_rows * d * 4) / (scatter_ms * 1e-3) / 1e9,
+        "edges_per_s_fwd": e / (fwd_ms * 1e-3), "edges_per_s_bwd": e / (bwd_ms * 1e-3),
+        "work_records": part.num_parts, "partial_slots": part.num_slots, "max_nz": mk.get_max_nz(),
+    }
+
+    # ---- end to end through the public entry points with HOST buffers
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty((n_rows, d), dtype=torch.float32).pin_memory()
+        hdy = torch.empty((n_rows, d), dtype=torch.float32).pin_memory()
+        hx.copy_(x_local)
+        hdy.copy_(dy)
+        hout = torch.empty((n_rows, d), dtype=torch.float32).pin_memory()
+        hdxs = torch.empty((n_rows, k), dtype=torch.float32).pin_memory()
+        dx_dev = torch.empty_like(x_local)
+        dy_dev = torch.empty_like(dy)
+
+        def e2e_step():
+            dx_dev.copy_(hx, non_blocking=True)
+            dy_dev.copy_(hdy, non_blocking=True)
+            sd, si = mk.maxk_forward_cbsr(dx_dev, k)
+            if world > 1:
+                fd, fi = mdist.allgather_cbsr(sd, si)
+            else:
+                fd, fi = sd, si
+            out, _ = mk.spgemm_forward(ptr, idx, val, fd, fi, n_rows, e_local, k, d)
+            dxs = mk.spgemm_backward(ptr, idx, val, dy_dev, fi, n_rows, e_local, k, d)
+            if world > 1:
+                dxs = mdist.reduce_scatter_rows(dxs)
+            hout.copy_(out, non_blocking=True)
+            hdxs.copy_(dxs, non_blocking=True)
+
+        e2e_step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        b.record()
+        barrier()
+        e2e_ms = a.elapsed_time(b) / args.e2e_steps
+        if world > 1:
+            tt = torch.tensor([e2e_ms], device=device, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_ms = float(tt.item())
+        e2e = {"value": 2.0 * e / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+               "steps": args.e2e_steps,
+               "h2d_bytes_per_step": 2 * n_rows * d * 4 * world,
+               "d2h_bytes_per_step": (n_rows * d * 4 + n_rows * k * 4) * world,
+               "path": "pinned host X,dY -> H2D -> maxk_forward_cbsr -> spgemm_forward -> "
+                       "spgemm_backward -> D2H out,dXs (graph CSR resident, as g.to(device) in the reference)"}
+
+    # ---- CPU baseline (rank 0, N == 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample, rows, e_s = cpu_sample_of(g, val_full, args.cpu_rows)
+        v, ms, cores, e_s, rows = cpu_reference(args, sample, x_local.cpu(), steps=3, warmup=1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
+               "sample": f"rows [0,{rows}) of the workload graph ({e_s} stored entries, all {n} "
+                         "columns): masked-dense CSR SpMM forward + transposed backward via torch "
+                         "autograd (torch.sparse.mm stands in for DGL's CPU SpMM, absent from the image)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world, n, e), "clocks": clk, "e2e": e2e,
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,127 @@
+/*
+ * maxk_b200.h -- C ABI of the B200-native MaxK-GNN aggregation hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch
+ * types, no exceptions, every entry point returns 0 or a negative MK_E* code and launches
+ * asynchronously on the CUDA stream it is given (a `cudaStream_t` passed as `void*`; NULL
+ * is the legacy default stream).  All pointers are DEVICE pointers unless the parameter
+ * name starts with `h_`.  Inputs are borrowed and never written.
+ *
+ * Each entry point names the reference interface it replaces.  Paths are relative to
+ * julius-sk/spgemm-gnn; `so@0x...` / `.o@0x...` are addresses inside the only form the
+ * reference ships its native code in (`maxk_kernels.cpython-39-x86_64-linux-gnu.so`,
+ * `build/temp.linux-x86_64-cpython-39/kernels/*.o`) as decoded in SURVEY.md section 2.3.
+ *
+ * CBSR ("compressed balanced sparse row"): a matrix with exactly k kept entries per row,
+ *   sp_data  float32 [n, k]  row-major, the kept values,
+ *   sp_index uint8   [n, k]  (index_bytes == 1, dim_origin <= 256) or
+ *            uint16  [n, k]  (index_bytes == 2, dim_origin <= 65536),
+ * entries of a row in ascending column order, columns of a row distinct.
+ */
+#ifndef MAXK_B200_H_
+#define MAXK_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define MK_API
+#else
+#define MK_API __attribute__((visibility("default")))
+#endif
+
+#define MK_VERSION 100 /* major*100 + minor */
+
+enum {
+    MK_OK = 0,
+    MK_EINVAL = -1,       /* bad argument (null pointer, k out of range, ...)            */
+    MK_EUNSUPPORTED = -2, /* combination of sizes the kernels do not cover               */
+    MK_ECUDA = -3,        /* a CUDA runtime call failed: see mk_last_cuda_error()        */
+    MK_ENODEVICE = -4     /* no CUDA device / not an sm_100 part                         */
+};
+
+/* One record per unit of work of the forward and backward kernels: the stored entries
+ * [loc, loc+len) of CSR row `row`.  Same 16-byte layout as the `.warp4` records the
+ * reference reads from disk on every call (`cuda_read_array<int>`, so@0x252c0; consumed
+ * with one LDG.E.128 at fwd.sass 0380).  The reference leaves the 4th word unused; here
+ * it is the partial-sum slot: -1 when the row has a single record (the kernel writes the
+ * output row itself), otherwise an index into the caller's partial buffer, folded in
+ * fixed order by mk_spgemm_fwd (no float atomics on the forward path). */
+typedef struct mk_part {
+    int32_t row;
+    int32_t loc;
+    int32_t len;
+    int32_t slot;
+} mk_part;
+
+MK_API int mk_version(void);
+MK_API const char* mk_error_string(int code);
+/* text of the last CUDA error this library saw on the calling thread ("" if none) */
+MK_API const char* mk_last_cuda_error(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), else MK_ENODEVICE */
+MK_API int mk_device_ok(void);
+
+/* ---- a-1  MaxK nonlinearity -> CBSR --------------------------------------------------
+ * Replaces `maxk_forward` -> `maxk_forward_cuda` -> `maxk_kernel` (maxk_cuda_kernels.o@0x1e0,
+ * so@0x21110; Python caller utils/maxk_layers.py:21) and the torch formulation
+ * `topk -> zeros_like -> scatter_ -> multiply` (utils/models.py:14-20).
+ * Exact top-k per row: larger value first, every NaN above +inf, -0.0 == +0.0, ties go to
+ * the LOWER column.  Values are bit copies of the inputs.  1 <= k <= d.                  */
+MK_API int mk_topk_cbsr(const float* x, int64_t n, int d, int k, float* sp_data, void* sp_index,
+                        int index_bytes, void* stream);
+
+/* ---- a-2  CBSR gradient -> dense ----------------------------------------------------
+ * Replaces `maxk_backward` -> `maxk_backward_cuda` (maxk_cuda_kernels.o@0x4d0: an N*k host
+ * loop of `.item()` copies; Python caller utils/maxk_layers.py:40) and `grad * mask`
+ * (utils/models.py:23-26).  dense[i, :] = 0; dense[i, sp_index[i,t]] = g[i,t].          */
+MK_API int mk_cbsr_scatter(const float* g, const void* sp_index, int index_bytes, float* dense,
+                           int64_t n, int k, int d, void* stream);
+
+/* out[i,t] = dense[i, sp_index[i,t]] -- the vectorised replacement of the per-row Python
+ * loop `_extract_sparse_format` (utils/maxk_layers.py:224-265) once the positions are
+ * known, and the first half of `grad * mask`.                                           */
+MK_API int mk_cbsr_gather(const float* dense, const void* sp_index, int index_bytes, float* out,
+                          int64_t n, int k, int d, void* stream);
+
+/* ---- a-5  work partition -------------------------------------------------------------
+ * Replaces kernels/generate_meta.py (offline) + the per-call file read of
+ * `../w12_nz64_warp_4/<graph>.warp4` (`SPMM_MAXK::do_test`, so@0x24c50-0x24d2c).
+ * Cuts every CSR row into records of at most max_nz stored entries; an empty row gets one
+ * record of length 0.  Records are in row order.
+ *   parts == NULL : size query; *h_num_parts / *h_num_slots are written (host ints) after
+ *                   the stream has been synchronised.
+ *   parts != NULL : must hold the queried number of records; filled asynchronously.     */
+MK_API int mk_partition(const int32_t* ptr, int64_t n_rows, int max_nz, mk_part* parts,
+                        int64_t* h_num_parts, int64_t* h_num_slots, void* stream);
+
+/* ---- a-3  forward row-wise-product SpGEMM -------------------------------------------
+ * Replaces `spgemm_forward` -> `spgemm_forward_cuda` -> `SPMM_MAXK::do_test` ->
+ * `spmm_kernel_opt2_sparse_v3` (maxk_cuda_kernels.o@0x1260, so@0x24bf0, so@0x24b60; Python
+ * callers utils/maxk_layers.py:166-171, 380-385) and DGL's `graph.update_all(copy_u, ...)`
+ * (utils/models.py:163,284,407).
+ *   out[r, sp_index[j,t]] += val[e] * sp_data[j,t]   for every stored e = (r <- j), t < k.
+ * `out` [n_rows, d] is fully written (no zero-fill needed).  `partial` [num_slots, d] is
+ * scratch, may be NULL when num_slots == 0.  Deterministic: no atomics.                  */
+MK_API int mk_spgemm_fwd(const mk_part* parts, int64_t num_parts, int64_t num_slots,
+                         const int32_t* idx, const float* val, const float* sp_data,
+                         const void* sp_index, int index_bytes, float* out, float* partial,
+                         int64_t n_rows, int k, int d, void* stream);
+
+/* ---- a-4  backward sampled SpMM (SSpMM) ----------------------------------------------
+ * Replaces `spgemm_backward` -> `spgemm_backward_cuda` -> `SPMM_MAXK_BACKWARD::do_test` ->
+ * `spmm_kernel_opt2_sparse_backward_v3` (maxk_cuda_kernels.o@0x1550, so@0x257a0) and the
+ * autograd of DGL's SpMM followed by `grad * mask`.
+ *   dxs[j,t] += val[e] * dy[r, sp_index[j,t]]        for every stored e = (r <- j), t < k.
+ * `dxs` [n_src, k] is zero-filled by the call itself, then accumulated with vector
+ * float reductions in L2 (summation order is not fixed, as in the reference's RED).      */
+MK_API int mk_sspmm_bwd(const mk_part* parts, int64_t num_parts, const int32_t* idx,
+                        const float* val, const float* dy, const void* sp_index, int index_bytes,
+                        float* dxs, int64_t n_rows, int64_t n_src, int k, int d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAXK_B200_H_ */

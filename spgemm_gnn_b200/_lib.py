@@ -1,0 +1,62 @@
+"""ctypes binding of libmaxk_b200.so (the C ABI declared in include/maxk_b200.h).
+
+There is no CPU fallback: if the shared object is missing or fails to load, every product
+entry point raises.  Build it with `python -m spgemm_gnn_b200.build` (or
+`__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libmaxk_b200.so")
+
+MK_OK, MK_EINVAL, MK_EUNSUPPORTED, MK_ECUDA, MK_ENODEVICE = 0, -1, -2, -3, -4
+
+# name -> (restype, argtypes); must list every symbol of include/maxk_b200.h
+_i32, _i64, _vp = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p
+SIGNATURES = {
+    "mk_version": (_i32, []),
+    "mk_error_string": (ctypes.c_char_p, [_i32]),
+    "mk_last_cuda_error": (ctypes.c_char_p, []),
+    "mk_device_ok": (_i32, []),
+    "mk_topk_cbsr": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "mk_cbsr_scatter": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, _i32, _vp]),
+    "mk_cbsr_gather": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, _i32, _vp]),
+    "mk_partition": (_i32, [_vp, _i64, _i32, _vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp]),
+    "mk_spgemm_fwd": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "mk_sspmm_bwd": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _i32, _vp]),
+}
+
+_lib = None
+
+
+class MaxKLibraryError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise MaxKLibraryError(
+                f"{SO_PATH} is missing: the CUDA library of the hot path is not built "
+                "(run `python -m spgemm_gnn_b200.build`); there is no CPU fallback")
+        L = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError here == header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc == MK_OK:
+        return
+    L = lib()
+    msg = L.mk_error_string(rc).decode()
+    if rc == MK_ECUDA:
+        msg += ": " + L.mk_last_cuda_error().decode()
+    raise RuntimeError(f"{what} failed: {msg}")

@@ -1,0 +1,253 @@
+// a-3  Forward row-wise-product SpGEMM:  out = A(CSR) x Xs(CBSR)  -> dense [n_rows, D].
+//
+// One warp per work record (<= max_nz stored entries of one CSR row), one record per CTA so
+// that the hardware CTA scheduler does the dynamic load balancing over the skewed degree
+// distribution.  The warp owns a dense fp32 accumulator of D floats in shared memory
+// (one per lane group when k < 32).  Per stored entry (r <- j) a group of LPN = min(k,32)
+// lanes gathers j's CBSR row with one coalesced load of the values (k*4 B) and one of the
+// column ids (k*w B) and adds val*data into acc[col] -- plain LDS/FFMA/STS, race-free because
+// the columns of a CBSR row are distinct.  Gathers of U neighbours are issued before their
+// accumulation so that U*2 loads per lane are in flight.
+//
+// Differences from the reference kernel (spmm_kernel_opt2_sparse_v3, so@0x24b60):
+//   * records come from mk_partition on the GPU, not from a .warp4 file;
+//   * a row with a single record is written with full-line vector stores, a row with several
+//     records goes through a partial buffer folded in fixed order: no float atomics
+//     (the reference does D RED.E.ADD.F32 per <=64-entry record), bit-reproducible output;
+//   * for k < 32 all 32 lanes work (32/k neighbours per step) instead of the first 12
+//     sub-warps of a 384-thread block;
+//   * entries whose value is exactly 0.0 are skipped, which makes the zero-padded rows of
+//     utils/maxk_layers.py:245-257 harmless (they race in the reference).
+//
+// Algorithmic bytes per launch:
+//   E*(4 + 4 + k*(4+w)) + N*D*4 + (N+1)*4 + P*16.
+#include "common.cuh"
+
+namespace mk {
+
+template <int K>
+struct FwdShape {
+    static constexpr int LPN = K < 32 ? K : 32;  // lanes per neighbour
+    static constexpr int EPL = K / LPN;          // entries per lane
+    static constexpr int G = 32 / LPN;           // neighbours per warp step
+    static_assert(K % LPN == 0, "K must be a power of two <= 32 or a multiple of 32");
+};
+
+template <int K, typename IdxT, int U, bool VEC>
+__global__ void __launch_bounds__(32)
+spgemm_fwd_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
+                  const float* __restrict__ val, const float* __restrict__ sp_data,
+                  const IdxT* __restrict__ sp_index, float* __restrict__ out,
+                  float* __restrict__ partial, int d) {
+    using S = FwdShape<K>;
+    extern __shared__ __align__(16) float acc[];  // S::G accumulators of dpad floats
+    const int dpad = (d + 3) & ~3;
+    const int lane = lane_id();
+    const int g = lane / S::LPN;
+    const int t = lane % S::LPN;
+    const mk_part rec = parts[blockIdx.x];
+
+    for (int c = lane * 4; c < S::G * dpad; c += 128)
+        *reinterpret_cast<float4*>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+
+    float* __restrict__ my = acc + g * dpad;
+    const int end = rec.loc + rec.len;
+    for (int base = rec.loc; base < end; base += 32) {
+        const int n_here = min(32, end - base);
+        int my_nz = 0;
+        float my_v = 0.f;
+        if (lane < n_here) {
+            my_nz = ld_stream_i1(idx + base + lane);
+            my_v = ld_stream_f1(val + base + lane);
+        }
+        for (int i = 0; i < n_here; i += S::G * U) {
+            float dv[U][S::EPL];
+            int cv[U][S::EPL];
+            float vv[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = i + u * S::G + g;
+                const int nz = __shfl_sync(kFull, my_nz, e & 31);
+                vv[u] = __shfl_sync(kFull, my_v, e & 31);
+                ok[u] = e < n_here;
+                if (ok[u]) {
+                    const float* __restrict__ dp = sp_data + static_cast<int64_t>(nz) * K;
+                    const IdxT* __restrict__ ip = sp_index + static_cast<int64_t>(nz) * K;
+#pragma unroll
+                    for (int q = 0; q < S::EPL; ++q) {
+                        dv[u][q] = __ldg(dp + t + q * S::LPN);
+                        cv[u][q] = static_cast<int>(__ldg(ip + t + q * S::LPN));
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (ok[u]) {
+#pragma unroll
+                    for (int q = 0; q < S::EPL; ++q)
+                        if (dv[u][q] != 0.0f) my[cv[u][q]] += vv[u] * dv[u][q];
+                }
+            }
+        }
+    }
+    __syncwarp();
+
+    float* __restrict__ o = rec.slot < 0 ? out + static_cast<int64_t>(rec.row) * d
+                                         : partial + static_cast<int64_t>(rec.slot) * d;
+    if (VEC) {
+        for (int c = lane * 4; c < d; c += 128) {
+            float4 s = *reinterpret_cast<const float4*>(acc + c);
+#pragma unroll
+            for (int q = 1; q < S::G; ++q) {
+                const float4 a = *reinterpret_cast<const float4*>(acc + q * dpad + c);
+                s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+            }
+            st_stream_f4(o + c, s);
+        }
+    } else {
+        for (int c = lane; c < d; c += 32) {
+            float s = acc[c];
+#pragma unroll
+            for (int q = 1; q < S::G; ++q) s += acc[q * dpad + c];
+            o[c] = s;
+        }
+    }
+}
+
+// Any k: one neighbour per warp step, lanes stride over its entries.
+template <typename IdxT>
+__global__ void __launch_bounds__(32)
+spgemm_fwd_generic_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
+                          const float* __restrict__ val, const float* __restrict__ sp_data,
+                          const IdxT* __restrict__ sp_index, float* __restrict__ out,
+                          float* __restrict__ partial, int k, int d) {
+    extern __shared__ __align__(16) float acc[];
+    const int lane = lane_id();
+    const mk_part rec = parts[blockIdx.x];
+    for (int c = lane; c < d; c += 32) acc[c] = 0.f;
+    __syncwarp();
+    const int end = rec.loc + rec.len;
+    for (int e = rec.loc; e < end; ++e) {
+        const int64_t nz = idx[e];
+        const float v = val[e];
+        for (int q = lane; q < k; q += 32) {
+            const float dv = __ldg(sp_data + nz * k + q);
+            const int c = static_cast<int>(__ldg(sp_index + nz * k + q));
+            if (dv != 0.0f) acc[c] += v * dv;
+        }
+        __syncwarp();
+    }
+    float* __restrict__ o = rec.slot < 0 ? out + static_cast<int64_t>(rec.row) * d
+                                         : partial + static_cast<int64_t>(rec.slot) * d;
+    for (int c = lane; c < d; c += 32) o[c] = acc[c];
+}
+
+// Folds the partial rows of every multi-record row in slot order.  One warp per record;
+// only the first record of such a row does work.
+__global__ void __launch_bounds__(256)
+spgemm_fold_kernel(const mk_part* __restrict__ parts, int64_t num_parts,
+                   const float* __restrict__ partial, float* __restrict__ out, int d) {
+    const int64_t p = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (p >= num_parts) return;
+    const mk_part rec = parts[p];
+    if (rec.slot < 0) return;
+    if (p > 0 && parts[p - 1].row == rec.row) return;
+    int cnt = 1;
+    while (p + cnt < num_parts && parts[p + cnt].row == rec.row) ++cnt;
+    const int lane = lane_id();
+    float* __restrict__ o = out + static_cast<int64_t>(rec.row) * d;
+    const float* __restrict__ src = partial + static_cast<int64_t>(rec.slot) * d;
+    for (int c = lane; c < d; c += 32) {
+        float s = src[c];
+        for (int q = 1; q < cnt; ++q) s += src[static_cast<int64_t>(q) * d + c];
+        o[c] = s;
+    }
+}
+
+template <int K, typename IdxT>
+static int launch_fwd_k(const mk_part* parts, int64_t num_parts, const int* idx, const float* val,
+                        const float* sp_data, const void* sp_index, float* out, float* partial,
+                        int d, cudaStream_t st) {
+    using S = FwdShape<K>;
+    constexpr int U = K >= 64 ? 4 : 8;
+    const int dpad = (d + 3) & ~3;
+    const size_t smem = static_cast<size_t>(S::G) * dpad * 4;
+    if (smem > 200 * 1024) return MK_EUNSUPPORTED;
+    const bool vec = (d % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
+                     (partial == nullptr || reinterpret_cast<uintptr_t>(partial) % 16 == 0);
+    const IdxT* si = static_cast<const IdxT*>(sp_index);
+    if (vec) {
+        auto kern = spgemm_fwd_kernel<K, IdxT, U, true>;
+        if (smem > 48 * 1024)
+            MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem)));
+        kern<<<static_cast<unsigned>(num_parts), 32, smem, st>>>(parts, idx, val, sp_data, si, out,
+                                                                 partial, d);
+    } else {
+        auto kern = spgemm_fwd_kernel<K, IdxT, U, false>;
+        if (smem > 48 * 1024)
+            MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem)));
+        kern<<<static_cast<unsigned>(num_parts), 32, smem, st>>>(parts, idx, val, sp_data, si, out,
+                                                                 partial, d);
+    }
+    MK_LAUNCH_CHECK("spgemm_fwd_kernel");
+    return MK_OK;
+}
+
+template <typename IdxT>
+static int launch_fwd(const mk_part* parts, int64_t num_parts, const int* idx, const float* val,
+                      const float* sp_data, const void* sp_index, float* out, float* partial,
+                      int k, int d, cudaStream_t st) {
+    switch (k) {
+        case 4: return launch_fwd_k<4, IdxT>(parts, num_parts, idx, val, sp_data, sp_index, out, partial, d, st);
+        case 8: return launch_fwd_k<8, IdxT>(parts, num_parts, idx, val, sp_data, sp_index, out, partial, d, st);
+        case 16: return launch_fwd_k<16, IdxT>(parts, num_parts, idx, val, sp_data, sp_index, out, partial, d, st);
+        case 32: return launch_fwd_k<32, IdxT>(parts, num_parts, idx, val, sp_data, sp_index, out, partial, d, st);
+        case 64: return launch_fwd_k<64, IdxT>(parts, num_parts, idx, val, sp_data, sp_index, out, partial, d, st);
+        case 96: return launch_fwd_k<96, IdxT>(parts, num_parts, idx, val, sp_data, sp_index, out, partial, d, st);
+        case 128: return launch_fwd_k<128, IdxT>(parts, num_parts, idx, val, sp_data, sp_index, out, partial, d, st);
+        default: break;
+    }
+    const size_t smem = static_cast<size_t>(d) * 4;
+    if (smem > 200 * 1024) return MK_EUNSUPPORTED;
+    if (smem > 48 * 1024)
+        MK_CUDA_TRY(cudaFuncSetAttribute(spgemm_fwd_generic_kernel<IdxT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    spgemm_fwd_generic_kernel<IdxT><<<static_cast<unsigned>(num_parts), 32, smem, st>>>(
+        parts, idx, val, sp_data, static_cast<const IdxT*>(sp_index), out, partial, k, d);
+    MK_LAUNCH_CHECK("spgemm_fwd_generic_kernel");
+    return MK_OK;
+}
+
+}  // namespace mk
+
+extern "C" int mk_spgemm_fwd(const mk_part* parts, int64_t num_parts, int64_t num_slots,
+                             const int32_t* idx, const float* val, const float* sp_data,
+                             const void* sp_index, int index_bytes, float* out, float* partial,
+                             int64_t n_rows, int k, int d, void* stream) {
+    if (n_rows < 0 || num_parts < 0 || num_slots < 0 || d < 1 || k < 1 || k > d) return MK_EINVAL;
+    if (index_bytes != 1 && index_bytes != 2) return MK_EINVAL;
+    if ((index_bytes == 1 && d > 256) || d > 65536) return MK_EINVAL;
+    if (n_rows == 0 || num_parts == 0) return MK_OK;
+    if (!parts || !out || !sp_data || !sp_index) return MK_EINVAL;
+    if (num_slots > 0 && !partial) return MK_EINVAL;
+    if (num_parts > 0x7fffffffLL) return MK_EUNSUPPORTED;
+    cudaStream_t st = mk::as_stream(stream);
+    const int rc = index_bytes == 1
+                       ? mk::launch_fwd<uint8_t>(parts, num_parts, idx, val, sp_data, sp_index, out,
+                                                 partial, k, d, st)
+                       : mk::launch_fwd<uint16_t>(parts, num_parts, idx, val, sp_data, sp_index,
+                                                  out, partial, k, d, st);
+    if (rc != MK_OK) return rc;
+    if (num_slots > 0) {
+        const int64_t blocks = (num_parts * 32 + 255) / 256;
+        mk::spgemm_fold_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(parts, num_parts,
+                                                                              partial, out, d);
+        MK_LAUNCH_CHECK("spgemm_fold_kernel");
+    }
+    return MK_OK;
+}

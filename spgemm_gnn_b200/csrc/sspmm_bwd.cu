@@ -1,0 +1,186 @@
+// a-4  Backward sampled SpMM (SSpMM):  dXs = sample(A^T x dY) at the forward's top-k positions,
+//      emitted as a CBSR gradient [n_src, k].
+//
+// Outer-product (push) form, like the reference (spmm_kernel_opt2_sparse_backward_v3,
+// so@0x257a0): one warp per work record of CSR row r; dY[r, :] is staged once in shared
+// memory; for every stored entry (r <- j) the warp reads j's k column ids, picks dY[r, col]
+// out of shared memory, scales by val and adds into dXs[j, :].
+// What is different:
+//   * each lane handles FOUR consecutive entries of a neighbour: one 4-byte (uint8) or
+//     8-byte (uint16) load of column ids and ONE vector reduction `red.global.add.v4.f32`
+//     (SASS REDG.E.ADD.F32x4) instead of four scalar RED -- k/4 lanes per neighbour, 128/k
+//     neighbours per warp step, all lanes busy for every k in {4..128};
+//   * U steps of column ids are loaded before any is consumed (the staged dY row is
+//     read-only, so the compiler is free to overlap them);
+//   * the record list is the one mk_partition builds on the GPU.
+// The sums land in L2 (dXs is n_src*k*4 B: 30 MB for the Reddit shape, L2-resident); their
+// order is not fixed, exactly as with the reference's RED.E.ADD.F32.
+//
+// Algorithmic bytes per launch:
+//   E*(4 + 4 + k*w + k*4) + N*D*4 + N*k*4 + (N+1)*4 + P*16.
+#include "common.cuh"
+
+namespace mk {
+
+template <typename IdxT>
+__device__ __forceinline__ void load_cols4(const IdxT* p, int (&c)[4]);
+template <>
+__device__ __forceinline__ void load_cols4<uint8_t>(const uint8_t* p, int (&c)[4]) {
+    const uchar4 q = __ldg(reinterpret_cast<const uchar4*>(p));
+    c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w;
+}
+template <>
+__device__ __forceinline__ void load_cols4<uint16_t>(const uint16_t* p, int (&c)[4]) {
+    const ushort4 q = __ldg(reinterpret_cast<const ushort4*>(p));
+    c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w;
+}
+
+template <int K, typename IdxT, int U>
+__global__ void __launch_bounds__(32)
+sspmm_bwd_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
+                 const float* __restrict__ val, const float* __restrict__ dy,
+                 const IdxT* __restrict__ sp_index, float* __restrict__ dxs, int d, int vec_dy) {
+    constexpr int LPN = K / 4;     // lanes per neighbour
+    constexpr int G = 32 / LPN;    // neighbours per warp step
+    static_assert(K % 4 == 0 && (32 % LPN) == 0, "K must be 4, 8, 16, 32, 64 or 128");
+    extern __shared__ __align__(16) float dys[];
+    const int lane = lane_id();
+    const int g = lane / LPN;
+    const int t = lane % LPN;
+    const mk_part rec = parts[blockIdx.x];
+    if (rec.len == 0) return;
+
+    const float* __restrict__ dyr = dy + static_cast<int64_t>(rec.row) * d;
+    if (vec_dy) {
+        for (int c = lane * 4; c < d; c += 128)
+            *reinterpret_cast<float4*>(dys + c) = ld_stream_f4(dyr + c);
+    } else {
+        for (int c = lane; c < d; c += 32) dys[c] = ld_stream_f1(dyr + c);
+    }
+    __syncwarp();
+
+    const int end = rec.loc + rec.len;
+    for (int base = rec.loc; base < end; base += 32) {
+        const int n_here = min(32, end - base);
+        int my_nz = 0;
+        float my_v = 0.f;
+        if (lane < n_here) {
+            my_nz = ld_stream_i1(idx + base + lane);
+            my_v = ld_stream_f1(val + base + lane);
+        }
+        for (int i = 0; i < n_here; i += G * U) {
+            int cv[U][4];
+            int nzv[U];
+            float vv[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = i + u * G + g;
+                nzv[u] = __shfl_sync(kFull, my_nz, e & 31);
+                vv[u] = __shfl_sync(kFull, my_v, e & 31);
+                ok[u] = e < n_here;
+                if (ok[u]) load_cols4<IdxT>(sp_index + static_cast<int64_t>(nzv[u]) * K + 4 * t, cv[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (ok[u]) {
+                    const float v = vv[u];
+                    red_add_f4(dxs + static_cast<int64_t>(nzv[u]) * K + 4 * t, v * dys[cv[u][0]],
+                               v * dys[cv[u][1]], v * dys[cv[u][2]], v * dys[cv[u][3]]);
+                }
+            }
+        }
+    }
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(32)
+sspmm_bwd_generic_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
+                         const float* __restrict__ val, const float* __restrict__ dy,
+                         const IdxT* __restrict__ sp_index, float* __restrict__ dxs, int k, int d) {
+    extern __shared__ __align__(16) float dys[];
+    const int lane = lane_id();
+    const mk_part rec = parts[blockIdx.x];
+    if (rec.len == 0) return;
+    const float* __restrict__ dyr = dy + static_cast<int64_t>(rec.row) * d;
+    for (int c = lane; c < d; c += 32) dys[c] = dyr[c];
+    __syncwarp();
+    const int end = rec.loc + rec.len;
+    for (int e = rec.loc; e < end; ++e) {
+        const int64_t nz = idx[e];
+        const float v = val[e];
+        for (int q = lane; q < k; q += 32) {
+            const int c = static_cast<int>(__ldg(sp_index + nz * k + q));
+            red_add_f1(dxs + nz * k + q, v * dys[c]);
+        }
+    }
+}
+
+template <int K, typename IdxT>
+static int launch_bwd_k(const mk_part* parts, int64_t num_parts, const int* idx, const float* val,
+                        const float* dy, const void* sp_index, float* dxs, int d,
+                        cudaStream_t st) {
+    constexpr int U = 8;
+    const int dpad = (d + 3) & ~3;
+    const size_t smem = static_cast<size_t>(dpad) * 4;
+    if (smem > 200 * 1024) return MK_EUNSUPPORTED;
+    auto kern = sspmm_bwd_kernel<K, IdxT, U>;
+    if (smem > 48 * 1024)
+        MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    const int vec_dy = (d % 4 == 0) && (reinterpret_cast<uintptr_t>(dy) % 16 == 0);
+    kern<<<static_cast<unsigned>(num_parts), 32, smem, st>>>(
+        parts, idx, val, dy, static_cast<const IdxT*>(sp_index), dxs, d, vec_dy);
+    MK_LAUNCH_CHECK("sspmm_bwd_kernel");
+    return MK_OK;
+}
+
+template <typename IdxT>
+static int launch_bwd(const mk_part* parts, int64_t num_parts, const int* idx, const float* val,
+                      const float* dy, const void* sp_index, float* dxs, int k, int d,
+                      cudaStream_t st) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(dxs) % 16 == 0) &&
+                         (reinterpret_cast<uintptr_t>(sp_index) % (4 * sizeof(IdxT)) == 0);
+    if (aligned) {
+        switch (k) {
+            case 4: return launch_bwd_k<4, IdxT>(parts, num_parts, idx, val, dy, sp_index, dxs, d, st);
+            case 8: return launch_bwd_k<8, IdxT>(parts, num_parts, idx, val, dy, sp_index, dxs, d, st);
+            case 16: return launch_bwd_k<16, IdxT>(parts, num_parts, idx, val, dy, sp_index, dxs, d, st);
+            case 32: return launch_bwd_k<32, IdxT>(parts, num_parts, idx, val, dy, sp_index, dxs, d, st);
+            case 64: return launch_bwd_k<64, IdxT>(parts, num_parts, idx, val, dy, sp_index, dxs, d, st);
+            case 128: return launch_bwd_k<128, IdxT>(parts, num_parts, idx, val, dy, sp_index, dxs, d, st);
+            default: break;
+        }
+    }
+    const size_t smem = static_cast<size_t>(d) * 4;
+    if (smem > 200 * 1024) return MK_EUNSUPPORTED;
+    if (smem > 48 * 1024)
+        MK_CUDA_TRY(cudaFuncSetAttribute(sspmm_bwd_generic_kernel<IdxT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    sspmm_bwd_generic_kernel<IdxT><<<static_cast<unsigned>(num_parts), 32, smem, st>>>(
+        parts, idx, val, dy, static_cast<const IdxT*>(sp_index), dxs, k, d);
+    MK_LAUNCH_CHECK("sspmm_bwd_generic_kernel");
+    return MK_OK;
+}
+
+}  // namespace mk
+
+extern "C" int mk_sspmm_bwd(const mk_part* parts, int64_t num_parts, const int32_t* idx,
+                            const float* val, const float* dy, const void* sp_index,
+                            int index_bytes, float* dxs, int64_t n_rows, int64_t n_src, int k,
+                            int d, void* stream) {
+    if (n_rows < 0 || n_src < 0 || num_parts < 0 || d < 1 || k < 1 || k > d) return MK_EINVAL;
+    if (index_bytes != 1 && index_bytes != 2) return MK_EINVAL;
+    if ((index_bytes == 1 && d > 256) || d > 65536) return MK_EINVAL;
+    if (n_src == 0) return MK_OK;
+    if (!dxs) return MK_EINVAL;
+    cudaStream_t st = mk::as_stream(stream);
+    MK_CUDA_TRY(cudaMemsetAsync(dxs, 0, static_cast<size_t>(n_src) * k * sizeof(float), st));
+    if (n_rows == 0 || num_parts == 0) return MK_OK;
+    if (!parts || !dy || !sp_index) return MK_EINVAL;
+    if (num_parts > 0x7fffffffLL) return MK_EUNSUPPORTED;
+    return index_bytes == 1
+               ? mk::launch_bwd<uint8_t>(parts, num_parts, idx, val, dy, sp_index, dxs, k, d, st)
+               : mk::launch_bwd<uint16_t>(parts, num_parts, idx, val, dy, sp_index, dxs, k, d, st);
+}

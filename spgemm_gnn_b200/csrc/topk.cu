@@ -1,0 +1,242 @@
+// a-1  MaxK nonlinearity: exact per-row top-k emitted as CBSR.
+//
+// One warp per row.  The row sits in registers (D <= 1024) as NV4 float4 per lane, turned
+// into order-preserving uint32 keys; the k-th largest key is found by a 32-step bitwise
+// search in which every step is one compare per element plus one REDUX (warp integer
+// reduction), with an early exit as soon as a candidate splits the row into exactly k / D-k.
+// Ties on the threshold are broken towards the lower column with a warp prefix sum.  The
+// kept entries are written in ascending column order.
+//
+// Replaces: maxk_kernel (so@0x21110) -- one thread per row, 8 bisection steps, approximate --
+// and torch.topk + zeros_like + scatter_ + mul (utils/models.py:14-20).
+// HBM traffic: reads N*D*4 once, writes N*k*(4+w).
+#include "common.cuh"
+
+namespace mk {
+
+__device__ __forceinline__ uint32_t order_key(float v) {
+    const uint32_t b = __float_as_uint(v);
+    uint32_t key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    if (b == 0x80000000u) key = 0x80000000u;  // -0.0 ties with +0.0
+    if (v != v) key = 0xFFFFFFFFu;            // every NaN above +inf (torch.topk convention)
+    return key;
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// Column of element (j, i) held by `lane`: j*128 + lane*4 + i.
+template <int NV4, typename IdxT, bool VEC>
+__global__ void __launch_bounds__(256)
+topk_cbsr_reg_kernel(const float* __restrict__ x, int64_t n, int d, int k,
+                     float* __restrict__ sp_data, IdxT* __restrict__ sp_index) {
+    const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;
+    const int lane = lane_id();
+    const float* __restrict__ xr = x + row * d;
+
+    float v[NV4 * 4];
+    uint32_t key[NV4 * 4];
+#pragma unroll
+    for (int j = 0; j < NV4; ++j) {
+        const int c0 = j * 128 + lane * 4;
+        if (VEC && c0 + 3 < d) {
+            const float4 f = ld_stream_f4(xr + c0);
+            v[4 * j + 0] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) key[4 * j + i] = order_key(v[4 * j + i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool in = c0 + i < d;
+                v[4 * j + i] = in ? ld_stream_f1(xr + (in ? c0 + i : 0)) : 0.0f;
+                key[4 * j + i] = in ? order_key(v[4 * j + i]) : 0u;  // below every real key
+            }
+        }
+    }
+
+    // largest T with #{key >= T} >= k
+    uint32_t thr = 0;
+    bool exact = false;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = thr | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int e = 0; e < NV4 * 4; ++e) c += (key[e] >= cand) ? 1 : 0;
+        c = __reduce_add_sync(kFull, c);
+        if (c >= k) {
+            thr = cand;
+            if (c == k) { exact = true; break; }
+        }
+    }
+
+    uint32_t selmask = 0;  // bit e: element e is kept
+    if (exact) {
+#pragma unroll
+        for (int e = 0; e < NV4 * 4; ++e) selmask |= (key[e] >= thr ? 1u : 0u) << e;
+    } else {
+        // more than k keys are >= thr: all keys > thr are kept, the lowest-column ties fill up
+        int gt = 0;
+#pragma unroll
+        for (int e = 0; e < NV4 * 4; ++e) gt += (key[e] > thr) ? 1 : 0;
+        gt = __reduce_add_sync(kFull, gt);
+        const int need = k - gt;
+        int before = 0;
+#pragma unroll
+        for (int j = 0; j < NV4; ++j) {
+            int cnt = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cnt += (key[4 * j + i] == thr) ? 1 : 0;
+            const int incl = warp_incl_scan(cnt, lane);
+            int rank = before + incl - cnt;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int e = 4 * j + i;
+                if (key[e] > thr) {
+                    selmask |= 1u << e;
+                } else if (key[e] == thr) {
+                    if (rank < need) selmask |= 1u << e;
+                    ++rank;
+                }
+            }
+            before += __shfl_sync(kFull, incl, 31);
+        }
+    }
+
+    // ascending-column slot of every kept element
+    float* __restrict__ od = sp_data + row * k;
+    IdxT* __restrict__ oi = sp_index + row * k;
+    int before = 0;
+#pragma unroll
+    for (int j = 0; j < NV4; ++j) {
+        const int cnt = __popc((selmask >> (4 * j)) & 0xFu);
+        const int incl = warp_incl_scan(cnt, lane);
+        int pos = before + incl - cnt;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = 4 * j + i;
+            if ((selmask >> e) & 1u) {
+                od[pos] = v[e];
+                oi[pos] = static_cast<IdxT>(j * 128 + lane * 4 + i);
+                ++pos;
+            }
+        }
+        before += __shfl_sync(kFull, incl, 31);
+    }
+}
+
+// Any D (<= 49152): the keys live in shared memory, same algorithm with strided loops.
+template <typename IdxT>
+__global__ void __launch_bounds__(32)
+topk_cbsr_smem_kernel(const float* __restrict__ x, int64_t n, int d, int k,
+                      float* __restrict__ sp_data, IdxT* __restrict__ sp_index) {
+    extern __shared__ uint32_t skey[];
+    const int lane = lane_id();
+    for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
+        const float* __restrict__ xr = x + row * d;
+        for (int c = lane; c < d; c += 32) skey[c] = order_key(ld_stream_f1(xr + c));
+        __syncwarp();
+        uint32_t thr = 0;
+        bool exact = false;
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t cand = thr | (1u << bit);
+            int c = 0;
+            for (int q = lane; q < d; q += 32) c += (skey[q] >= cand) ? 1 : 0;
+            c = __reduce_add_sync(kFull, c);
+            if (c >= k) {
+                thr = cand;
+                if (c == k) { exact = true; break; }
+            }
+        }
+        int need = 0;
+        if (!exact) {
+            int gt = 0;
+            for (int q = lane; q < d; q += 32) gt += (skey[q] > thr) ? 1 : 0;
+            need = k - __reduce_add_sync(kFull, gt);
+        }
+        float* __restrict__ od = sp_data + row * k;
+        IdxT* __restrict__ oi = sp_index + row * k;
+        int pos = 0, ties = 0;
+        const unsigned lt = (1u << lane) - 1u;
+        for (int base = 0; base < d; base += 32) {
+            const int c = base + lane;
+            const uint32_t kc = c < d ? skey[c] : 0u;
+            bool keep;
+            if (exact) {
+                keep = c < d && kc >= thr;
+            } else {
+                const bool eq = c < d && kc == thr;
+                const unsigned be = __ballot_sync(kFull, eq);
+                const int rank = ties + __popc(be & lt);
+                keep = c < d && (kc > thr || (eq && rank < need));
+                ties += __popc(be);
+            }
+            const unsigned bk = __ballot_sync(kFull, keep);
+            if (keep) {
+                const int p = pos + __popc(bk & lt);
+                od[p] = xr[c];
+                oi[p] = static_cast<IdxT>(c);
+            }
+            pos += __popc(bk);
+        }
+        __syncwarp();
+    }
+}
+
+template <int NV4, typename IdxT>
+static int launch_reg(const float* x, int64_t n, int d, int k, float* sp_data, void* sp_index,
+                      cudaStream_t st) {
+    const int64_t blocks = (n * 32 + 255) / 256;
+    if (blocks > 0x7fffffffLL) return MK_EUNSUPPORTED;
+    const bool vec = (d % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0);
+    if (vec)
+        topk_cbsr_reg_kernel<NV4, IdxT, true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+            x, n, d, k, sp_data, static_cast<IdxT*>(sp_index));
+    else
+        topk_cbsr_reg_kernel<NV4, IdxT, false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+            x, n, d, k, sp_data, static_cast<IdxT*>(sp_index));
+    MK_LAUNCH_CHECK("topk_cbsr_reg_kernel");
+    return MK_OK;
+}
+
+template <typename IdxT>
+static int launch_topk(const float* x, int64_t n, int d, int k, float* sp_data, void* sp_index,
+                       cudaStream_t st) {
+    if (d <= 128) return launch_reg<1, IdxT>(x, n, d, k, sp_data, sp_index, st);
+    if (d <= 256) return launch_reg<2, IdxT>(x, n, d, k, sp_data, sp_index, st);
+    if (d <= 384) return launch_reg<3, IdxT>(x, n, d, k, sp_data, sp_index, st);
+    if (d <= 512) return launch_reg<4, IdxT>(x, n, d, k, sp_data, sp_index, st);
+    if (d <= 768) return launch_reg<6, IdxT>(x, n, d, k, sp_data, sp_index, st);
+    if (d <= 1024) return launch_reg<8, IdxT>(x, n, d, k, sp_data, sp_index, st);
+    if (d > 49152) return MK_EUNSUPPORTED;
+    const size_t smem = static_cast<size_t>(d) * 4;
+    if (smem > 48 * 1024)
+        MK_CUDA_TRY(cudaFuncSetAttribute(topk_cbsr_smem_kernel<IdxT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    const unsigned blocks = static_cast<unsigned>(n < 148 * 32 ? n : 148 * 32);
+    topk_cbsr_smem_kernel<IdxT><<<blocks, 32, smem, st>>>(x, n, d, k, sp_data,
+                                                          static_cast<IdxT*>(sp_index));
+    MK_LAUNCH_CHECK("topk_cbsr_smem_kernel");
+    return MK_OK;
+}
+
+}  // namespace mk
+
+extern "C" int mk_topk_cbsr(const float* x, int64_t n, int d, int k, float* sp_data,
+                            void* sp_index, int index_bytes, void* stream) {
+    if (n < 0 || d < 1 || k < 1 || k > d) return MK_EINVAL;
+    if (index_bytes != 1 && index_bytes != 2) return MK_EINVAL;
+    if ((index_bytes == 1 && d > 256) || d > 65536) return MK_EINVAL;
+    if (n == 0) return MK_OK;
+    if (!x || !sp_data || !sp_index) return MK_EINVAL;
+    cudaStream_t st = mk::as_stream(stream);
+    return index_bytes == 1 ? mk::launch_topk<uint8_t>(x, n, d, k, sp_data, sp_index, st)
+                            : mk::launch_topk<uint16_t>(x, n, d, k, sp_data, sp_index, st);
+}

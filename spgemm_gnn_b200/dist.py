@@ -1,0 +1,148 @@
+"""1-D node/row partition of the aggregation over the GPUs of one box.
+
+The reference is single-GPU (README_INTEGRATED.md:382 lists multi-GPU as future work); this
+module is the B200 answer BASELINE.json asks for.  One process per GPU, `torch.distributed`
+(NCCL over NVLink 5 / NVSwitch; gloo on CPU for the tests):
+
+  * rank p owns the R = ceil(N / P) consecutive rows [p*R, (p+1)*R) of the adjacency (local CSR
+    with GLOBAL column ids) and those nodes' features; equal row counts keep every collective on
+    NCCL's equal-size fast path, and a random node order (the synthetic shapes are random;
+    `random_relabel` does it for others) makes equal rows also nnz-balanced;
+  * forward: MaxK -> CBSR is local; ONE all-gather moves only the compact CBSR table
+    (N*k*(4+w) bytes: 12.8x smaller than dense at k=32, D=256); the SpGEMM then runs locally
+    against the gathered table;
+  * backward: the push-form SSpMM produces contributions to every node's CBSR gradient, folded
+    by ONE reduce-scatter of N*k*4 bytes (the column ids are already resident from the forward);
+  * weights are replicated, their gradients all-reduced in one flat bucket.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch.autograd import Function
+
+from .graph import CSRGraph, ceil_div
+
+
+def rows_per_rank(num_nodes: int, world: int) -> int:
+    return ceil_div(num_nodes, world)
+
+
+def shard_graph(g: CSRGraph, rank: int, world: int) -> Tuple[CSRGraph, int, int]:
+    """Rank's row block of `g`, padded to R rows with empty rows; columns stay global and the
+    column space is padded to world*R so that gathered tables index directly by global id."""
+    n = g.num_nodes()
+    r = rows_per_rank(n, world)
+    r0, r1 = min(rank * r, n), min((rank + 1) * r, n)
+    s = g.row_slice(r0, r1)
+    ptr = s.indptr
+    if r1 - r0 < r:  # pad with empty rows
+        pad = ptr[-1:].expand(r - (r1 - r0))
+        ptr = torch.cat([ptr, pad]).contiguous()
+    local = CSRGraph(ptr, s.indices, num_src=world * r)
+    local._cache["symmetric"] = False
+    return local, r0, r1
+
+
+def shard_edge_weights(g: CSRGraph, local: CSRGraph, r0: int, r1: int, kind: str) -> torch.Tensor:
+    """Per-edge weights of the rank's rows, computed from GLOBAL degrees."""
+    lo, hi = int(g.indptr[r0]), int(g.indptr[r1])
+    return g.edge_weights(kind)[lo:hi].contiguous()
+
+
+def random_relabel(g: CSRGraph, seed: int = 97) -> Tuple[CSRGraph, torch.Tensor]:
+    """Random node permutation (new = perm[old]) so that equal-row shards are nnz-balanced."""
+    from .graph import from_edges
+    n = g.num_nodes()
+    gen = torch.Generator(device=g.device).manual_seed(seed)
+    perm = torch.randperm(n, generator=gen, device=g.device)
+    rows = perm[g.row_ids()]
+    cols = perm[g.indices.to(torch.int64)]
+    return from_edges(rows, cols, n, symmetric=g._cache.get("symmetric", False)), perm
+
+
+# ---------------------------------------------------------------------------------------
+# the two exchanges
+# ---------------------------------------------------------------------------------------
+def _backend(group) -> str:
+    return dist.get_backend(group)
+
+
+def allgather_cbsr(sp_data: torch.Tensor, sp_index: torch.Tensor, group=None):
+    """[R,k] local CBSR -> [P*R,k] table, rows ordered by owner rank == global node id."""
+    world = dist.get_world_size(group)
+    r, k = sp_data.shape
+    full_data = torch.empty((world * r, k), dtype=sp_data.dtype, device=sp_data.device)
+    full_index = torch.empty((world * r, k), dtype=sp_index.dtype, device=sp_index.device)
+    dist.all_gather_into_tensor(full_data, sp_data.contiguous(), group=group)
+    # column ids travel as raw bytes (uint16 has no NCCL dtype in every torch build)
+    dist.all_gather_into_tensor(full_index.view(torch.uint8), sp_index.contiguous().view(torch.uint8),
+                                group=group)
+    return full_data, full_index
+
+
+def reduce_scatter_rows(full: torch.Tensor, group=None) -> torch.Tensor:
+    """[P*R,k] per-rank partial sums -> [R,k] summed rows of this rank."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    r = full.shape[0] // world
+    if _backend(group) == "gloo":  # gloo has no reduce_scatter: all-reduce and slice
+        buf = full.clone()
+        dist.all_reduce(buf, group=group)
+        return buf[rank * r:(rank + 1) * r].contiguous()
+    out = torch.empty((r, full.shape[1]), dtype=full.dtype, device=full.device)
+    dist.reduce_scatter_tensor(out, full.contiguous(), group=group)
+    return out
+
+
+def allreduce_grads(params: Iterable[torch.nn.Parameter], group=None) -> None:
+    """Sum the (small, replicated) weight gradients in one flat bucket."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+# ---------------------------------------------------------------------------------------
+# the sharded hot path as an autograd Function
+# ---------------------------------------------------------------------------------------
+class DistSpGEMMFunction(Function):
+    """Local rows of A x Xs where Xs is row-sharded: all-gather(CBSR) -> spgemm_forward;
+    backward: spgemm_backward against the gathered column ids -> reduce-scatter."""
+
+    @staticmethod
+    def forward(ctx, sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, group):
+        from . import maxk_kernels
+        full_data, full_index = allgather_cbsr(sp_data, sp_index, group)
+        k = sp_data.shape[1]
+        out, _ = maxk_kernels.spgemm_forward(ptr, idx, val, full_data, full_index, num_rows,
+                                             idx.numel(), k, dim_origin)
+        ctx.save_for_backward(full_index, ptr, idx, val)
+        ctx.meta = (num_rows, k, dim_origin, group)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from . import maxk_kernels
+        full_index, ptr, idx, val = ctx.saved_tensors
+        num_rows, k, dim_origin, group = ctx.meta
+        dxs_full = maxk_kernels.spgemm_backward(ptr, idx, val, grad_out.contiguous(), full_index,
+                                                num_rows, idx.numel(), k, dim_origin)
+        return reduce_scatter_rows(dxs_full, group), None, None, None, None, None, None, None
+
+
+def dist_maxk_aggregate(local: CSRGraph, val: torch.Tensor, feat: torch.Tensor, k: int,
+                        group=None) -> torch.Tensor:
+    """Sharded MaxK -> CBSR -> all-gather -> SpGEMM for the rank's (padded) rows."""
+    from .maxk_layers import MaxKCBSRFunction
+    sp_data, sp_index = MaxKCBSRFunction.apply(feat, k)
+    return DistSpGEMMFunction.apply(sp_data, sp_index, local.indptr, local.indices, val,
+                                    local.num_nodes(), feat.shape[1], group)

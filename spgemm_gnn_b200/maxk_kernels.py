@@ -1,0 +1,294 @@
+"""`maxk_kernels` -- the reference's PyTorch-extension entry points, kept name for name and
+argument for argument (positional), as a thin shim over the C ABI of libmaxk_b200.so.
+
+Reference surface (pybind module `maxk_kernels`, kernels/maxk_bindings.cpp -- source absent,
+signatures and TORCH_CHECK strings recovered from the shipped binary):
+
+    maxk_forward(input, k) -> Tensor
+    maxk_backward(grad_output, indices) -> Tensor
+    spgemm_forward(ptr, idx, val, sp_data, sp_index, num_nodes, num_edges, dim_sparse, dim_origin)
+        -> (Tensor, Tensor)
+    spgemm_backward(ptr, idx, val, grad_output, sp_index, num_nodes, num_edges, dim_sparse, dim_origin)
+        -> Tensor
+
+Additions (new names, existing ones untouched): `maxk_forward_cbsr`, `cbsr_scatter`,
+`cbsr_gather`, `partition`, `clear_partition_cache`, `set_max_nz`.
+
+Everything launches on torch's current CUDA stream; nothing synchronises the device except
+the one-off partition size query per graph.  No CPU path exists.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import weakref
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+__all__ = [
+    "maxk_forward", "maxk_backward", "spgemm_forward", "spgemm_backward",
+    "maxk_forward_cbsr", "cbsr_scatter", "cbsr_gather", "partition",
+    "clear_partition_cache", "set_max_nz", "get_max_nz", "launch_count",
+]
+
+_MAX_NZ = int(os.environ.get("MAXK_MAX_NZ", "1024"))
+_launches = 0  # kernels launched through this module (bench.py reports it)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def set_max_nz(max_nz: int) -> None:
+    """Stored entries per work record (the reference hard-wires WARP_MAX_NZ=64,
+    README_INTEGRATED.md:256)."""
+    global _MAX_NZ
+    if max_nz < 1:
+        raise ValueError("max_nz must be positive")
+    _MAX_NZ = int(max_nz)
+
+
+def get_max_nz() -> int:
+    return _MAX_NZ
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(cond: bool, msg: str) -> None:
+    # TORCH_CHECK -> RuntimeError, messages as in the reference binary
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _cuda_contig(t: torch.Tensor, name: str) -> None:
+    _chk(isinstance(t, torch.Tensor) and t.is_cuda, f"{name} must be a CUDA tensor")
+    _chk(t.is_contiguous(), f"{name} must be contiguous")
+
+
+def _index_bytes(sp_index: torch.Tensor, dim_origin: int) -> int:
+    if sp_index.dtype == torch.uint8:
+        _chk(dim_origin <= 256, "sp_index must be uint16 when dim_origin > 256")
+        return 1
+    if sp_index.dtype in (torch.uint16, torch.int16):
+        return 2
+    raise RuntimeError("sp_index must be uint8 or uint16")
+
+
+def _index_dtype(dim_origin: int) -> torch.dtype:
+    return torch.uint8 if dim_origin <= 256 else torch.uint16
+
+
+# ---------------------------------------------------------------------------------------
+# MaxK
+# ---------------------------------------------------------------------------------------
+def maxk_forward_cbsr(input: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exact top-k per row as CBSR: (sp_data fp32 [N,k], sp_index uint8|uint16 [N,k]),
+    ascending columns, ties to the lower column.  The native `maxk_forward` of the
+    reference computes both and throws the index away (maxk_cuda_kernels.o@0x31d-0x3a5)."""
+    global _launches
+    _cuda_contig(input, "input")
+    _chk(input.dim() == 2, "Input must be 2D tensor")
+    _chk(input.dtype == torch.float32, "input must be float32")
+    n, d = input.shape
+    _chk(1 <= k <= d, "k must be between 1 and input dimension")
+    _chk(d <= 65536, "input dimension above 65536 is not supported")
+    sp_data = torch.empty((n, k), dtype=torch.float32, device=input.device)
+    sp_index = torch.empty((n, k), dtype=_index_dtype(d), device=input.device)
+    with torch.cuda.device(input.device):
+        rc = _lib.lib().mk_topk_cbsr(input.data_ptr(), n, d, k, sp_data.data_ptr(),
+                                     sp_index.data_ptr(), sp_index.element_size(), _stream())
+    _lib.check(rc, "mk_topk_cbsr")
+    _launches += 1
+    return sp_data, sp_index
+
+
+def maxk_forward(input: torch.Tensor, k: int) -> torch.Tensor:
+    """Reference signature `(Tensor input, int k) -> Tensor`: the [N,k] CBSR values
+    (SURVEY.md section 2.2).  Use `maxk_forward_cbsr` to get the column ids as well."""
+    return maxk_forward_cbsr(input, k)[0]
+
+
+def cbsr_scatter(grad: torch.Tensor, sp_index: torch.Tensor, dim_origin: int) -> torch.Tensor:
+    """dense [N, dim_origin]: zeros with dense[i, sp_index[i,t]] = grad[i,t]."""
+    global _launches
+    _cuda_contig(grad, "grad_output")
+    _cuda_contig(sp_index, "indices")
+    _chk(grad.dim() == 2, "grad_output must be 2D tensor")
+    _chk(grad.dtype == torch.float32, "grad_output must be float32")
+    _chk(sp_index.shape == grad.shape, "indices must have the shape of grad_output")
+    n, k = grad.shape
+    _chk(1 <= k <= dim_origin, "k must be between 1 and input dimension")
+    ib = _index_bytes(sp_index, dim_origin)
+    out = torch.empty((n, dim_origin), dtype=torch.float32, device=grad.device)
+    with torch.cuda.device(grad.device):
+        rc = _lib.lib().mk_cbsr_scatter(grad.data_ptr(), sp_index.data_ptr(), ib, out.data_ptr(),
+                                        n, k, dim_origin, _stream())
+    _lib.check(rc, "mk_cbsr_scatter")
+    _launches += 1
+    return out
+
+
+def cbsr_gather(dense: torch.Tensor, sp_index: torch.Tensor) -> torch.Tensor:
+    """[N,k]: dense[i, sp_index[i,t]]."""
+    global _launches
+    _cuda_contig(dense, "input")
+    _cuda_contig(sp_index, "indices")
+    _chk(dense.dim() == 2 and sp_index.dim() == 2, "Input must be 2D tensor")
+    _chk(dense.dtype == torch.float32, "input must be float32")
+    n, d = dense.shape
+    k = sp_index.shape[1]
+    _chk(sp_index.shape[0] == n and 1 <= k <= d, "k must be between 1 and input dimension")
+    ib = _index_bytes(sp_index, d)
+    out = torch.empty((n, k), dtype=torch.float32, device=dense.device)
+    with torch.cuda.device(dense.device):
+        rc = _lib.lib().mk_cbsr_gather(dense.data_ptr(), sp_index.data_ptr(), ib, out.data_ptr(),
+                                       n, k, d, _stream())
+    _lib.check(rc, "mk_cbsr_gather")
+    _launches += 1
+    return out
+
+
+def maxk_backward(grad_output: torch.Tensor, indices: torch.Tensor,
+                  dim_origin: Optional[int] = None) -> torch.Tensor:
+    """Reference signature `(Tensor grad_output, Tensor indices) -> Tensor`: scatter a
+    CBSR-shaped gradient [N,k] to dense [N,D] (maxk_backward_cuda, maxk_cuda_kernels.o@0x4d0).
+    Like the reference, D defaults to `indices.max()+1` (a device sync); pass `dim_origin`
+    to avoid it.  int64 `indices` (what utils/maxk_layers.py:23 saves from torch.topk) are
+    accepted and narrowed."""
+    _cuda_contig(grad_output, "grad_output")
+    _cuda_contig(indices, "indices")
+    _chk(grad_output.dim() == 2, "grad_output must be 2D tensor")
+    if dim_origin is None:
+        dim_origin = int(indices.max().item()) + 1 if indices.numel() else 1
+        dim_origin = max(dim_origin, grad_output.shape[1])
+    if indices.dtype not in (torch.uint8, torch.uint16, torch.int16):
+        if dim_origin <= 256:
+            indices = indices.to(torch.uint8)
+        else:  # narrow through int16: same bits as uint16, and every torch build can cast to it
+            indices = indices.to(torch.int16).view(torch.uint16)
+    return cbsr_scatter(grad_output, indices, dim_origin)
+
+
+# ---------------------------------------------------------------------------------------
+# work partition cache (per graph)
+# ---------------------------------------------------------------------------------------
+class _Partition:
+    __slots__ = ("parts", "num_parts", "num_slots", "max_nz", "partial", "ptr_ref", "version")
+
+    def partial_for(self, d: int, device) -> Optional[torch.Tensor]:
+        if self.num_slots == 0:
+            return None
+        if self.partial is None or self.partial.shape[1] != d:
+            self.partial = torch.empty((self.num_slots, d), dtype=torch.float32, device=device)
+        return self.partial
+
+
+_part_cache = {}
+
+
+def clear_partition_cache() -> None:
+    _part_cache.clear()
+
+
+def partition(ptr: torch.Tensor, num_nodes: int, max_nz: Optional[int] = None) -> _Partition:
+    """Work records of a CSR row pointer, built on the GPU once per graph and cached on
+    `(ptr.data_ptr(), num_nodes, max_nz)` -- replaces generate_meta.py + the `.warp4` file."""
+    global _launches
+    max_nz = _MAX_NZ if max_nz is None else int(max_nz)
+    key = (ptr.device.index, ptr.data_ptr(), int(num_nodes), max_nz)
+    hit = _part_cache.get(key)
+    if hit is not None and hit.ptr_ref() is ptr and hit.version == ptr._version:
+        return hit
+    _chk(ptr.numel() >= num_nodes + 1, "ptr must have num_nodes + 1 entries")
+    L = _lib.lib()
+    np_, ns_ = ctypes.c_int64(0), ctypes.c_int64(0)
+    with torch.cuda.device(ptr.device):
+        rc = L.mk_partition(ptr.data_ptr(), num_nodes, max_nz, None, ctypes.byref(np_),
+                            ctypes.byref(ns_), _stream())
+        _lib.check(rc, "mk_partition")
+        p = _Partition()
+        p.num_parts, p.num_slots, p.max_nz = int(np_.value), int(ns_.value), max_nz
+        p.parts = torch.empty((max(p.num_parts, 1), 4), dtype=torch.int32, device=ptr.device)
+        p.partial = None
+        rc = L.mk_partition(ptr.data_ptr(), num_nodes, max_nz, p.parts.data_ptr(), None, None,
+                            _stream())
+        _lib.check(rc, "mk_partition")
+    _launches += 5
+    p.ptr_ref = weakref.ref(ptr)
+    p.version = ptr._version
+    if len(_part_cache) > 64:
+        _part_cache.clear()
+    _part_cache[key] = p
+    return p
+
+
+# ---------------------------------------------------------------------------------------
+# SpGEMM forward / SSpMM backward
+# ---------------------------------------------------------------------------------------
+def _check_graph(ptr, idx, val):
+    _cuda_contig(ptr, "ptr")
+    _cuda_contig(idx, "idx")
+    _cuda_contig(val, "val")
+    _chk(ptr.dtype == torch.int32, "ptr must be int32")
+    _chk(idx.dtype == torch.int32, "idx must be int32")
+    _chk(val.dtype == torch.float32, "val must be float32")
+
+
+def spgemm_forward(ptr, idx, val, sp_data, sp_index, num_nodes, num_edges, dim_sparse, dim_origin):
+    """out[r, sp_index[j,t]] += val[e] * sp_data[j,t] over the stored entries e=(r<-j) of the
+    CSR (ptr, idx, val).  Returns `(out fp32 [num_nodes, dim_origin], sp_index)` like the
+    reference (spgemm_forward_cuda, maxk_cuda_kernels.o@0x1260)."""
+    global _launches
+    _check_graph(ptr, idx, val)
+    _cuda_contig(sp_data, "sp_data")
+    _cuda_contig(sp_index, "sp_index")
+    _chk(sp_data.dtype == torch.float32, "sp_data must be float32")
+    _chk(sp_data.dim() == 2 and sp_index.shape == sp_data.shape, "sp_index must have the shape of sp_data")
+    _chk(sp_data.shape[1] == dim_sparse, "dim_sparse must equal sp_data.size(1)")
+    _chk(1 <= dim_sparse <= dim_origin, "k must be between 1 and input dimension")
+    _chk(idx.numel() >= num_edges and val.numel() >= num_edges, "idx/val must hold num_edges entries")
+    ib = _index_bytes(sp_index, dim_origin)
+    part = partition(ptr, num_nodes)
+    out = torch.empty((num_nodes, dim_origin), dtype=torch.float32, device=sp_data.device)
+    partial = part.partial_for(dim_origin, sp_data.device)
+    with torch.cuda.device(sp_data.device):
+        rc = _lib.lib().mk_spgemm_fwd(
+            part.parts.data_ptr(), part.num_parts, part.num_slots, idx.data_ptr(), val.data_ptr(),
+            sp_data.data_ptr(), sp_index.data_ptr(), ib, out.data_ptr(),
+            partial.data_ptr() if partial is not None else None, num_nodes, dim_sparse, dim_origin,
+            _stream())
+    _lib.check(rc, "mk_spgemm_fwd")
+    _launches += 1 + (1 if part.num_slots else 0)
+    return out, sp_index
+
+
+def spgemm_backward(ptr, idx, val, grad_output, sp_index, num_nodes, num_edges, dim_sparse, dim_origin):
+    """dXs[j,t] = sum over stored e=(r<-j) of val[e] * grad_output[r, sp_index[j,t]]; fp32
+    [sp_index.size(0), dim_sparse] (spgemm_backward_cuda, maxk_cuda_kernels.o@0x1550)."""
+    global _launches
+    _check_graph(ptr, idx, val)
+    _cuda_contig(grad_output, "grad_output")
+    _cuda_contig(sp_index, "sp_index")
+    _chk(grad_output.dtype == torch.float32, "grad_output must be float32")
+    _chk(grad_output.dim() == 2, "grad_output must be 2D tensor")
+    _chk(grad_output.shape[0] == num_nodes and grad_output.shape[1] == dim_origin,
+         "grad_output must be [num_nodes, dim_origin]")
+    _chk(sp_index.dim() == 2 and sp_index.shape[1] == dim_sparse, "dim_sparse must equal sp_index.size(1)")
+    _chk(1 <= dim_sparse <= dim_origin, "k must be between 1 and input dimension")
+    ib = _index_bytes(sp_index, dim_origin)
+    n_src = sp_index.shape[0]
+    part = partition(ptr, num_nodes)
+    dxs = torch.empty((n_src, dim_sparse), dtype=torch.float32, device=grad_output.device)
+    with torch.cuda.device(grad_output.device):
+        rc = _lib.lib().mk_sspmm_bwd(
+            part.parts.data_ptr(), part.num_parts, idx.data_ptr(), val.data_ptr(),
+            grad_output.data_ptr(), sp_index.data_ptr(), ib, dxs.data_ptr(), num_nodes, n_src,
+            dim_sparse, dim_origin, _stream())
+    _lib.check(rc, "mk_sspmm_bwd")
+    _launches += 2  # memset + kernel
+    return dxs

@@ -1,0 +1,237 @@
+"""Autograd Functions and conv layers of the reference's `utils/maxk_layers.py`, bodies
+rewritten over the B200 kernels; class names, constructor arguments and call signatures kept.
+
+What changed underneath:
+  * CBSR (values + column ids) flows from the MaxK kernel straight into the SpGEMM kernel --
+    no dense masked intermediate, no per-row Python `_extract_sparse_format` loop
+    (utils/maxk_layers.py:224-265), no per-node `.item()` loop for the mean weights (:150-157);
+  * the aggregation is an autograd Function whose backward IS `spgemm_backward` (the reference
+    never calls it: its SpGEMM output is detached from autograd, utils/maxk_layers.py:166-171);
+  * there is no DGL fallback and no CPU fallback: without the CUDA library every call raises.
+
+`graph` is a `spgemm_gnn_b200.graph.CSRGraph` (destination-indexed CSR); DGL is not needed.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import maxk_kernels
+from .graph import CSRGraph
+
+KERNELS_AVAILABLE = True  # kept for callers that test it (maxk_gnn_integrated.py:24-31)
+
+
+# ---------------------------------------------------------------------------------------
+# autograd Functions
+# ---------------------------------------------------------------------------------------
+class MaxKFunction(Function):
+    """`MaxKFunction.apply(input, k)` -> dense [N,D] with everything but the k largest entries
+    of each row zeroed (utils/maxk_layers.py:16-45, same contract as utils/models.py::MaxK).
+    forward = top-k -> CBSR -> scatter; backward = gather at the kept columns -> scatter
+    (== grad * mask, without ever storing the N x D mask)."""
+
+    @staticmethod
+    def forward(ctx, input, k=32):
+        x = input.contiguous()
+        sp_data, sp_index = maxk_kernels.maxk_forward_cbsr(x, k)
+        ctx.save_for_backward(sp_index)
+        ctx.dim_origin = x.shape[1]
+        return maxk_kernels.cbsr_scatter(sp_data, sp_index, x.shape[1])
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (sp_index,) = ctx.saved_tensors
+        g = maxk_kernels.cbsr_gather(grad_output.contiguous(), sp_index)
+        return maxk_kernels.cbsr_scatter(g, sp_index, ctx.dim_origin), None
+
+
+class MaxKCBSRFunction(Function):
+    """x [N,D] -> (sp_data [N,k], sp_index [N,k]).  backward: CBSR gradient -> dense."""
+
+    @staticmethod
+    def forward(ctx, input, k):
+        x = input.contiguous()
+        sp_data, sp_index = maxk_kernels.maxk_forward_cbsr(x, k)
+        ctx.save_for_backward(sp_index)
+        ctx.dim_origin = x.shape[1]
+        ctx.mark_non_differentiable(sp_index)
+        return sp_data, sp_index
+
+    @staticmethod
+    def backward(ctx, grad_data, _grad_index):
+        (sp_index,) = ctx.saved_tensors
+        return maxk_kernels.cbsr_scatter(grad_data.contiguous(), sp_index, ctx.dim_origin), None
+
+
+class CBSRToDenseFunction(Function):
+    """(sp_data, sp_index) -> dense masked [N,D]; backward gathers at the kept columns."""
+
+    @staticmethod
+    def forward(ctx, sp_data, sp_index, dim_origin):
+        ctx.save_for_backward(sp_index)
+        return maxk_kernels.cbsr_scatter(sp_data.contiguous(), sp_index, dim_origin)
+
+    @staticmethod
+    def backward(ctx, grad_dense):
+        (sp_index,) = ctx.saved_tensors
+        return maxk_kernels.cbsr_gather(grad_dense.contiguous(), sp_index), None, None
+
+
+class SpGEMMFunction(Function):
+    """out = A x Xs with A = CSR(ptr, idx, val) and Xs = CBSR(sp_data, sp_index).
+    forward = `spgemm_forward`, backward (w.r.t. sp_data) = `spgemm_backward`."""
+
+    @staticmethod
+    def forward(ctx, sp_data, sp_index, ptr, idx, val, num_nodes, dim_origin):
+        sp_data = sp_data.contiguous()
+        k = sp_data.shape[1]
+        out, _ = maxk_kernels.spgemm_forward(ptr, idx, val, sp_data, sp_index, num_nodes,
+                                             idx.numel(), k, dim_origin)
+        ctx.save_for_backward(sp_index, ptr, idx, val)
+        ctx.meta = (num_nodes, k, dim_origin)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        sp_index, ptr, idx, val = ctx.saved_tensors
+        num_nodes, k, dim_origin = ctx.meta
+        dxs = maxk_kernels.spgemm_backward(ptr, idx, val, grad_out.contiguous(), sp_index,
+                                           num_nodes, idx.numel(), k, dim_origin)
+        return dxs, None, None, None, None, None, None
+
+
+def maxk_aggregate(graph: CSRGraph, feat: torch.Tensor, k: int, weight_kind: str) -> torch.Tensor:
+    """MaxK -> CBSR -> SpGEMM in one go: sum_j w(i<-j) * maxk(feat)[j].  The hot path."""
+    sp_data, sp_index = MaxKCBSRFunction.apply(feat, k)
+    return SpGEMMFunction.apply(sp_data, sp_index, graph.indptr, graph.indices,
+                                graph.edge_weights(weight_kind), graph.num_nodes(), feat.shape[1])
+
+
+def _dense_aggregate(graph: CSRGraph, feat: torch.Tensor, weight_kind: str) -> torch.Tensor:
+    """Non-MaxK (`--nonlinear relu`) branch: dense SpMM through cuSPARSE, the comparator the
+    reference reports its speed-ups against (README.md:136).  Not the hot path."""
+    key = ("adj", weight_kind)
+    adj = graph._cache.get(key)
+    if adj is None:
+        adj = torch.sparse_csr_tensor(graph.indptr.to(torch.int64), graph.indices.to(torch.int64),
+                                      graph.edge_weights(weight_kind),
+                                      size=(graph.num_nodes(), graph.num_src))
+        graph._cache[key] = adj
+    return torch.sparse.mm(adj, feat)
+
+
+# ---------------------------------------------------------------------------------------
+# layers (utils/maxk_layers.py:47-265, 267-447; utils/integrated_models.py:221-270)
+# ---------------------------------------------------------------------------------------
+class MaxKSAGEConv(nn.Module):
+    """h_self + aggregate(MaxK(fc_neigh(feat))), then norm and dropout
+    (utils/maxk_layers.py:82-99, 161-184)."""
+
+    def __init__(self, in_feats, out_feats, aggregator_type="mean", feat_drop=0.0, norm=None, maxk=32):
+        super().__init__()
+        if aggregator_type not in ("mean", "sum"):
+            raise ValueError(f"Unsupported aggregator type: {aggregator_type}")
+        self.in_feats = in_feats
+        self.out_feats = out_feats
+        self.aggregator_type = aggregator_type
+        self.maxk = maxk
+        self.fc_self = nn.Linear(in_feats, out_feats, bias=False)
+        self.fc_neigh = nn.Linear(in_feats, out_feats, bias=False)
+        self.norm = norm
+        if norm is not None and isinstance(norm, type):
+            self.norm = norm(out_feats)
+        self.feat_drop = nn.Dropout(feat_drop)
+        self.maxk_fn = MaxKFunction.apply
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        gain = nn.init.calculate_gain("relu")
+        nn.init.xavier_uniform_(self.fc_self.weight, gain=gain)
+        nn.init.xavier_uniform_(self.fc_neigh.weight, gain=gain)
+
+    def forward(self, graph, feat):
+        h_self = self.fc_self(feat)
+        h_neigh = self.fc_neigh(feat)
+        agg = maxk_aggregate(graph, h_neigh, self.maxk, self.aggregator_type)
+        output = h_self + agg
+        if self.norm is not None:
+            output = self.norm(output)
+        return self.feat_drop(output)
+
+
+class MaxKGCNConv(nn.Module):
+    """D_in^-1/2 A D_out^-1/2 MaxK(feat W) + b (utils/maxk_layers.py:300-324, 370-390); both
+    normalisations are folded into the per-edge weights once per graph."""
+
+    def __init__(self, in_feats, out_feats, norm="both", weight=True, bias=True,
+                 allow_zero_in_degree=False, maxk=32):
+        super().__init__()
+        if norm not in ("none", "both", "right"):
+            raise ValueError(f"Unsupported norm: {norm}")
+        self.in_feats = in_feats
+        self.out_feats = out_feats
+        self.norm = norm
+        self.maxk = maxk
+        self.allow_zero_in_degree = allow_zero_in_degree
+        if weight:
+            self.weight = nn.Parameter(torch.empty(in_feats, out_feats))
+        else:
+            self.register_parameter("weight", None)
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_feats))
+        else:
+            self.register_parameter("bias", None)
+        self.maxk_fn = MaxKFunction.apply
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        if self.weight is not None:
+            nn.init.xavier_uniform_(self.weight)
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    def forward(self, graph, feat):
+        if not self.allow_zero_in_degree:
+            zero = graph._cache.get("has_zero_in")
+            if zero is None:
+                zero = bool((graph.in_degrees() == 0).any())
+                graph._cache["has_zero_in"] = zero
+            if zero:
+                raise ValueError("Graph has nodes with zero in-degree")
+        if self.weight is not None:
+            feat = torch.mm(feat, self.weight)
+        output = maxk_aggregate(graph, feat, self.maxk, self.norm)
+        if self.bias is not None:
+            output = output + self.bias
+        return output
+
+
+class MaxKGINConv(nn.Module):
+    """mlp((1 + eps) * feat + sum_j MaxK(feat)[j]) (utils/integrated_models.py:221-270, where
+    the sum is a DGL `update_all(copy_u, sum)` on the dense masked features)."""
+
+    def __init__(self, in_feats, out_feats, learn_eps=True, maxk=32):
+        super().__init__()
+        self.in_feats = in_feats
+        self.out_feats = out_feats
+        self.maxk = maxk
+        if learn_eps:
+            self.eps = nn.Parameter(torch.zeros(1))
+        else:
+            self.register_buffer("eps", torch.zeros(1))
+        self.mlp = nn.Sequential(nn.Linear(in_feats, out_feats), nn.ReLU(),
+                                 nn.Linear(out_feats, out_feats))
+        self.maxk_fn = MaxKFunction.apply
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for layer in self.mlp:
+            if isinstance(layer, nn.Linear):
+                nn.init.xavier_uniform_(layer.weight)
+
+    def forward(self, graph, feat):
+        neigh = maxk_aggregate(graph, feat, self.maxk, "sum")
+        output = (1 + self.eps) * feat + neigh
+        return self.mlp(output)

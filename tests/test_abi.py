@@ -1,0 +1,95 @@
+"""The C-ABI library loads and exports exactly what include/maxk_b200.h declares (no GPU)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+from spgemm_gnn_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "maxk_b200.h")).read()
+    return sorted(set(re.findall(r"MK_API\s+[\w\s\*]+?\b(mk_\w+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound(built_lib):
+    names = _declared()
+    assert len(names) >= 10
+    assert sorted(_lib.SIGNATURES) == names          # the ctypes table covers the header
+    L = ctypes.CDLL(built_lib)
+    for n in names:
+        assert hasattr(L, n), n
+    out = subprocess.check_output(["nm", "-D", "--defined-only", built_lib]).decode()
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l)
+    assert exported == names                          # and nothing else leaks out
+
+
+def test_library_is_sm100a_and_has_no_torch_dependency(built_lib):
+    out = subprocess.check_output(["cuobjdump", "-lelf", built_lib]).decode()
+    assert "sm_100a" in out and "sm_80" not in out
+    dyn = subprocess.check_output(["readelf", "-d", built_lib]).decode()
+    needed = " ".join(l for l in dyn.splitlines() if "NEEDED" in l)
+    assert "torch" not in needed and "c10" not in needed and "libcudart" not in needed
+
+
+def test_version_and_error_strings(built_lib):
+    L = _lib.lib()
+    assert L.mk_version() == 100
+    assert L.mk_error_string(0) == b"ok"
+    assert L.mk_error_string(-1) == b"invalid argument"
+    assert b"CUDA" in L.mk_error_string(-3)
+
+
+def test_argument_validation_without_a_device(built_lib):
+    """Bad arguments are rejected before any CUDA call, so this runs on the CPU box."""
+    L = _lib.lib()
+    assert L.mk_topk_cbsr(None, 4, 16, 0, None, None, 1, None) == _lib.MK_EINVAL      # k < 1
+    assert L.mk_topk_cbsr(None, 4, 16, 17, None, None, 1, None) == _lib.MK_EINVAL     # k > d
+    assert L.mk_topk_cbsr(None, 4, 300, 8, None, None, 1, None) == _lib.MK_EINVAL     # u8 with d>256
+    assert L.mk_topk_cbsr(None, 4, 16, 8, None, None, 3, None) == _lib.MK_EINVAL      # index_bytes
+    assert L.mk_topk_cbsr(None, 0, 16, 8, None, None, 1, None) == _lib.MK_OK          # empty
+    assert L.mk_spgemm_fwd(None, 0, 0, None, None, None, None, 1, None, None, 0, 8, 16, None) == _lib.MK_OK
+    assert L.mk_spgemm_fwd(None, 5, 0, None, None, None, None, 1, None, None, 5, 8, 4, None) == _lib.MK_EINVAL
+    assert L.mk_partition(None, -1, 64, None, None, None, None) == _lib.MK_EINVAL
+    assert L.mk_partition(None, 10, 0, None, None, None, None) == _lib.MK_EINVAL
+
+
+def test_entry_points_refuse_cpu_tensors(built_lib):
+    """TORCH_CHECK messages of the reference binding."""
+    import maxk_kernels as mk
+    x = torch.randn(4, 16)
+    with pytest.raises(RuntimeError, match="input must be a CUDA tensor"):
+        mk.maxk_forward(x, 4)
+    with pytest.raises(RuntimeError, match="grad_output must be a CUDA tensor"):
+        mk.maxk_backward(x, torch.zeros(4, 16, dtype=torch.uint8))
+    ptr = torch.zeros(5, dtype=torch.int32)
+    with pytest.raises(RuntimeError, match="ptr must be a CUDA tensor"):
+        mk.spgemm_forward(ptr, ptr, x, x, x, 4, 0, 4, 16)
+    with pytest.raises(RuntimeError, match="ptr must be a CUDA tensor"):
+        mk.spgemm_backward(ptr, ptr, x, x, x, 4, 0, 4, 16)
+    assert mk.__all__[:4] == ["maxk_forward", "maxk_backward", "spgemm_forward", "spgemm_backward"]
+
+
+def test_product_never_imports_the_oracle():
+    """The shipped path must not route through oracle/ (checked textually)."""
+    bad = []
+    for base in ("spgemm_gnn_b200", "."):
+        d = os.path.join(ROOT, base)
+        for f in os.listdir(d):
+            if f.endswith(".py") and f not in ("bench.py", "__graft_entry__.py"):
+                src = open(os.path.join(d, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M):
+                    bad.append(os.path.join(base, f))
+    assert not bad, bad
+
+
+def test_missing_library_is_loud(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "SO_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.MaxKLibraryError, match="no CPU fallback"):
+        _lib.lib()

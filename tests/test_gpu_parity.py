@@ -1,0 +1,368 @@
+"""Parity of the CUDA path (through `maxk_kernels` -> ctypes -> C ABI) with the CPU oracle.
+
+Bars (BASELINE.json north_star): column ids and CBSR layout bit-exact; SpGEMM / SSpMM values
+within 1e-5 relative, measured against sum|terms| of each output element (the fp32 sums are
+formed in a different order than the float64 oracle's; SURVEY.md section 7 'fp32 tolerance').
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def mk():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import maxk_kernels
+    from spgemm_gnn_b200 import _lib
+    assert _lib.lib().mk_device_ok() == 0, "not an sm_100 device"
+    return maxk_kernels
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def assert_rel(got, want64, bound, what):
+    got = got.detach().cpu().numpy().astype(np.float64)
+    err = np.abs(got - want64)
+    lim = REL_TOL * bound + 1e-30
+    worst = float((err / lim).max()) if err.size else 0.0
+    assert worst <= 1.0, f"{what}: error is {worst:.3g} x the 1e-5*sum|terms| bound"
+
+
+# ---------------------------------------------------------------------------------------
+# a-1 / a-2  MaxK -> CBSR, scatter, gather
+# ---------------------------------------------------------------------------------------
+TOPK_CASES = [(257, 256, 32), (100, 256, 8), (100, 256, 16), (64, 256, 64), (33, 256, 256),
+              (50, 64, 8), (50, 32, 32), (40, 96, 1), (37, 100, 7), (31, 130, 20),
+              (40, 384, 16), (20, 512, 32), (20, 768, 64), (12, 1024, 32), (9, 1500, 40),
+              (5, 4100, 33), (1, 256, 32)]
+
+
+@pytest.mark.parametrize("n,d,k", TOPK_CASES)
+def test_topk_cbsr_bit_exact(mk, n, d, k):
+    from oracle import c_oracle
+    rng = np.random.default_rng(n * 7 + d + k)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    data, idx = mk.maxk_forward_cbsr(dev(x), k)
+    want_data, want_idx = c_oracle.maxk_cbsr(x, k)
+    assert idx.dtype == (torch.uint8 if d <= 256 else torch.uint16)
+    got_idx = idx.cpu().numpy() if d <= 256 else idx.view(torch.int16).cpu().numpy().view(np.uint16)
+    assert np.array_equal(got_idx, want_idx)
+    assert np.array_equal(data.cpu().numpy().view(np.uint32), want_data.view(np.uint32))
+    assert torch.equal(mk.maxk_forward(dev(x), k), data)          # reference signature: values only
+
+
+def test_topk_ties_nan_signed_zero(mk):
+    from oracle import maxk_oracle as mo
+    nan, inf = np.nan, np.inf
+    rows = [
+        [1, 3, 3, 3, 0, 3, -1, 2], [0] * 8, [-0.0, 0.0, -0.0, 0.0, -1, -1, -1, -1],
+        [nan, 1, inf, nan, -inf, 5, 4, nan], [-inf, -inf, -inf, -5, -inf, -inf, -inf, -inf],
+    ]
+    x = np.array(rows, dtype=np.float32)
+    for k in (1, 2, 3, 5, 8):
+        data, idx = mk.maxk_forward_cbsr(dev(x), k)
+        wd, wi = mo.maxk_cbsr(x, k)
+        assert np.array_equal(idx.cpu().numpy(), wi), k
+        assert np.array_equal(data.cpu().numpy().view(np.uint32), wd.view(np.uint32)), k
+    # heavy ties at realistic width: quantised values, many duplicates of the threshold
+    rng = np.random.default_rng(0)
+    for d, k in ((256, 32), (384, 16), (1500, 64)):
+        xq = np.round(rng.standard_normal((64, d)) * 2).astype(np.float32) / 2
+        xq[3] = 0.0
+        xq[5, ::3] = np.nan
+        data, idx = mk.maxk_forward_cbsr(dev(xq), k)
+        wd, wi = mo.maxk_cbsr(xq, k)
+        gi = idx.cpu().numpy() if d <= 256 else idx.view(torch.int16).cpu().numpy().view(np.uint16)
+        assert np.array_equal(gi, wi), (d, k)
+        assert np.array_equal(data.cpu().numpy().view(np.uint32), wd.view(np.uint32)), (d, k)
+
+
+def test_golden_vectors_through_the_cuda_path(mk, golden):
+    """Outputs of the reference's own Python (tests/golden/make_golden.py)."""
+    from spgemm_gnn_b200.maxk_layers import MaxKFunction
+    for ci in range(int(golden["num_cases"])):
+        pre = f"c{ci}_"
+        x, k = golden[pre + "x"], int(golden[pre + "k"])
+        xt = dev(x).requires_grad_(True)
+        y = MaxKFunction.apply(xt, k)                       # utils/maxk_layers.py::MaxKFunction
+        assert np.array_equal(y.detach().cpu().numpy(), golden[pre + "maxk_out"])
+        y.backward(dev(golden[pre + "grad_out"]))
+        assert np.array_equal(xt.grad.cpu().numpy(), golden[pre + "maxk_grad_in"])
+        if pre + "sp_index" in golden.files:              # _extract_sparse_format layout
+            data, idx = mk.maxk_forward_cbsr(dev(x), k)
+            assert np.array_equal(idx.cpu().numpy(), golden[pre + "sp_index"])
+            assert np.array_equal(data.cpu().numpy(), golden[pre + "sp_data"])
+
+
+@pytest.mark.parametrize("n,d,k", [(100, 256, 32), (33, 100, 7), (20, 384, 16), (7, 1500, 40)])
+def test_scatter_and_gather(mk, n, d, k):
+    from oracle import maxk_oracle as mo
+    rng = np.random.default_rng(d)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    g = rng.standard_normal((n, k)).astype(np.float32)
+    _, wi = mo.maxk_cbsr(x, k)
+    idx = dev(wi.astype(np.uint8)) if d <= 256 else dev(wi.view(np.int16)).view(torch.uint16)
+    dense = mk.cbsr_scatter(dev(g), idx, d)
+    assert np.array_equal(dense.cpu().numpy(), mo.cbsr_scatter(g, wi, d))
+    assert np.array_equal(mk.cbsr_gather(dev(x), idx).cpu().numpy(), mo.cbsr_gather(x, wi))
+    # reference signature maxk_backward(grad_output, indices): D inferred as indices.max()+1,
+    # int64 indices accepted (what utils/maxk_layers.py:23 saves)
+    d_inf = max(int(wi.max()) + 1, k)
+    got = mk.maxk_backward(dev(g), dev(wi.astype(np.int64)))
+    assert got.shape == (n, d_inf)
+    assert np.array_equal(got.cpu().numpy(), mo.cbsr_scatter(g, wi, d)[:, :d_inf])
+
+
+# ---------------------------------------------------------------------------------------
+# a-5  partition
+# ---------------------------------------------------------------------------------------
+def _edge_case_ptr():
+    deg = np.array([0, 1, 63, 64, 65, 0, 0, 128, 129, 20000, 1, 0, 5000, 7], dtype=np.int64)
+    rng = np.random.default_rng(1)
+    deg = np.concatenate([deg, rng.integers(0, 300, 3000)])
+    return np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+
+
+@pytest.mark.parametrize("max_nz", [1, 64, 100, 1024, 1 << 20])
+def test_partition_matches_oracle(mk, max_nz):
+    from oracle import c_oracle
+    ptr = _edge_case_ptr()
+    if max_nz == 1:
+        ptr = ptr[:200]
+        ptr = ptr - ptr[0]
+    want, slots = c_oracle.partition_rows(ptr, max_nz)
+    p = mk.partition(dev(ptr), ptr.size - 1, max_nz)
+    assert (p.num_parts, p.num_slots) == (len(want), slots)
+    assert np.array_equal(p.parts.cpu().numpy()[: p.num_parts], want)
+
+
+# ---------------------------------------------------------------------------------------
+# a-3 / a-4  SpGEMM forward, SSpMM backward
+# ---------------------------------------------------------------------------------------
+def _problem(n, avg_deg, d, k, seed, kind="mean", extra_ptr=None):
+    from oracle import maxk_oracle as mo
+    from spgemm_gnn_b200.graph import synthetic_graph
+    g = synthetic_graph(n, n * avg_deg, seed=seed)
+    ptr, idx = g.indptr.numpy(), g.indices.numpy()
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    dy = rng.standard_normal((n, d)).astype(np.float32)
+    val = mo.edge_weights(ptr, idx, kind)
+    return ptr, idx, val, x, dy
+
+
+def _to_index_tensor(wi, d):
+    return dev(wi) if d <= 256 else dev(wi.view(np.int16)).view(torch.uint16)
+
+
+LAYER_CASES = [
+    # n, avg_deg, d, k, max_nz
+    (2000, 40, 256, 32, 1024), (2000, 40, 256, 16, 1024), (2000, 40, 256, 8, 1024),
+    (2000, 40, 256, 64, 1024), (1500, 30, 256, 32, 64), (1500, 30, 64, 16, 7),
+    (1000, 20, 384, 16, 256), (1000, 20, 384, 64, 256), (800, 25, 256, 7, 128),
+    (800, 25, 100, 20, 128), (600, 10, 512, 128, 1024), (600, 10, 96, 96, 1024),
+    (500, 12, 1500, 40, 200), (700, 15, 128, 4, 50),
+]
+
+
+@pytest.mark.parametrize("n,avg_deg,d,k,max_nz", LAYER_CASES)
+@pytest.mark.parametrize("kind", ["mean", "both"])
+def test_spgemm_forward_and_sspmm_backward(mk, n, avg_deg, d, k, max_nz, kind):
+    from oracle import c_oracle, maxk_oracle as mo
+    ptr, idx, val, x, dy = _problem(n, avg_deg, d, k, seed=n + d + k, kind=kind)
+    wd, wi = c_oracle.maxk_cbsr(x, k)
+    mk.set_max_nz(max_nz)
+    try:
+        tptr, tidx, tval = dev(ptr), dev(idx), dev(val)
+        sp_data, sp_index = dev(wd), _to_index_tensor(wi, d)
+        out, ret_index = mk.spgemm_forward(tptr, tidx, tval, sp_data, sp_index, n, idx.size, k, d)
+        assert ret_index is sp_index and out.shape == (n, d) and out.dtype == torch.float32
+        want = c_oracle.spgemm_fwd(ptr, idx, val, wd, wi, d)
+        bound = c_oracle.spgemm_fwd(ptr, idx, np.abs(val), np.abs(wd), wi, d)
+        assert_rel(out, want, bound, "spgemm_forward")
+        # no atomics on the forward path: bit-reproducible
+        out2, _ = mk.spgemm_forward(tptr, tidx, tval, sp_data, sp_index, n, idx.size, k, d)
+        assert torch.equal(out, out2)
+
+        dxs = mk.spgemm_backward(tptr, tidx, tval, dev(dy), sp_index, n, idx.size, k, d)
+        assert dxs.shape == (n, k)
+        want_b = c_oracle.sspmm_bwd(ptr, idx, val, dy, wi)
+        bound_b = c_oracle.sspmm_bwd(ptr, idx, np.abs(val), np.abs(dy), wi)
+        assert_rel(dxs, want_b, bound_b, "spgemm_backward")
+    finally:
+        mk.set_max_nz(1024)
+
+
+def test_degree_edge_cases_and_empty_rows(mk):
+    """degrees 0 / 1 / 64 / 65 / > 10^4 in one graph (SURVEY.md section 4 implication)."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(4)
+    n, d, k = 12000, 256, 32
+    deg = np.zeros(n, dtype=np.int64)
+    deg[:8] = [0, 1, 64, 65, 11000, 0, 1025, 2048]
+    deg[8:] = rng.integers(0, 6, n - 8)
+    ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    idx = np.concatenate([np.sort(rng.choice(n, dg, replace=False)) for dg in deg]).astype(np.int32)
+    val = rng.standard_normal(idx.size).astype(np.float32)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    dy = rng.standard_normal((n, d)).astype(np.float32)
+    wd, wi = c_oracle.maxk_cbsr(x, k)
+    for max_nz in (64, 1024):
+        mk.set_max_nz(max_nz)
+        try:
+            out, _ = mk.spgemm_forward(dev(ptr), dev(idx), dev(val), dev(wd), dev(wi), n, idx.size, k, d)
+            want = c_oracle.spgemm_fwd(ptr, idx, val, wd, wi, d)
+            bound = c_oracle.spgemm_fwd(ptr, idx, np.abs(val), np.abs(wd), wi, d)
+            assert_rel(out, want, bound, f"fwd max_nz={max_nz}")
+            assert float(out[0].abs().max()) == 0.0 and float(out[5].abs().max()) == 0.0
+            dxs = mk.spgemm_backward(dev(ptr), dev(idx), dev(val), dev(dy), dev(wi), n, idx.size, k, d)
+            want_b = c_oracle.sspmm_bwd(ptr, idx, val, dy, wi)
+            bound_b = c_oracle.sspmm_bwd(ptr, idx, np.abs(val), np.abs(dy), wi)
+            assert_rel(dxs, want_b, bound_b, f"bwd max_nz={max_nz}")
+        finally:
+            mk.set_max_nz(1024)
+
+
+def test_identity_adjacency_and_reference_padding(mk, golden):
+    """A = I  =>  Y == dense(Xs) exactly; zero-padded CBSR rows (utils/maxk_layers.py:245-257)
+    produce the plain dense view (they race in the reference kernel)."""
+    from oracle import maxk_oracle as mo
+    x = golden["pad_x"]
+    n, d = x.shape
+    k = int(golden["pad_k"])
+    ptr = dev(np.arange(n + 1, dtype=np.int32))
+    idx = dev(np.arange(n, dtype=np.int32))
+    val = torch.ones(n, device="cuda")
+    out, _ = mk.spgemm_forward(ptr, idx, val, dev(golden["pad_sp_data"]), dev(golden["pad_sp_index"]),
+                               n, n, k, d)
+    want = mo.cbsr_to_dense(golden["pad_sp_data"], golden["pad_sp_index"], d)
+    assert np.array_equal(out.cpu().numpy().astype(np.float64), want)
+
+
+def test_rectangular_shard_with_global_columns(mk):
+    """Row shard of a bigger graph: n_rows < n_src (the 1-D partition of SURVEY.md section 8e)."""
+    from oracle import c_oracle, maxk_oracle as mo
+    from spgemm_gnn_b200.graph import synthetic_graph
+    g = synthetic_graph(3000, 90000, seed=8)
+    s = g.row_slice(1000, 1700)
+    ptr, idx = s.indptr.numpy(), s.indices.numpy()
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((3000, 256)).astype(np.float32)
+    dy = rng.standard_normal((700, 256)).astype(np.float32)
+    val = mo.edge_weights(ptr, idx, "mean", num_src=3000)
+    wd, wi = c_oracle.maxk_cbsr(x, 32)
+    out, _ = mk.spgemm_forward(dev(ptr), dev(idx), dev(val), dev(wd), dev(wi), 700, idx.size, 32, 256)
+    assert_rel(out, c_oracle.spgemm_fwd(ptr, idx, val, wd, wi, 256),
+               c_oracle.spgemm_fwd(ptr, idx, np.abs(val), np.abs(wd), wi, 256), "shard fwd")
+    dxs = mk.spgemm_backward(dev(ptr), dev(idx), dev(val), dev(dy), dev(wi), 700, idx.size, 32, 256)
+    assert dxs.shape == (3000, 32)
+    assert_rel(dxs, c_oracle.sspmm_bwd(ptr, idx, val, dy, wi),
+               c_oracle.sspmm_bwd(ptr, idx, np.abs(val), np.abs(dy), wi), "shard bwd")
+
+
+def test_error_behaviour_matches_reference_binding(mk):
+    x = torch.randn(8, 32, device="cuda")
+    with pytest.raises(RuntimeError, match="k must be between 1 and input dimension"):
+        mk.maxk_forward(x, 0)
+    with pytest.raises(RuntimeError, match="k must be between 1 and input dimension"):
+        mk.maxk_forward(x, 33)
+    with pytest.raises(RuntimeError, match="Input must be 2D tensor"):
+        mk.maxk_forward(x.view(-1), 4)
+    with pytest.raises(RuntimeError, match="input must be contiguous"):
+        mk.maxk_forward(x.t(), 4)
+    ptr = torch.arange(9, dtype=torch.int64, device="cuda")
+    idx = torch.arange(8, dtype=torch.int32, device="cuda")
+    val = torch.ones(8, device="cuda")
+    d, i = mk.maxk_forward_cbsr(x, 4)
+    with pytest.raises(RuntimeError, match="ptr must be int32"):
+        mk.spgemm_forward(ptr, idx, val, d, i, 8, 8, 4, 32)
+    with pytest.raises(RuntimeError, match="val must be float32"):
+        mk.spgemm_forward(ptr.int(), idx, val.double(), d, i, 8, 8, 4, 32)
+    with pytest.raises(RuntimeError, match="sp_data must be float32"):
+        mk.spgemm_forward(ptr.int(), idx, val, d.half(), i, 8, 8, 4, 32)
+    with pytest.raises(RuntimeError, match="grad_output must be float32"):
+        mk.spgemm_backward(ptr.int(), idx, val, x.half(), i, 8, 8, 4, 32)
+
+
+# ---------------------------------------------------------------------------------------
+# layers against the torch restatement of the reference's training path
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["mean", "both", "sum"])
+def test_autograd_layer_matches_torch_reference(mk, kind):
+    from oracle import ref_torch
+    from spgemm_gnn_b200.graph import synthetic_graph
+    from spgemm_gnn_b200.maxk_layers import maxk_aggregate
+    g = synthetic_graph(1500, 45000, seed=21)
+    gen = torch.Generator().manual_seed(21)
+    x = torch.randn(1500, 256, generator=gen)
+    dy = torch.randn(1500, 256, generator=gen)
+    adj = ref_torch.csr_matrix(g.indptr, g.indices, g.edge_weights(kind), g.num_src)
+    y_ref, dx_ref = ref_torch.layer_forward_backward(adj.to(torch.float64), x.double(), dy.double(), 32)
+    gg = g.to("cuda")
+    xc = x.cuda().requires_grad_(True)
+    y = maxk_aggregate(gg, xc, 32, kind)
+    y.backward(dy.cuda())
+    scale_y = float(y_ref.abs().max())
+    scale_g = float(dx_ref.abs().max())
+    assert float((y.cpu().double() - y_ref).abs().max()) <= 1e-5 * scale_y
+    assert float((xc.grad.cpu().double() - dx_ref).abs().max()) <= 1e-5 * scale_g
+    # the gradient is zero exactly where the reference's mask is zero
+    assert torch.equal(xc.grad.cpu() == 0, dx_ref == 0)
+
+
+# ---------------------------------------------------------------------------------------
+# full BASELINE size: properties that need no CPU oracle
+# ---------------------------------------------------------------------------------------
+def test_reddit_shape_properties(mk):
+    """Reddit-shaped synthetic graph (232,965 nodes, ~114M edges), D=256, k=32: adjointness
+    <A Xs, dY> == <Xs, dXs>, exact linearity in val (power-of-two scaling), agreement with the
+    dense cuSPARSE SpMM on the masked matrix, bit-reproducible forward."""
+    from spgemm_gnn_b200.graph import shaped_graph
+    g = shaped_graph("reddit", device="cuda")
+    n, e = g.num_nodes(), g.num_edges()
+    assert n == 232965 and 0.9e8 < e < 1.3e8
+    gen = torch.Generator(device="cuda").manual_seed(97)
+    x = torch.randn(n, 256, device="cuda", generator=gen)
+    dy = torch.randn(n, 256, device="cuda", generator=gen)
+    val = g.edge_weights("mean")
+    sp_data, sp_index = mk.maxk_forward_cbsr(x, 32)
+    # top-k: ascending distinct columns, values are the k largest of the row
+    cols = sp_index.to(torch.int32)
+    assert bool((cols[:, 1:] > cols[:, :-1]).all())
+    kth = torch.topk(x, 32, dim=1)[0][:, -1]
+    assert bool((sp_data.min(dim=1)[0] == kth).all())
+    assert torch.equal(torch.gather(x, 1, cols.long()), sp_data)
+
+    out, _ = mk.spgemm_forward(g.indptr, g.indices, val, sp_data, sp_index, n, e, 32, 256)
+    out2, _ = mk.spgemm_forward(g.indptr, g.indices, val, sp_data, sp_index, n, e, 32, 256)
+    assert torch.equal(out, out2)
+    out4, _ = mk.spgemm_forward(g.indptr, g.indices, val * 4.0, sp_data, sp_index, n, e, 32, 256)
+    assert torch.equal(out4, out * 4.0)
+    dxs = mk.spgemm_backward(g.indptr, g.indices, val, dy, sp_index, n, e, 32, 256)
+    lhs = float((out.double() * dy.double()).sum())
+    rhs = float((sp_data.double() * dxs.double()).sum())
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs), 1.0)
+
+    # mean aggregation of a constant CBSR table reproduces the constant (rows of A sum to 1)
+    ones = torch.ones_like(sp_data)
+    same_idx = sp_index[:1].expand(n, 32).contiguous()
+    o1, _ = mk.spgemm_forward(g.indptr, g.indices, val, ones, same_idx, n, e, 32, 256)
+    picked = o1[:, same_idx[0].long()]
+    assert float((picked - 1.0).abs().max()) < 1e-4
+    assert float(o1.sum()) == pytest.approx(32.0 * n, rel=1e-4)
+
+    # independent check at full size: cuSPARSE dense SpMM on the masked matrix
+    xm = mk.cbsr_scatter(sp_data, sp_index, 256)
+    adj = torch.sparse_csr_tensor(g.indptr.long(), g.indices.long(), val, size=(n, n))
+    ref = torch.sparse.mm(adj, xm)
+    assert float((out - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    gref = torch.sparse.mm(adj.t().to_sparse_csr(), dy)
+    gpick = torch.gather(gref, 1, cols.long())
+    assert float((dxs - gpick).abs().max()) <= 2e-5 * float(gpick.abs().max())

@@ -1,0 +1,69 @@
+"""Host-side logic: CSR container, synthetic shapes, edge weights, row partition (no GPU)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import maxk_oracle as mo
+from spgemm_gnn_b200 import graph as G
+
+
+def test_synthetic_graph_is_symmetric_sorted_with_self_loops():
+    g = G.synthetic_graph(500, 6000, seed=97)
+    ptr, idx = g.indptr.numpy(), g.indices.numpy()
+    n = g.num_nodes()
+    assert ptr[0] == 0 and ptr[-1] == idx.size and np.all(np.diff(ptr) >= 1)
+    rows = np.repeat(np.arange(n), np.diff(ptr))
+    a = set(zip(rows.tolist(), idx.tolist()))
+    assert len(a) == idx.size                                  # no duplicate edges
+    assert all((c, r) in a for r, c in a)                      # symmetric
+    assert all((i, i) in a for i in range(n))                  # self-loops
+    for r in range(n):
+        assert np.all(np.diff(idx[ptr[r]:ptr[r + 1]]) > 0)     # ascending neighbours
+    assert 0.6 * 6000 < idx.size < 1.4 * 6000
+    g2 = G.synthetic_graph(500, 6000, seed=97)
+    assert torch.equal(g.indices, g2.indices)                 # seeded
+
+
+@pytest.mark.parametrize("kind", ["mean", "both", "sum", "right"])
+def test_edge_weights_match_oracle(kind):
+    g = G.synthetic_graph(300, 3000, seed=3)
+    w = g.edge_weights(kind).numpy()
+    ref = mo.edge_weights(g.indptr.numpy(), g.indices.numpy(), kind)
+    np.testing.assert_allclose(w, ref, rtol=1e-6)
+    if kind == "mean":       # rows of a mean adjacency sum to one
+        rows = g.row_ids().numpy()
+        np.testing.assert_allclose(np.bincount(rows, weights=w), 1.0, rtol=1e-5)
+
+
+def test_row_partition_bounds_balance_nnz_and_slices_keep_global_columns():
+    g = G.synthetic_graph(1000, 20000, seed=9)
+    for world in (1, 2, 4, 8):
+        b = G.row_partition_bounds(g.indptr, world)
+        assert b[0] == 0 and b[-1] == 1000 and len(b) == world + 1 and b == sorted(b)
+        nnz = [int(g.indptr[b[p + 1]] - g.indptr[b[p]]) for p in range(world)]
+        assert max(nnz) <= 1.3 * g.num_edges() / world + 2000
+        cat = torch.cat([g.row_slice(b[p], b[p + 1]).indices for p in range(world)])
+        assert torch.equal(cat, g.indices)
+        for p in range(world):
+            s = g.row_slice(b[p], b[p + 1])
+            assert s.num_src == 1000 and s.indptr[0] == 0 and int(s.indptr[-1]) == s.num_edges()
+
+
+def test_shapes_and_index_dtype():
+    assert G.SHAPES["reddit"] == (232965, 114615891)
+    assert G.index_dtype_for(256) == torch.uint8 and G.index_dtype_for(384) == torch.uint16
+    g = G.shaped_graph("flickr", scale=0.02)
+    assert abs(g.num_nodes() - 1785) <= 1
+    with pytest.raises(TypeError):
+        G.CSRGraph(torch.zeros(3, dtype=torch.int64), torch.zeros(0, dtype=torch.int32))
+
+
+def test_dgl_surface_used_by_reference_layers():
+    g = G.synthetic_graph(50, 300, seed=1)
+    assert g.number_of_nodes() == 50 and g.num_edges() == g.indices.numel()
+    assert hasattr(g, "_sparse_format")                      # utils/maxk_layers.py:94
+    ptr, idx, eid = g.adj_tensors("csr")                     # symmetric: csr == csc
+    assert ptr is g.indptr and idx is g.indices and eid.numel() == g.num_edges()
+    with g.local_scope():
+        assert int(g.in_degrees().sum()) == g.num_edges() == int(g.out_degrees().sum())
+    assert torch.equal(g.in_degrees(), g.out_degrees())      # symmetric graph
