@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Small driver for ncu: W warm-up steps then S steps of (spgemm_forward, spgemm_backward) on one
+of the BASELINE shapes.  Also times each with CUDA events (ignored under ncu)."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import maxk_kernels as mk
+from spgemm_gnn_b200.graph import shaped_graph
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="reddit")
+ap.add_argument("--scale", type=float, default=1.0)
+ap.add_argument("--k", type=int, default=32)
+ap.add_argument("--dim", type=int, default=256)
+ap.add_argument("--warmup", type=int, default=2)
+ap.add_argument("--steps", type=int, default=1)
+ap.add_argument("--max-nz", type=int, default=None)
+ap.add_argument("--with-maxk", action="store_true")
+a = ap.parse_args()
+if a.max_nz:
+    mk.set_max_nz(a.max_nz)
+g = shaped_graph(a.workload, scale=a.scale, device="cuda")
+n, e = g.num_nodes(), g.num_edges()
+val = g.edge_weights("mean")
+gen = torch.Generator(device="cuda").manual_seed(97)
+x = torch.randn(n, a.dim, device="cuda", generator=gen)
+dy = torch.randn(n, a.dim, device="cuda", generator=gen)
+sd, si = mk.maxk_forward_cbsr(x, a.k)
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+for it in range(a.warmup + a.steps):
+    if a.with_maxk:
+        sd, si = mk.maxk_forward_cbsr(x, a.k)
+    ev[0].record()
+    out, _ = mk.spgemm_forward(g.indptr, g.indices, val, sd, si, n, e, a.k, a.dim)
+    ev[1].record()
+    dxs = mk.spgemm_backward(g.indptr, g.indices, val, dy, si, n, e, a.k, a.dim)
+    ev[2].record()
+    if a.with_maxk:
+        dx = mk.cbsr_scatter(dxs, si, a.dim)
+torch.cuda.synchronize()
+print(f"{a.workload} N={n} E={e} k={a.k} D={a.dim} max_nz={mk.get_max_nz()}: "
+      f"fwd {ev[0].elapsed_time(ev[1]):.3f} ms  bwd {ev[1].elapsed_time(ev[2]):.3f} ms")
