@@ -1,0 +1,108 @@
+"""Full-graph training on a synthetic graph of one of the reference's dataset shapes -- the role
+of `maxk_gnn_integrated.py` (and of `maxk_gnn_dgl.py`, the driver that produced every logged
+number) with the DGL/OGB dataset loaders replaced by a seeded generator (no network, no DGL).
+
+    python -m spgemm_gnn_b200.train --dataset reddit --model sage --maxk 32 --epochs 50
+
+Flags keep the names of `utils/config.py:30-70`.  With torchrun the graph is row-partitioned
+over the ranks (see `dist.py`); weights are replicated and their gradients all-reduced.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import time
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .graph import FEATS, SHAPES, CSRGraph, shaped_graph
+from .models import MODELS
+
+
+def synthetic_task(name: str, scale: float, device, seed: int = 97):
+    """Graph + random features / labels / 66-10-24 split with the logged in_feats and class
+    counts of the real dataset.  Accuracy is meaningless; losses are not."""
+    g = shaped_graph(name, scale=scale, seed=seed, device=device)
+    n = g.num_nodes()
+    in_feats, classes = FEATS[name]
+    gen = torch.Generator(device=device).manual_seed(seed + 1)
+    feats = torch.randn(n, in_feats, device=device, generator=gen)
+    labels = torch.randint(0, classes, (n,), device=device, generator=gen)
+    r = torch.rand(n, device=device, generator=gen)
+    train_mask, val_mask = r < 0.66, (r >= 0.66) & (r < 0.76)
+    return g, feats, labels, train_mask, val_mask, ~(train_mask | val_mask), in_feats, classes
+
+
+def train_epochs(model: nn.Module, g: CSRGraph, feats, labels, train_mask, epochs: int,
+                 lr: float = 0.01, weight_decay: float = 0.0, eval_every: int = 0, log=None):
+    """The loop of maxk_gnn_dgl.py:98-134: one full-graph forward + backward per epoch (+ an
+    eval forward every `eval_every` epochs).  Returns (losses, seconds per epoch)."""
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
+    losses, times = [], []
+    cuda = feats.is_cuda
+    for ep in range(epochs):
+        model.train()
+        if cuda:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        logits = model(g, feats)
+        loss = F.cross_entropy(logits[train_mask], labels[train_mask])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        if eval_every and (ep + 1) % eval_every == 0:
+            model.eval()
+            with torch.no_grad():
+                model(g, feats)
+        if cuda:
+            torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+        losses.append(float(loss.detach()))
+        if log:
+            log(f"epoch {ep:4d} loss {losses[-1]:.6f} time {times[-1] * 1e3:.2f} ms")
+    return losses, times
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--dataset", default="flickr", choices=sorted(SHAPES))
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--model", default="sage", choices=sorted(MODELS))
+    ap.add_argument("--epochs", type=int, default=50)
+    ap.add_argument("--w_lr", type=float, default=0.01)
+    ap.add_argument("--w_weight_decay", type=float, default=0.0)
+    ap.add_argument("--hidden_dim", type=int, default=256)
+    ap.add_argument("--hidden_layers", type=int, default=3)
+    ap.add_argument("--nonlinear", default="maxk", choices=["maxk", "relu"])
+    ap.add_argument("--maxk", type=int, default=32)
+    ap.add_argument("--dropout", type=float, default=0.5)
+    ap.add_argument("--norm", action="store_true")
+    ap.add_argument("--gpu", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=97)
+    ap.add_argument("--tf32", action="store_true", help="TF32 GEMMs as maxk_gnn_dgl.py:30-33")
+    a = ap.parse_args(argv)
+    if not torch.cuda.is_available():
+        raise SystemExit("training needs a CUDA device: the aggregation has no CPU fallback")
+    torch.cuda.set_device(a.gpu)
+    dev = torch.device("cuda", a.gpu)
+    torch.manual_seed(a.seed)
+    torch.backends.cuda.matmul.allow_tf32 = a.tf32
+    torch.backends.cudnn.allow_tf32 = a.tf32
+    g, feats, labels, train_mask, _, _, in_feats, classes = synthetic_task(a.dataset, a.scale, dev, a.seed)
+    model = MODELS[a.model](in_feats, a.hidden_dim, a.hidden_layers, classes, maxk=a.maxk,
+                            feat_drop=a.dropout, norm=a.norm, nonlinear=a.nonlinear).to(dev)
+    print(f"{a.dataset}: {g.num_nodes()} nodes, {g.num_edges()} edges; model {a.model} "
+          f"{sum(p.numel() for p in model.parameters())} params")
+    losses, times = train_epochs(model, g, feats, labels, train_mask, a.epochs, a.w_lr,
+                                 a.w_weight_decay, eval_every=1, log=print)
+    steady = sorted(times[len(times) // 5:])
+    print(json.dumps({"dataset": a.dataset, "model": a.model, "nonlinear": a.nonlinear, "maxk": a.maxk,
+                      "epochs": a.epochs, "final_loss": losses[-1],
+                      "epoch_ms_median": steady[len(steady) // 2] * 1e3}))
+
+
+if __name__ == "__main__":
+    main()
