@@ -40,7 +40,8 @@ def train_epochs(model: nn.Module, g: CSRGraph, feats, labels, train_mask, epoch
                  lr: float = 0.01, weight_decay: float = 0.0, eval_every: int = 0, log=None):
     """The loop of maxk_gnn_dgl.py:98-134: one full-graph forward + backward per epoch (+ an
     eval forward every `eval_every` epochs).  Returns (losses, seconds per epoch)."""
-    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=lr,
+                           weight_decay=weight_decay)
     losses, times = [], []
     cuda = feats.is_cuda
     for ep in range(epochs):
