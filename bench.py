@@ -260,14 +260,13 @@ def main():
 
     def step():
         if world > 1:
-            fd, fi = mdist.allgather_cbsr(sp_data, sp_index)
+            out, fi = mdist.sharded_forward(sp_data, sp_index, ptr, idx, val, n_rows, d)
+            mid.record()
+            dxs = mdist.sharded_backward(dy, fi, ptr, idx, val, n_rows, d)
         else:
-            fd, fi = sp_data, sp_index
-        out, _ = mk.spgemm_forward(ptr, idx, val, fd, fi, n_rows, e_local, k, d)
-        mid.record()
-        dxs = mk.spgemm_backward(ptr, idx, val, dy, fi, n_rows, e_local, k, d)
-        if world > 1:
-            dxs = mdist.reduce_scatter_rows(dxs)
+            out, _ = mk.spgemm_forward(ptr, idx, val, sp_data, sp_index, n_rows, e_local, k, d)
+            mid.record()
+            dxs = mk.spgemm_backward(ptr, idx, val, dy, sp_index, n_rows, e_local, k, d)
         return out, dxs
 
     def barrier():
@@ -347,6 +346,8 @@ def main():
         "scatter_alg_GBps": (n_rows * k * (4 + w) + n_rows * d * 4) / (scatter_ms * 1e-3) / 1e9,
         "edges_per_s_fwd": e / (fwd_ms * 1e-3), "edges_per_s_bwd": e / (bwd_ms * 1e-3),
         "work_records": part.num_parts, "partial_slots": part.num_slots, "max_nz": mk.get_max_nz(),
+        "forward_variant": "banked (mk_cbsr_bank + mk_spgemm_fwd_banked, both inside spgemm_fwd_ms)"
+        if mk.use_banked(part.num_parts, e_local, k, d) else "plain (mk_spgemm_fwd)",
     }
 
     # ---- end to end through the public entry points with HOST buffers
@@ -366,13 +367,11 @@ def main():
             dy_dev.copy_(hdy, non_blocking=True)
             sd, si = mk.maxk_forward_cbsr(dx_dev, k)
             if world > 1:
-                fd, fi = mdist.allgather_cbsr(sd, si)
+                out, fi = mdist.sharded_forward(sd, si, ptr, idx, val, n_rows, d)
+                dxs = mdist.sharded_backward(dy_dev, fi, ptr, idx, val, n_rows, d)
             else:
-                fd, fi = sd, si
-            out, _ = mk.spgemm_forward(ptr, idx, val, fd, fi, n_rows, e_local, k, d)
-            dxs = mk.spgemm_backward(ptr, idx, val, dy_dev, fi, n_rows, e_local, k, d)
-            if world > 1:
-                dxs = mdist.reduce_scatter_rows(dxs)
+                out, _ = mk.spgemm_forward(ptr, idx, val, sd, si, n_rows, e_local, k, d)
+                dxs = mk.spgemm_backward(ptr, idx, val, dy_dev, si, n_rows, e_local, k, d)
             hout.copy_(out, non_blocking=True)
             hdxs.copy_(dxs, non_blocking=True)
 

@@ -121,6 +121,27 @@ MK_API int mk_sspmm_bwd(const mk_part* parts, int64_t num_parts, const int32_t* 
                         const float* val, const float* dy, const void* sp_index, int index_bytes,
                         float* dxs, int64_t n_rows, int64_t n_src, int k, int d, void* stream);
 
+/* ---- banked CBSR: the conflict-free internal form of the hot path ----------------------------
+ * Not in the reference.  The forward / backward kernels above are bound by shared-memory bank
+ * conflicts (3.6 wavefronts per access measured); mk_cbsr_bank re-orders the k entries of every
+ * CBSR row and picks one of two shared-memory cells per entry so that the 8 lanes working on a
+ * neighbour hit 8 different banks.  Outputs have the shapes of the inputs: bk_data / bk_index are a
+ * permutation of the row (still a valid CBSR row, columns no longer ascending), bk_slot uint16
+ * [n,k] is the cell offset.  The *_banked kernels compute exactly what mk_spgemm_fwd /
+ * mk_sspmm_bwd compute; mk_sspmm_bwd_banked emits the gradient in the banked entry order (pair it
+ * with bk_index).  Supported: k in {8,16,32,64}, d % 8 == 0, d <= 512 (mk_banked_supported).     */
+MK_API int mk_banked_supported(int k, int d);
+MK_API int mk_banked_rows(int d);
+MK_API int mk_cbsr_bank(const float* sp_data, const void* sp_index, int index_bytes, float* bk_data,
+                        void* bk_index, uint16_t* bk_slot, int64_t n, int k, int d, void* stream);
+MK_API int mk_spgemm_fwd_banked(const mk_part* parts, int64_t num_parts, int64_t num_slots,
+                                const int32_t* idx, const float* val, const float* bk_data,
+                                const uint16_t* bk_slot, float* out, float* partial, int64_t n_rows,
+                                int k, int d, void* stream);
+MK_API int mk_sspmm_bwd_banked(const mk_part* parts, int64_t num_parts, const int32_t* idx,
+                               const float* val, const float* dy, const uint16_t* bk_slot,
+                               float* dxs, int64_t n_rows, int64_t n_src, int k, int d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -276,3 +276,36 @@ def layer_dense_backward(indptr, indices, val, grad_y, mask):
     g = np.zeros((mask.shape[0], grad_y.shape[1]))
     np.add.at(g, np.asarray(indices), np.asarray(val, np.float64)[:, None] * np.asarray(grad_y, np.float64)[rows])
     return g * mask
+
+
+# ---------------------------------------------------------------------------------------
+# banked CBSR (product-internal format, csrc/bank.cu): validity check + conflict count
+# ---------------------------------------------------------------------------------------
+def banked_rows(dim_origin: int) -> int:
+    return (dim_origin + 7) // 8 + 8 * ((dim_origin + 63) // 64)
+
+
+def check_banked(sp_data, sp_index, bk_data, bk_index, bk_slot, dim_origin: int):
+    """Asserts that (bk_data, bk_index) is a per-row permutation of (sp_data, sp_index) and
+    that every bk_slot is one of the two legal cells of its column.  Returns the mean number
+    of shared-memory wavefronts per 8-lane step (1.0 = conflict-free)."""
+    n, k = sp_data.shape
+    cap = k // 8
+    ra = (dim_origin + 7) // 8
+    order = np.argsort(bk_index.astype(np.int64), axis=1, kind="stable")
+    assert np.array_equal(np.take_along_axis(bk_index, order, 1), sp_index)
+    assert np.array_equal(np.take_along_axis(bk_data, order, 1).view(np.uint32), sp_data.view(np.uint32))
+    c = bk_index.astype(np.int64)
+    slot = bk_slot.astype(np.int64) & 0xFFFF
+    slot_a = 32 * (c >> 3) + (c & 7)
+    slot_b = 32 * (ra + ((c >> 6) << 3) + (c & 7)) + ((c >> 3) & 7)
+    assert np.all((slot == slot_a) | (slot == slot_b))
+    assert slot.max() < 32 * banked_rows(dim_origin)
+    bank = slot & 7  # inside the group's octet
+    assert np.all(((slot >> 3) & 3) == 0)  # group offset is added by the kernel
+    steps = bank.reshape(n, 8, cap)        # position p = cap * t + q
+    wf = np.zeros((n, cap))
+    for q in range(cap):
+        b = steps[:, :, q]
+        wf[:, q] = np.max(np.stack([(b == x).sum(1) for x in range(8)], 1), 1)
+    return float(wf.mean()), wf

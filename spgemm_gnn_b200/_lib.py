@@ -27,6 +27,11 @@ SIGNATURES = {
     "mk_partition": (_i32, [_vp, _i64, _i32, _vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp]),
     "mk_spgemm_fwd": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _i32, _vp]),
     "mk_sspmm_bwd": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _i32, _vp]),
+    "mk_banked_supported": (_i32, [_i32, _i32]),
+    "mk_banked_rows": (_i32, [_i32]),
+    "mk_cbsr_bank": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "mk_spgemm_fwd_banked": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "mk_sspmm_bwd_banked": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
 }
 
 _lib = None

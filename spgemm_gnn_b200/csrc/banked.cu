@@ -1,0 +1,334 @@
+// Forward SpGEMM and backward SSpMM on a BANKED CBSR table (see bank.cu for the format).
+//
+// Same work decomposition as spgemm_fwd.cu / sspmm_bwd.cu -- one warp per work record, one record
+// per CTA, 8 lanes per neighbour, 4 neighbours per warp step, CAP = k/8 entries per lane fetched
+// with one vector load of values and one of cell offsets -- but every shared-memory access goes to
+// the cell `slot + 8*g` chosen by mk_cbsr_bank: group g only ever touches banks [8g, 8g+8), and
+// inside a group the 8 lanes of a step hit 8 different banks except for the few duplicates the
+// assignment could not avoid.  The L1TEX data pipe (the bound of the unbanked kernels) then sees
+// ~1.4 wavefronts per LDS / STS instead of 3.6.
+//
+// Shared memory per warp: 32 banks x ROWS rows of fp32, ROWS = ceil(D/8) + 8*ceil(D/64)
+// (copy A rows, then copy B rows; 8 KB at D = 256).  Forward: the cells are accumulators, folded
+// over the 4 groups and the 2 copies when the row is written.  Backward: the cells are replicas
+// of dY[r, :], built once per record.
+#include "common.cuh"
+
+namespace mk {
+
+template <int CAP>
+struct BankedLoad;
+template <>
+struct BankedLoad<1> {
+    static __device__ __forceinline__ void data(const float* p, float (&v)[1]) { v[0] = __ldg(p); }
+    static __device__ __forceinline__ void slots(const uint16_t* p, int (&s)[1]) { s[0] = __ldg(p); }
+};
+template <>
+struct BankedLoad<2> {
+    static __device__ __forceinline__ void data(const float* p, float (&v)[2]) {
+        const float2 f = __ldg(reinterpret_cast<const float2*>(p));
+        v[0] = f.x; v[1] = f.y;
+    }
+    static __device__ __forceinline__ void slots(const uint16_t* p, int (&s)[2]) {
+        const ushort2 q = __ldg(reinterpret_cast<const ushort2*>(p));
+        s[0] = q.x; s[1] = q.y;
+    }
+};
+template <>
+struct BankedLoad<4> {
+    static __device__ __forceinline__ void data(const float* p, float (&v)[4]) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    }
+    static __device__ __forceinline__ void slots(const uint16_t* p, int (&s)[4]) {
+        const ushort4 q = __ldg(reinterpret_cast<const ushort4*>(p));
+        s[0] = q.x; s[1] = q.y; s[2] = q.z; s[3] = q.w;
+    }
+};
+template <>
+struct BankedLoad<8> {
+    static __device__ __forceinline__ void data(const float* p, float (&v)[8]) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(p));
+        const float4 h = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        v[4] = h.x; v[5] = h.y; v[6] = h.z; v[7] = h.w;
+    }
+    static __device__ __forceinline__ void slots(const uint16_t* p, int (&s)[8]) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+        s[0] = q.x & 0xffff; s[1] = q.x >> 16; s[2] = q.y & 0xffff; s[3] = q.y >> 16;
+        s[4] = q.z & 0xffff; s[5] = q.z >> 16; s[6] = q.w & 0xffff; s[7] = q.w >> 16;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <int K, int U>
+__global__ void __launch_bounds__(32)
+spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
+                         const float* __restrict__ val, const float* __restrict__ bk_data,
+                         const uint16_t* __restrict__ bk_slot, float* __restrict__ out,
+                         float* __restrict__ partial, int d, int rows) {
+    constexpr int CAP = K / 8;
+    extern __shared__ __align__(16) float acc[];  // 32 * rows
+    const int lane = lane_id();
+    const int g = lane >> 3;
+    const int t = lane & 7;
+    const mk_part rec = parts[blockIdx.x];
+
+    for (int c = lane * 4; c < 32 * rows; c += 128)
+        *reinterpret_cast<float4*>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+
+    float* __restrict__ my = acc + 8 * g;
+    const int end = rec.loc + rec.len;
+    for (int base = rec.loc; base < end; base += 32) {
+        const int n_here = min(32, end - base);
+        int my_nz = 0;
+        float my_v = 0.f;
+        if (lane < n_here) {
+            my_nz = ld_stream_i1(idx + base + lane);
+            my_v = ld_stream_f1(val + base + lane);
+        }
+        for (int i = 0; i < n_here; i += 4 * U) {
+            float dv[U][CAP];
+            int sl[U][CAP];
+            float vv[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = i + u * 4 + g;
+                const int nz = __shfl_sync(kFull, my_nz, e & 31);
+                vv[u] = __shfl_sync(kFull, my_v, e & 31);
+                ok[u] = e < n_here;
+                if (ok[u]) {
+                    const int64_t off = static_cast<int64_t>(nz) * K + CAP * t;
+                    BankedLoad<CAP>::data(bk_data + off, dv[u]);
+                    BankedLoad<CAP>::slots(bk_slot + off, sl[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (ok[u]) {
+#pragma unroll
+                    for (int q = 0; q < CAP; ++q)
+                        if (dv[u][q] != 0.0f) my[sl[u][q]] += vv[u] * dv[u][q];
+                }
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- fold the 4 groups and the 2 copies.  Lane (s, b) sums, for row 4i+s, the cells of bank
+    //      b of every group, visiting the groups in the order (j+s)&3 so that the four rows read
+    //      by one instruction sit in four different bank octets.  Copy-A rows produce 8
+    //      consecutive columns each; their sums are parked in acc[0..D) (rows already consumed);
+    //      copy-B rows are then added on top.
+    const int ra = (d + 7) >> 3;
+    const int s = lane >> 3, b = lane & 7;
+    for (int row0 = 0; row0 < ra; row0 += 4) {
+        const int row = row0 + s;
+        float sum = 0.f;
+        if (row < ra) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sum += acc[32 * row + 8 * ((j + s) & 3) + b];
+        }
+        __syncwarp();
+        if (row < ra) acc[8 * row + b] = sum;  // column 8*row + b
+    }
+    __syncwarp();
+    for (int row0 = ra; row0 < rows; row0 += 4) {
+        const int row = row0 + s;
+        if (row < rows) {
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sum += acc[32 * row + 8 * ((j + s) & 3) + b];
+            const int rb = row - ra;
+            const int c = ((rb >> 3) << 6) + (b << 3) + (rb & 7);
+            if (c < d) acc[c] += sum;
+        }
+    }
+    __syncwarp();
+    float* __restrict__ o = rec.slot < 0 ? out + static_cast<int64_t>(rec.row) * d
+                                         : partial + static_cast<int64_t>(rec.slot) * d;
+    for (int c = lane * 4; c < d; c += 128)
+        st_stream_f4(o + c, *reinterpret_cast<const float4*>(acc + c));
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+template <int CAP>
+__device__ __forceinline__ void red_add_cap(float* p, const float (&g)[CAP]);
+template <>
+__device__ __forceinline__ void red_add_cap<1>(float* p, const float (&g)[1]) { red_add_f1(p, g[0]); }
+template <>
+__device__ __forceinline__ void red_add_cap<2>(float* p, const float (&g)[2]) { red_add_f2(p, g[0], g[1]); }
+template <>
+__device__ __forceinline__ void red_add_cap<4>(float* p, const float (&g)[4]) {
+    red_add_f4(p, g[0], g[1], g[2], g[3]);
+}
+template <>
+__device__ __forceinline__ void red_add_cap<8>(float* p, const float (&g)[8]) {
+    red_add_f4(p, g[0], g[1], g[2], g[3]);
+    red_add_f4(p + 4, g[4], g[5], g[6], g[7]);
+}
+
+template <int K, int U>
+__global__ void __launch_bounds__(32)
+sspmm_bwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
+                        const float* __restrict__ val, const float* __restrict__ dy,
+                        const uint16_t* __restrict__ bk_slot, float* __restrict__ dxs, int d,
+                        int rows) {
+    constexpr int CAP = K / 8;
+    extern __shared__ __align__(16) float sm[];  // 32*rows replicated cells, then d floats of dY
+    float* __restrict__ cells = sm;
+    float* __restrict__ tmp = sm + 32 * rows;
+    const int lane = lane_id();
+    const int g = lane >> 3;
+    const int t = lane & 7;
+    const mk_part rec = parts[blockIdx.x];
+    if (rec.len == 0) return;
+
+    const float* __restrict__ dyr = dy + static_cast<int64_t>(rec.row) * d;
+    for (int c = lane * 4; c < d; c += 128)
+        *reinterpret_cast<float4*>(tmp + c) = ld_stream_f4(dyr + c);
+    __syncwarp();
+    const int ra = (d + 7) >> 3;
+    for (int row = 0; row < ra; ++row)  // copy A: column 8*row + t in bank t of every group
+        cells[32 * row + lane] = tmp[8 * row + t];
+    for (int row = ra; row < rows; ++row) {  // copy B: column 64h + 8*t + l in bank t
+        const int rb = row - ra;
+        const int c = ((rb >> 3) << 6) + (t << 3) + (rb & 7);
+        cells[32 * row + lane] = c < d ? tmp[c] : 0.f;
+    }
+    __syncwarp();
+
+    const float* __restrict__ my = cells + 8 * g;
+    const int end = rec.loc + rec.len;
+    for (int base = rec.loc; base < end; base += 32) {
+        const int n_here = min(32, end - base);
+        int my_nz = 0;
+        float my_v = 0.f;
+        if (lane < n_here) {
+            my_nz = ld_stream_i1(idx + base + lane);
+            my_v = ld_stream_f1(val + base + lane);
+        }
+        for (int i = 0; i < n_here; i += 4 * U) {
+            int sl[U][CAP];
+            int nzv[U];
+            float vv[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = i + u * 4 + g;
+                nzv[u] = __shfl_sync(kFull, my_nz, e & 31);
+                vv[u] = __shfl_sync(kFull, my_v, e & 31);
+                ok[u] = e < n_here;
+                if (ok[u])
+                    BankedLoad<CAP>::slots(bk_slot + static_cast<int64_t>(nzv[u]) * K + CAP * t, sl[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (ok[u]) {
+                    float gq[CAP];
+#pragma unroll
+                    for (int q = 0; q < CAP; ++q) gq[q] = vv[u] * my[sl[u][q]];
+                    red_add_cap<CAP>(dxs + static_cast<int64_t>(nzv[u]) * K + CAP * t, gq);
+                }
+            }
+        }
+    }
+}
+
+template <int K>
+static int launch_fwd_banked(const mk_part* parts, int64_t num_parts, const int* idx,
+                             const float* val, const float* bk_data, const uint16_t* bk_slot,
+                             float* out, float* partial, int d, int rows, cudaStream_t st) {
+    constexpr int U = K >= 64 ? 2 : (K == 32 ? 4 : 8);
+    const size_t smem = static_cast<size_t>(32) * rows * 4;
+    auto kern = spgemm_fwd_banked_kernel<K, U>;
+    if (smem > 48 * 1024)
+        MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    kern<<<static_cast<unsigned>(num_parts), 32, smem, st>>>(parts, idx, val, bk_data, bk_slot, out,
+                                                             partial, d, rows);
+    MK_LAUNCH_CHECK("spgemm_fwd_banked_kernel");
+    return MK_OK;
+}
+
+template <int K>
+static int launch_bwd_banked(const mk_part* parts, int64_t num_parts, const int* idx,
+                             const float* val, const float* dy, const uint16_t* bk_slot, float* dxs,
+                             int d, int rows, cudaStream_t st) {
+    constexpr int U = K >= 64 ? 4 : 8;
+    const size_t smem = (static_cast<size_t>(32) * rows + d) * 4;
+    auto kern = sspmm_bwd_banked_kernel<K, U>;
+    if (smem > 48 * 1024)
+        MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    kern<<<static_cast<unsigned>(num_parts), 32, smem, st>>>(parts, idx, val, dy, bk_slot, dxs, d,
+                                                             rows);
+    MK_LAUNCH_CHECK("sspmm_bwd_banked_kernel");
+    return MK_OK;
+}
+
+int launch_fold(const mk_part* parts, int64_t num_parts, const float* partial, float* out, int d,
+                cudaStream_t st);  // spgemm_fwd.cu
+
+}  // namespace mk
+
+extern "C" int mk_banked_supported(int k, int d);
+extern "C" int mk_banked_rows(int d);
+
+extern "C" int mk_spgemm_fwd_banked(const mk_part* parts, int64_t num_parts, int64_t num_slots,
+                                    const int32_t* idx, const float* val, const float* bk_data,
+                                    const uint16_t* bk_slot, float* out, float* partial,
+                                    int64_t n_rows, int k, int d, void* stream) {
+    if (n_rows < 0 || num_parts < 0 || num_slots < 0 || d < 1 || k < 1 || k > d) return MK_EINVAL;
+    if (!mk_banked_supported(k, d)) return MK_EUNSUPPORTED;
+    if (n_rows == 0 || num_parts == 0) return MK_OK;
+    if (!parts || !out || !bk_data || !bk_slot) return MK_EINVAL;
+    if (num_slots > 0 && !partial) return MK_EINVAL;
+    if (num_parts > 0x7fffffffLL) return MK_EUNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(out) % 16 || reinterpret_cast<uintptr_t>(bk_data) % 16 ||
+        reinterpret_cast<uintptr_t>(bk_slot) % 16 || (partial && reinterpret_cast<uintptr_t>(partial) % 16))
+        return MK_EINVAL;
+    cudaStream_t st = mk::as_stream(stream);
+    const int rows = mk_banked_rows(d);
+    int rc;
+    switch (k) {
+        case 8: rc = mk::launch_fwd_banked<8>(parts, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, st); break;
+        case 16: rc = mk::launch_fwd_banked<16>(parts, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, st); break;
+        case 32: rc = mk::launch_fwd_banked<32>(parts, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, st); break;
+        default: rc = mk::launch_fwd_banked<64>(parts, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, st); break;
+    }
+    if (rc != MK_OK) return rc;
+    if (num_slots > 0) return mk::launch_fold(parts, num_parts, partial, out, d, st);
+    return MK_OK;
+}
+
+extern "C" int mk_sspmm_bwd_banked(const mk_part* parts, int64_t num_parts, const int32_t* idx,
+                                   const float* val, const float* dy, const uint16_t* bk_slot,
+                                   float* dxs, int64_t n_rows, int64_t n_src, int k, int d,
+                                   void* stream) {
+    if (n_rows < 0 || n_src < 0 || num_parts < 0 || d < 1 || k < 1 || k > d) return MK_EINVAL;
+    if (!mk_banked_supported(k, d)) return MK_EUNSUPPORTED;
+    if (n_src == 0) return MK_OK;
+    if (!dxs) return MK_EINVAL;
+    cudaStream_t st = mk::as_stream(stream);
+    MK_CUDA_TRY(cudaMemsetAsync(dxs, 0, static_cast<size_t>(n_src) * k * sizeof(float), st));
+    if (n_rows == 0 || num_parts == 0) return MK_OK;
+    if (!parts || !dy || !bk_slot) return MK_EINVAL;
+    if (num_parts > 0x7fffffffLL) return MK_EUNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(dxs) % 16 || reinterpret_cast<uintptr_t>(dy) % 16 ||
+        reinterpret_cast<uintptr_t>(bk_slot) % 16)
+        return MK_EINVAL;
+    const int rows = mk_banked_rows(d);
+    switch (k) {
+        case 8: return mk::launch_bwd_banked<8>(parts, num_parts, idx, val, dy, bk_slot, dxs, d, rows, st);
+        case 16: return mk::launch_bwd_banked<16>(parts, num_parts, idx, val, dy, bk_slot, dxs, d, rows, st);
+        case 32: return mk::launch_bwd_banked<32>(parts, num_parts, idx, val, dy, bk_slot, dxs, d, rows, st);
+        default: return mk::launch_bwd_banked<64>(parts, num_parts, idx, val, dy, bk_slot, dxs, d, rows, st);
+    }
+}

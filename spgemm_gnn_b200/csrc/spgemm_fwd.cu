@@ -302,6 +302,14 @@ spgemm_fold_kernel(const mk_part* __restrict__ parts, int64_t num_parts,
     }
 }
 
+int launch_fold(const mk_part* parts, int64_t num_parts, const float* partial, float* out, int d,
+                cudaStream_t st) {
+    const int64_t blocks = (num_parts * 32 + 255) / 256;
+    spgemm_fold_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(parts, num_parts, partial, out, d);
+    MK_LAUNCH_CHECK("spgemm_fold_kernel");
+    return MK_OK;
+}
+
 template <int K, typename IdxT>
 static int launch_fwd_k(const mk_part* parts, int64_t num_parts, const int* idx, const float* val,
                         const float* sp_data, const void* sp_index, float* out, float* partial,
@@ -422,11 +430,6 @@ extern "C" int mk_spgemm_fwd(const mk_part* parts, int64_t num_parts, int64_t nu
                        : mk::launch_fwd<uint16_t>(parts, num_parts, idx, val, sp_data, sp_index,
                                                   out, partial, k, d, st);
     if (rc != MK_OK) return rc;
-    if (num_slots > 0) {
-        const int64_t blocks = (num_parts * 32 + 255) / 256;
-        mk::spgemm_fold_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(parts, num_parts,
-                                                                              partial, out, d);
-        MK_LAUNCH_CHECK("spgemm_fold_kernel");
-    }
+    if (num_slots > 0) return mk::launch_fold(parts, num_parts, partial, out, d, st);
     return MK_OK;
 }

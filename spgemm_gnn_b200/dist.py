@@ -83,6 +83,15 @@ def allgather_cbsr(sp_data: torch.Tensor, sp_index: torch.Tensor, group=None):
     return full_data, full_index
 
 
+def allgather_rows(local: torch.Tensor, group=None) -> torch.Tensor:
+    """[R,k] of any dtype -> [P*R,k] (moved as raw bytes)."""
+    world = dist.get_world_size(group)
+    full = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
+                       device=local.device)
+    dist.all_gather_into_tensor(full.view(torch.uint8), local.contiguous().view(torch.uint8), group=group)
+    return full
+
+
 def reduce_scatter_rows(full: torch.Tensor, group=None) -> torch.Tensor:
     """[P*R,k] per-rank partial sums -> [R,k] summed rows of this rank."""
     world = dist.get_world_size(group)
@@ -114,29 +123,56 @@ def allreduce_grads(params: Iterable[torch.nn.Parameter], group=None) -> None:
 # ---------------------------------------------------------------------------------------
 # the sharded hot path as an autograd Function
 # ---------------------------------------------------------------------------------------
+def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, group=None):
+    """Exchange + local forward SpGEMM of one rank.  Returns (out [num_rows, D], gathered sorted
+    column ids [P*R, k] for the backward).  Where the banked kernels apply, the LOCAL rows are
+    banked first and the banked values + cell offsets are gathered next to the sorted column ids
+    (7 bytes per entry instead of 5), so that no rank re-banks rows it does not own."""
+    from . import maxk_kernels
+    k = sp_data.shape[1]
+    part = maxk_kernels.partition(ptr, num_rows)
+    if maxk_kernels.use_banked(part.num_parts, idx.numel(), k, dim_origin):
+        bk_data, _, bk_slot = maxk_kernels.cbsr_bank(sp_data, sp_index, dim_origin, with_index=False)
+        full_data, full_slot = allgather_cbsr(bk_data, bk_slot, group)
+        full_index = allgather_rows(sp_index, group)
+        out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, full_data, full_slot, num_rows,
+                                                 idx.numel(), k, dim_origin)
+    else:
+        full_data, full_index = allgather_cbsr(sp_data, sp_index, group)
+        out, _ = maxk_kernels.spgemm_forward(ptr, idx, val, full_data, full_index, num_rows,
+                                             idx.numel(), k, dim_origin, allow_banked=False)
+    return out, full_index
+
+
+def sharded_backward(grad_out, full_index, ptr, idx, val, num_rows, dim_origin, group=None):
+    """Local push-form SSpMM into a full-height buffer, folded by one reduce-scatter."""
+    from . import maxk_kernels
+    k = full_index.shape[1]
+    dxs_full = maxk_kernels.spgemm_backward(ptr, idx, val, grad_out, full_index, num_rows,
+                                            idx.numel(), k, dim_origin)
+    return reduce_scatter_rows(dxs_full, group)
+
+
 class DistSpGEMMFunction(Function):
     """Local rows of A x Xs where Xs is row-sharded: all-gather(CBSR) -> spgemm_forward;
     backward: spgemm_backward against the gathered column ids -> reduce-scatter."""
 
     @staticmethod
     def forward(ctx, sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, group):
-        from . import maxk_kernels
-        full_data, full_index = allgather_cbsr(sp_data, sp_index, group)
+        out, full_index = sharded_forward(sp_data.contiguous(), sp_index, ptr, idx, val, num_rows,
+                                          dim_origin, group)
         k = sp_data.shape[1]
-        out, _ = maxk_kernels.spgemm_forward(ptr, idx, val, full_data, full_index, num_rows,
-                                             idx.numel(), k, dim_origin)
         ctx.save_for_backward(full_index, ptr, idx, val)
         ctx.meta = (num_rows, k, dim_origin, group)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        from . import maxk_kernels
         full_index, ptr, idx, val = ctx.saved_tensors
         num_rows, k, dim_origin, group = ctx.meta
-        dxs_full = maxk_kernels.spgemm_backward(ptr, idx, val, grad_out.contiguous(), full_index,
-                                                num_rows, idx.numel(), k, dim_origin)
-        return reduce_scatter_rows(dxs_full, group), None, None, None, None, None, None, None
+        dxs = sharded_backward(grad_out.contiguous(), full_index, ptr, idx, val, num_rows,
+                               dim_origin, group)
+        return dxs, None, None, None, None, None, None, None
 
 
 def dist_maxk_aggregate(local: CSRGraph, val: torch.Tensor, feat: torch.Tensor, k: int,

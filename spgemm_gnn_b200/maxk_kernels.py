@@ -32,9 +32,13 @@ __all__ = [
     "maxk_forward", "maxk_backward", "spgemm_forward", "spgemm_backward",
     "maxk_forward_cbsr", "cbsr_scatter", "cbsr_gather", "partition",
     "clear_partition_cache", "set_max_nz", "get_max_nz", "launch_count",
+    "banked_supported", "cbsr_bank", "maxk_forward_banked", "spgemm_forward_banked",
+    "spgemm_backward_banked", "set_banked", "use_banked",
 ]
 
 _MAX_NZ = int(os.environ.get("MAXK_MAX_NZ", "1024"))
+_BANKED = os.environ.get("MAXK_BANKED", "1") != "0"
+_BANKED_MIN_RECORD = 96   # mean stored entries per work record below which banking does not pay
 _launches = 0  # kernels launched through this module (bench.py reports it)
 
 
@@ -53,6 +57,18 @@ def set_max_nz(max_nz: int) -> None:
 
 def get_max_nz() -> int:
     return _MAX_NZ
+
+
+def set_banked(on: bool) -> None:
+    """Let `spgemm_forward` re-order the CBSR table into the conflict-free banked form first
+    (csrc/bank.cu).  Same result; on by default where it is faster."""
+    global _BANKED
+    _BANKED = bool(on)
+
+
+def use_banked(num_parts: int, num_edges: int, dim_sparse: int, dim_origin: int) -> bool:
+    return (_BANKED and banked_supported(dim_sparse, dim_origin)
+            and num_edges >= _BANKED_MIN_RECORD * max(num_parts, 1))
 
 
 def _stream() -> int:
@@ -239,7 +255,8 @@ def _check_graph(ptr, idx, val):
     _chk(val.dtype == torch.float32, "val must be float32")
 
 
-def spgemm_forward(ptr, idx, val, sp_data, sp_index, num_nodes, num_edges, dim_sparse, dim_origin):
+def spgemm_forward(ptr, idx, val, sp_data, sp_index, num_nodes, num_edges, dim_sparse, dim_origin,
+                   *, allow_banked: bool = True):
     """out[r, sp_index[j,t]] += val[e] * sp_data[j,t] over the stored entries e=(r<-j) of the
     CSR (ptr, idx, val).  Returns `(out fp32 [num_nodes, dim_origin], sp_index)` like the
     reference (spgemm_forward_cuda, maxk_cuda_kernels.o@0x1260)."""
@@ -254,6 +271,11 @@ def spgemm_forward(ptr, idx, val, sp_data, sp_index, num_nodes, num_edges, dim_s
     _chk(idx.numel() >= num_edges and val.numel() >= num_edges, "idx/val must hold num_edges entries")
     ib = _index_bytes(sp_index, dim_origin)
     part = partition(ptr, num_nodes)
+    if allow_banked and use_banked(part.num_parts, num_edges, dim_sparse, dim_origin):
+        bk_data, _, bk_slot = cbsr_bank(sp_data, sp_index, dim_origin, with_index=False)
+        out = spgemm_forward_banked(ptr, idx, val, bk_data, bk_slot, num_nodes, num_edges,
+                                    dim_sparse, dim_origin)
+        return out, sp_index
     out = torch.empty((num_nodes, dim_origin), dtype=torch.float32, device=sp_data.device)
     partial = part.partial_for(dim_origin, sp_data.device)
     with torch.cuda.device(sp_data.device):
@@ -291,4 +313,91 @@ def spgemm_backward(ptr, idx, val, grad_output, sp_index, num_nodes, num_edges, 
             dim_sparse, dim_origin, _stream())
     _lib.check(rc, "mk_sspmm_bwd")
     _launches += 2  # memset + kernel
+    return dxs
+
+
+# ---------------------------------------------------------------------------------------
+# banked CBSR: the conflict-free internal form (not in the reference; see csrc/bank.cu)
+# ---------------------------------------------------------------------------------------
+def banked_supported(k: int, dim_origin: int) -> bool:
+    return bool(_lib.lib().mk_banked_supported(int(k), int(dim_origin)))
+
+
+def cbsr_bank(sp_data: torch.Tensor, sp_index: torch.Tensor, dim_origin: int, with_index: bool = True):
+    """(sp_data, sp_index) -> (bk_data, bk_index, bk_slot): every row re-ordered and every entry
+    given one of two shared-memory cells so that the aggregation kernels run without bank
+    conflicts.  `(bk_data, bk_index)` is the same CBSR row in another entry order; with
+    `with_index=False` bk_index is not produced (the forward kernel does not read it)."""
+    global _launches
+    _cuda_contig(sp_data, "sp_data")
+    _cuda_contig(sp_index, "sp_index")
+    _chk(sp_data.dtype == torch.float32, "sp_data must be float32")
+    _chk(sp_data.dim() == 2 and sp_index.shape == sp_data.shape, "sp_index must have the shape of sp_data")
+    n, k = sp_data.shape
+    _chk(banked_supported(k, dim_origin), "banked CBSR needs k in {8,16,32,64}, dim % 8 == 0, dim <= 512")
+    ib = _index_bytes(sp_index, dim_origin)
+    bk_data = torch.empty_like(sp_data)
+    bk_index = torch.empty_like(sp_index) if with_index else None
+    bk_slot = torch.empty((n, k), dtype=torch.int16, device=sp_data.device)
+    with torch.cuda.device(sp_data.device):
+        rc = _lib.lib().mk_cbsr_bank(sp_data.data_ptr(), sp_index.data_ptr(), ib, bk_data.data_ptr(),
+                                     bk_index.data_ptr() if with_index else None, bk_slot.data_ptr(),
+                                     n, k, dim_origin, _stream())
+    _lib.check(rc, "mk_cbsr_bank")
+    _launches += 1
+    return bk_data, bk_index, bk_slot
+
+
+def maxk_forward_banked(input: torch.Tensor, k: int):
+    """top-k -> CBSR -> banked form in one call: (bk_data, bk_index, bk_slot)."""
+    sp_data, sp_index = maxk_forward_cbsr(input, k)
+    return cbsr_bank(sp_data, sp_index, input.shape[1])
+
+
+def spgemm_forward_banked(ptr, idx, val, bk_data, bk_slot, num_nodes, num_edges, dim_sparse, dim_origin):
+    """`spgemm_forward` on a banked table: same result, no shared-memory bank conflicts."""
+    global _launches
+    _check_graph(ptr, idx, val)
+    _cuda_contig(bk_data, "sp_data")
+    _cuda_contig(bk_slot, "sp_index")
+    _chk(bk_data.dtype == torch.float32, "sp_data must be float32")
+    _chk(bk_slot.dtype in (torch.int16, torch.uint16) and bk_slot.shape == bk_data.shape,
+         "bk_slot must be 16-bit with the shape of bk_data")
+    _chk(bk_data.shape[1] == dim_sparse, "dim_sparse must equal sp_data.size(1)")
+    part = partition(ptr, num_nodes)
+    out = torch.empty((num_nodes, dim_origin), dtype=torch.float32, device=bk_data.device)
+    partial = part.partial_for(dim_origin, bk_data.device)
+    with torch.cuda.device(bk_data.device):
+        rc = _lib.lib().mk_spgemm_fwd_banked(
+            part.parts.data_ptr(), part.num_parts, part.num_slots, idx.data_ptr(), val.data_ptr(),
+            bk_data.data_ptr(), bk_slot.data_ptr(), out.data_ptr(),
+            partial.data_ptr() if partial is not None else None, num_nodes, dim_sparse, dim_origin,
+            _stream())
+    _lib.check(rc, "mk_spgemm_fwd_banked")
+    _launches += 1 + (1 if part.num_slots else 0)
+    return out
+
+
+def spgemm_backward_banked(ptr, idx, val, grad_output, bk_slot, num_nodes, num_edges, dim_sparse, dim_origin):
+    """`spgemm_backward` on a banked table; the [n_src, k] gradient comes out in the BANKED entry
+    order (pair it with bk_index)."""
+    global _launches
+    _check_graph(ptr, idx, val)
+    _cuda_contig(grad_output, "grad_output")
+    _cuda_contig(bk_slot, "sp_index")
+    _chk(grad_output.dtype == torch.float32, "grad_output must be float32")
+    _chk(grad_output.dim() == 2 and grad_output.shape[0] == num_nodes and grad_output.shape[1] == dim_origin,
+         "grad_output must be [num_nodes, dim_origin]")
+    _chk(bk_slot.dtype in (torch.int16, torch.uint16) and bk_slot.shape[1] == dim_sparse,
+         "bk_slot must be 16-bit [n_src, dim_sparse]")
+    n_src = bk_slot.shape[0]
+    part = partition(ptr, num_nodes)
+    dxs = torch.empty((n_src, dim_sparse), dtype=torch.float32, device=grad_output.device)
+    with torch.cuda.device(grad_output.device):
+        rc = _lib.lib().mk_sspmm_bwd_banked(
+            part.parts.data_ptr(), part.num_parts, idx.data_ptr(), val.data_ptr(),
+            grad_output.data_ptr(), bk_slot.data_ptr(), dxs.data_ptr(), num_nodes, n_src,
+            dim_sparse, dim_origin, _stream())
+    _lib.check(rc, "mk_sspmm_bwd_banked")
+    _launches += 2
     return dxs

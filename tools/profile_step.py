@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Small driver for ncu: W warm-up steps then S steps of (spgemm_forward, spgemm_backward) on one
-of the BASELINE shapes.  Also times each with CUDA events (ignored under ncu)."""
+"""Small driver for ncu / timing: W warm-up steps then S steps of (forward SpGEMM, backward SSpMM)
+on one of the BASELINE shapes, plain or banked.  Times each with CUDA events."""
 import argparse
 import os
 import sys
@@ -19,7 +19,7 @@ ap.add_argument("--dim", type=int, default=256)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--max-nz", type=int, default=None)
-ap.add_argument("--with-maxk", action="store_true")
+ap.add_argument("--plain", action="store_true", help="unbanked kernels")
 a = ap.parse_args()
 if a.max_nz:
     mk.set_max_nz(a.max_nz)
@@ -30,17 +30,24 @@ gen = torch.Generator(device="cuda").manual_seed(97)
 x = torch.randn(n, a.dim, device="cuda", generator=gen)
 dy = torch.randn(n, a.dim, device="cuda", generator=gen)
 sd, si = mk.maxk_forward_cbsr(x, a.k)
-ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+banked = not a.plain and mk.banked_supported(a.k, a.dim)
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 for it in range(a.warmup + a.steps):
-    if a.with_maxk:
-        sd, si = mk.maxk_forward_cbsr(x, a.k)
     ev[0].record()
-    out, _ = mk.spgemm_forward(g.indptr, g.indices, val, sd, si, n, e, a.k, a.dim)
+    if banked:
+        bd, bi, bs = mk.cbsr_bank(sd, si, a.dim)
     ev[1].record()
-    dxs = mk.spgemm_backward(g.indptr, g.indices, val, dy, si, n, e, a.k, a.dim)
+    if banked:
+        out = mk.spgemm_forward_banked(g.indptr, g.indices, val, bd, bs, n, e, a.k, a.dim)
+    else:
+        out, _ = mk.spgemm_forward(g.indptr, g.indices, val, sd, si, n, e, a.k, a.dim)
     ev[2].record()
-    if a.with_maxk:
-        dx = mk.cbsr_scatter(dxs, si, a.dim)
+    if banked:
+        dxs = mk.spgemm_backward_banked(g.indptr, g.indices, val, dy, bs, n, e, a.k, a.dim)
+    else:
+        dxs = mk.spgemm_backward(g.indptr, g.indices, val, dy, si, n, e, a.k, a.dim)
+    ev[3].record()
 torch.cuda.synchronize()
-print(f"{a.workload} N={n} E={e} k={a.k} D={a.dim} max_nz={mk.get_max_nz()}: "
-      f"fwd {ev[0].elapsed_time(ev[1]):.3f} ms  bwd {ev[1].elapsed_time(ev[2]):.3f} ms")
+print(f"{a.workload} N={n} E={e} k={a.k} D={a.dim} max_nz={mk.get_max_nz()} "
+      f"{'banked' if banked else 'plain'}: bank {ev[0].elapsed_time(ev[1]):.3f} ms  "
+      f"fwd {ev[1].elapsed_time(ev[2]):.3f} ms  bwd {ev[2].elapsed_time(ev[3]):.3f} ms")
