@@ -175,6 +175,34 @@ class DistSpGEMMFunction(Function):
         return dxs, None, None, None, None, None, None, None
 
 
+class ShardedGraph(CSRGraph):
+    """One rank's row block of a graph, usable wherever the layers and models take a `CSRGraph`:
+    the aggregation then goes through `DistSpGEMMFunction` (all-gather / reduce-scatter).
+    Built from the FULL graph so that the per-edge weights use global degrees."""
+
+    def __init__(self, full: CSRGraph, rank: int, world: int, group=None):
+        local, r0, r1 = shard_graph(full, rank, world)
+        super().__init__(local.indptr, local.indices, local.num_src)
+        self.rank, self.world, self.group = rank, world, group
+        self.row_begin, self.row_end = r0, r1
+        self.global_nodes = full.num_nodes()
+        self.rows_per_rank = rows_per_rank(full.num_nodes(), world)
+        self._weights = {k: shard_edge_weights(full, local, r0, r1, k) for k in ("mean", "both", "sum")}
+        self._cache["symmetric"] = False
+        # padded rows are empty by construction; only real rows count for GraphConv's check
+        self._cache["has_zero_in"] = bool((self.in_degrees()[: r1 - r0] == 0).any())
+
+    def edge_weights(self, kind: str) -> torch.Tensor:
+        kind = {"right": "mean", "none": "sum"}.get(kind, kind)
+        return self._weights[kind]
+
+    def local_rows(self, t: torch.Tensor) -> torch.Tensor:
+        """Rows [row_begin, row_end) of a full-height tensor, zero-padded to rows_per_rank."""
+        out = t.new_zeros((self.rows_per_rank,) + tuple(t.shape[1:]))
+        out[: self.row_end - self.row_begin] = t[self.row_begin:self.row_end]
+        return out
+
+
 def dist_maxk_aggregate(local: CSRGraph, val: torch.Tensor, feat: torch.Tensor, k: int,
                         group=None) -> torch.Tensor:
     """Sharded MaxK -> CBSR -> all-gather -> SpGEMM for the rank's (padded) rows."""

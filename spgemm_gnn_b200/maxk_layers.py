@@ -102,16 +102,32 @@ class SpGEMMFunction(Function):
         return dxs, None, None, None, None, None, None
 
 
+def aggregate_cbsr(graph: CSRGraph, sp_data, sp_index, weight_kind: str, dim_origin: int):
+    """A x Xs for a CBSR table; on a `dist.ShardedGraph` the table is row-sharded and the call
+    includes the all-gather (forward) and the reduce-scatter (backward)."""
+    val = graph.edge_weights(weight_kind)
+    if getattr(graph, "world", 1) > 1:
+        from .dist import DistSpGEMMFunction
+        return DistSpGEMMFunction.apply(sp_data, sp_index, graph.indptr, graph.indices, val,
+                                        graph.num_nodes(), dim_origin, graph.group)
+    return SpGEMMFunction.apply(sp_data, sp_index, graph.indptr, graph.indices, val,
+                                graph.num_nodes(), dim_origin)
+
+
 def maxk_aggregate(graph: CSRGraph, feat: torch.Tensor, k: int, weight_kind: str) -> torch.Tensor:
     """MaxK -> CBSR -> SpGEMM in one go: sum_j w(i<-j) * maxk(feat)[j].  The hot path."""
     sp_data, sp_index = MaxKCBSRFunction.apply(feat, k)
-    return SpGEMMFunction.apply(sp_data, sp_index, graph.indptr, graph.indices,
-                                graph.edge_weights(weight_kind), graph.num_nodes(), feat.shape[1])
+    return aggregate_cbsr(graph, sp_data, sp_index, weight_kind, feat.shape[1])
 
 
 def _dense_aggregate(graph: CSRGraph, feat: torch.Tensor, weight_kind: str) -> torch.Tensor:
     """Non-MaxK (`--nonlinear relu`) branch: dense SpMM through cuSPARSE, the comparator the
     reference reports its speed-ups against (README.md:136).  Not the hot path."""
+    if getattr(graph, "world", 1) > 1:  # comparator path only: gather the dense rows
+        import torch.distributed as dist
+        full = torch.empty((graph.num_src, feat.shape[1]), dtype=feat.dtype, device=feat.device)
+        dist.all_gather_into_tensor(full, feat.contiguous(), group=graph.group)
+        feat = full
     key = ("adj", weight_kind)
     adj = graph._cache.get(key)
     if adj is None:

@@ -25,12 +25,11 @@ import torch.nn.init as init
 from torch.nn import Linear
 
 from .maxk_layers import (CBSRToDenseFunction, MaxKCBSRFunction, MaxKFunction, MaxKGCNConv,
-                          MaxKGINConv, MaxKSAGEConv, SpGEMMFunction, _dense_aggregate)
+                          MaxKGINConv, MaxKSAGEConv, _dense_aggregate, aggregate_cbsr)
 
 
 def _aggregate_cbsr(g, sp_data, sp_index, kind, dim):
-    return SpGEMMFunction.apply(sp_data, sp_index, g.indptr, g.indices, g.edge_weights(kind),
-                                g.num_nodes(), dim)
+    return aggregate_cbsr(g, sp_data, sp_index, kind, dim)
 
 
 # ---------------------------------------------------------------------------------------

@@ -39,20 +39,37 @@ def synthetic_task(name: str, scale: float, device, seed: int = 97):
 def train_epochs(model: nn.Module, g: CSRGraph, feats, labels, train_mask, epochs: int,
                  lr: float = 0.01, weight_decay: float = 0.0, eval_every: int = 0, log=None):
     """The loop of maxk_gnn_dgl.py:98-134: one full-graph forward + backward per epoch (+ an
-    eval forward every `eval_every` epochs).  Returns (losses, seconds per epoch)."""
+    eval forward every `eval_every` epochs).  Returns (losses, seconds per epoch).
+
+    With a `dist.ShardedGraph` every rank passes ITS rows of feats / labels / mask: the loss is
+    the sum over the local train nodes divided by the global count, the weight gradients are
+    all-reduced, and every rank takes the same optimizer step."""
     opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=lr,
                            weight_decay=weight_decay)
     losses, times = [], []
     cuda = feats.is_cuda
+    sharded = getattr(g, "world", 1) > 1
+    if sharded:
+        import torch.distributed as dist
+        from .dist import allreduce_grads
+        count = train_mask.sum().to(torch.float32)
+        dist.all_reduce(count, group=g.group)
     for ep in range(epochs):
         model.train()
         if cuda:
             torch.cuda.synchronize()
         t0 = time.perf_counter()
         logits = model(g, feats)
-        loss = F.cross_entropy(logits[train_mask], labels[train_mask])
+        if sharded:
+            loss = F.cross_entropy(logits[train_mask], labels[train_mask], reduction="sum") / count
+        else:
+            loss = F.cross_entropy(logits[train_mask], labels[train_mask])
         opt.zero_grad(set_to_none=True)
         loss.backward()
+        if sharded:
+            allreduce_grads(model.parameters(), g.group)
+            loss = loss.detach().clone()
+            dist.all_reduce(loss, group=g.group)
         opt.step()
         if eval_every and (ep + 1) % eval_every == 0:
             model.eval()
@@ -84,25 +101,44 @@ def main(argv=None):
     ap.add_argument("--gpu", type=int, default=0)
     ap.add_argument("--seed", type=int, default=97)
     ap.add_argument("--tf32", action="store_true", help="TF32 GEMMs as maxk_gnn_dgl.py:30-33")
+    ap.add_argument("--eval_every", type=int, default=1, help="eval forward every n epochs (reference: 1)")
+    ap.add_argument("--verbose", action="store_true")
     a = ap.parse_args(argv)
     if not torch.cuda.is_available():
         raise SystemExit("training needs a CUDA device: the aggregation has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:
+        a.gpu = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(a.gpu)
     dev = torch.device("cuda", a.gpu)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(a.seed)
     torch.backends.cuda.matmul.allow_tf32 = a.tf32
     torch.backends.cudnn.allow_tf32 = a.tf32
     g, feats, labels, train_mask, _, _, in_feats, classes = synthetic_task(a.dataset, a.scale, dev, a.seed)
     model = MODELS[a.model](in_feats, a.hidden_dim, a.hidden_layers, classes, maxk=a.maxk,
                             feat_drop=a.dropout, norm=a.norm, nonlinear=a.nonlinear).to(dev)
-    print(f"{a.dataset}: {g.num_nodes()} nodes, {g.num_edges()} edges; model {a.model} "
-          f"{sum(p.numel() for p in model.parameters())} params")
+    n_nodes, n_edges = g.num_nodes(), g.num_edges()
+    if world > 1:  # 1-D row partition: every rank keeps its rows of the graph and of the node data
+        from .dist import ShardedGraph
+        sg = ShardedGraph(g, rank, world)
+        feats, labels, train_mask = sg.local_rows(feats), sg.local_rows(labels), sg.local_rows(train_mask)
+        g = sg
+    say = print if rank == 0 else (lambda *_: None)
+    say(f"{a.dataset}: {n_nodes} nodes, {n_edges} edges; model {a.model} "
+        f"{sum(p.numel() for p in model.parameters())} params; {world} GPU(s)")
     losses, times = train_epochs(model, g, feats, labels, train_mask, a.epochs, a.w_lr,
-                                 a.w_weight_decay, eval_every=1, log=print)
+                                 a.w_weight_decay, eval_every=a.eval_every, log=say if a.verbose else None)
     steady = sorted(times[len(times) // 5:])
-    print(json.dumps({"dataset": a.dataset, "model": a.model, "nonlinear": a.nonlinear, "maxk": a.maxk,
-                      "epochs": a.epochs, "final_loss": losses[-1],
-                      "epoch_ms_median": steady[len(steady) // 2] * 1e3}))
+    say(json.dumps({"dataset": a.dataset, "model": a.model, "nonlinear": a.nonlinear, "maxk": a.maxk,
+                    "gpus": world, "epochs": a.epochs, "first_loss": losses[0], "final_loss": losses[-1],
+                    "epoch_ms_median": steady[len(steady) // 2] * 1e3,
+                    "eval_forward_per_epoch": bool(a.eval_every)}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
