@@ -10,7 +10,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libmaxk_b200.so")
+SO_PATH = os.environ.get("MAXK_LIB") or os.path.join(HERE, "libmaxk_b200.so")
 
 MK_OK, MK_EINVAL, MK_EUNSUPPORTED, MK_ECUDA, MK_ENODEVICE = 0, -1, -2, -3, -4
 

@@ -35,16 +35,20 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defs=(), out: str = None) -> str:
+    """`defs` / `out` build an experimental variant (extra -D flags) next to the product library;
+    `MAXK_LIB=<path>` makes `_lib` load it (tuning runs only)."""
+    so = out or SO
+    if not defs and not out and not force and not _stale():
         return SO
     nvcc = nvcc_path()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if not out else "build_" + os.path.basename(out))
     os.makedirs(objdir, exist_ok=True)
     common = [
         nvcc, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden",
         "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-ccbin", "/usr/bin/g++",
     ]
+    common += list(defs)
     if verbose:
         common += ["-Xptxas", "-v"]
     objs = []
@@ -63,9 +67,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed")
     subprocess.check_call([nvcc, *ARCH, "-shared", "-cudart", "static", "-ccbin", "/usr/bin/g++",
-                           "-o", SO] + objs)
-    return SO
+                           "-o", so] + objs)
+    return so
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    out = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")), None)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defs=defs, out=out))

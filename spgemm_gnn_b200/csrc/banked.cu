@@ -111,8 +111,12 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
             for (int u = 0; u < U; ++u) {
                 if (ok[u]) {
 #pragma unroll
-                    for (int q = 0; q < CAP; ++q)
+                    for (int q = 0; q < CAP; ++q) {
                         if (dv[u][q] != 0.0f) my[sl[u][q]] += vv[u] * dv[u][q];
+#ifdef MK_SYNCWARP_STEPS
+                        __syncwarp();
+#endif
+                    }
                 }
             }
         }
@@ -245,7 +249,11 @@ template <int K>
 static int launch_fwd_banked(const mk_part* parts, int64_t num_parts, const int* idx,
                              const float* val, const float* bk_data, const uint16_t* bk_slot,
                              float* out, float* partial, int d, int rows, cudaStream_t st) {
+#ifdef MK_FWD_U
+    constexpr int U = MK_FWD_U;
+#else
     constexpr int U = K >= 64 ? 2 : (K == 32 ? 4 : 8);
+#endif
     const size_t smem = static_cast<size_t>(32) * rows * 4;
     auto kern = spgemm_fwd_banked_kernel<K, U>;
     if (smem > 48 * 1024)

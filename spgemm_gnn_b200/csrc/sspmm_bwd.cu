@@ -120,7 +120,11 @@ template <int K, typename IdxT>
 static int launch_bwd_k(const mk_part* parts, int64_t num_parts, const int* idx, const float* val,
                         const float* dy, const void* sp_index, float* dxs, int d,
                         cudaStream_t st) {
+#ifdef MK_BWD_U
+    constexpr int U = MK_BWD_U;
+#else
     constexpr int U = 8;
+#endif
     const int dpad = (d + 3) & ~3;
     const size_t smem = static_cast<size_t>(dpad) * 4;
     if (smem > 200 * 1024) return MK_EUNSUPPORTED;

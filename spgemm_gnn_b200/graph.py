@@ -164,6 +164,42 @@ class CSRGraph:
         return CSRGraph(ptr, self.indices[lo:hi].contiguous(), self.num_src)
 
 
+FILE_MAGIC = "maxk-b200-graph-v1"
+
+
+def save_graph(g: CSRGraph, path: str, max_nz: int = None) -> None:
+    """On-disk form of a graph for the hot path: CSR plus, when a CUDA device is present, the work
+    records of `mk_partition` -- the successor of the reference's `<graph>.warp4` file (read by
+    `cuda_read_array<int>` on EVERY kernel call there, so@0x24d16; read once here)."""
+    import numpy as np
+    blob = {"magic": np.array(FILE_MAGIC), "indptr": g.indptr.cpu().numpy(),
+            "indices": g.indices.cpu().numpy(), "num_src": np.int64(g.num_src),
+            "symmetric": np.bool_(g._cache.get("symmetric", False))}
+    if g.indptr.is_cuda:
+        from . import maxk_kernels
+        part = maxk_kernels.partition(g.indptr, g.num_nodes(), max_nz)
+        blob.update(parts=part.parts[: part.num_parts].cpu().numpy(), num_slots=np.int64(part.num_slots),
+                    max_nz=np.int64(part.max_nz))
+    np.savez(path, **blob)
+
+
+def load_graph(path: str, device="cpu") -> CSRGraph:
+    """Inverse of `save_graph`; stored work records are installed in the partition cache so that
+    the first kernel call does not rebuild them."""
+    import numpy as np
+    z = np.load(path if path.endswith(".npz") else path + ".npz")
+    if str(z["magic"]) != FILE_MAGIC:
+        raise ValueError(f"{path}: not a {FILE_MAGIC} file")
+    g = CSRGraph(torch.from_numpy(z["indptr"]).to(device), torch.from_numpy(z["indices"]).to(device),
+                 int(z["num_src"]))
+    g._cache["symmetric"] = bool(z["symmetric"])
+    if "parts" in z.files and torch.device(device).type == "cuda":
+        from . import maxk_kernels
+        maxk_kernels.install_partition(g.indptr, g.num_nodes(), int(z["max_nz"]),
+                                       torch.from_numpy(z["parts"]).to(device), int(z["num_slots"]))
+    return g
+
+
 def from_edges(dst: torch.Tensor, src: torch.Tensor, num_nodes: int, *, symmetric=False) -> CSRGraph:
     """CSR from an edge list dst<-src.  Duplicate edges are merged, neighbours sorted."""
     key = dst.to(torch.int64) * num_nodes + src.to(torch.int64)
@@ -269,6 +305,8 @@ __all__ = [
     "SHAPES",
     "FEATS",
     "from_edges",
+    "save_graph",
+    "load_graph",
     "synthetic_graph",
     "shaped_graph",
     "row_partition_bounds",

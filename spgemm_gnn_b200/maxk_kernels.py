@@ -31,7 +31,7 @@ from . import _lib
 __all__ = [
     "maxk_forward", "maxk_backward", "spgemm_forward", "spgemm_backward",
     "maxk_forward_cbsr", "cbsr_scatter", "cbsr_gather", "partition",
-    "clear_partition_cache", "set_max_nz", "get_max_nz", "launch_count",
+    "clear_partition_cache", "install_partition", "set_max_nz", "get_max_nz", "launch_count",
     "banked_supported", "cbsr_bank", "maxk_forward_banked", "spgemm_forward_banked",
     "spgemm_backward_banked", "set_banked", "use_banked",
 ]
@@ -242,6 +242,21 @@ def partition(ptr: torch.Tensor, num_nodes: int, max_nz: Optional[int] = None) -
     if len(_part_cache) > 64:
         _part_cache.clear()
     _part_cache[key] = p
+    return p
+
+
+def install_partition(ptr: torch.Tensor, num_nodes: int, max_nz: int, parts: torch.Tensor,
+                      num_slots: int) -> _Partition:
+    """Put work records that were built earlier (graph.load_graph) into the cache."""
+    _chk(parts.is_cuda and parts.dtype == torch.int32 and parts.dim() == 2 and parts.shape[1] == 4,
+         "parts must be a CUDA int32 [P,4] tensor")
+    p = _Partition()
+    p.num_parts, p.num_slots, p.max_nz = int(parts.shape[0]), int(num_slots), int(max_nz)
+    p.parts = parts.contiguous()
+    p.partial = None
+    p.ptr_ref = weakref.ref(ptr)
+    p.version = ptr._version
+    _part_cache[(ptr.device.index, ptr.data_ptr(), int(num_nodes), int(max_nz))] = p
     return p
 
 

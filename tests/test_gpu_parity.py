@@ -424,3 +424,18 @@ def test_banked_forward_and_backward(mk, n, avg_deg, d, k, max_nz):
         assert_rel(got, want_b, bound_b, "spgemm_backward_banked")
     finally:
         mk.set_max_nz(1024)
+
+
+def test_graph_file_carries_the_work_records(mk, tmp_path):
+    """f-4: the .warp4 successor -- records saved with the graph are installed, not rebuilt."""
+    from spgemm_gnn_b200 import graph as G
+    g = G.synthetic_graph(3000, 200000, seed=12, device="cuda")
+    p0 = mk.partition(g.indptr, g.num_nodes(), 256)
+    path = str(tmp_path / "g.npz")
+    G.save_graph(g, path, max_nz=256)
+    mk.clear_partition_cache()
+    h = G.load_graph(path, device="cuda")
+    before = mk.launch_count()
+    p1 = mk.partition(h.indptr, h.num_nodes(), 256)
+    assert mk.launch_count() == before                     # served from the installed records
+    assert p1.num_slots == p0.num_slots and torch.equal(p1.parts[: p1.num_parts], p0.parts[: p0.num_parts])

@@ -67,3 +67,16 @@ def test_dgl_surface_used_by_reference_layers():
     with g.local_scope():
         assert int(g.in_degrees().sum()) == g.num_edges() == int(g.out_degrees().sum())
     assert torch.equal(g.in_degrees(), g.out_degrees())      # symmetric graph
+
+
+def test_graph_file_round_trip(tmp_path):
+    g = G.synthetic_graph(200, 1500, seed=4)
+    path = str(tmp_path / "g.npz")
+    G.save_graph(g, path)
+    h = G.load_graph(path)
+    assert torch.equal(g.indptr, h.indptr) and torch.equal(g.indices, h.indices)
+    assert h.num_src == g.num_src and h._cache["symmetric"] is True
+    import numpy as np
+    np.savez(str(tmp_path / "bad.npz"), magic=np.array("nope"))
+    with pytest.raises(ValueError):
+        G.load_graph(str(tmp_path / "bad.npz"))

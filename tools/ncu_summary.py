@@ -63,7 +63,11 @@ def main():
             table.append(r)
     if kern:
         blocks.append((kern, table))
+    seen = set()
     for kern, table in blocks:
+        if kern in seen:
+            continue
+        seen.add(kern)
         tot = sum(int(t[2] or 0) for t in table) or 1
         lines.append(f"== top stall-sample instructions: {kern} (total samples {tot}, {len(table)} SASS instr)")
         for t in sorted(table, key=lambda t: -int(t[2] or 0))[:22]:

@@ -20,6 +20,7 @@ ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--max-nz", type=int, default=None)
 ap.add_argument("--plain", action="store_true", help="unbanked kernels")
+ap.add_argument("--banked-bwd", action="store_true", help="banked backward too (default: plain backward)")
 a = ap.parse_args()
 if a.max_nz:
     mk.set_max_nz(a.max_nz)
@@ -42,7 +43,7 @@ for it in range(a.warmup + a.steps):
     else:
         out, _ = mk.spgemm_forward(g.indptr, g.indices, val, sd, si, n, e, a.k, a.dim)
     ev[2].record()
-    if banked:
+    if banked and a.banked_bwd:
         dxs = mk.spgemm_backward_banked(g.indptr, g.indices, val, dy, bs, n, e, a.k, a.dim)
     else:
         dxs = mk.spgemm_backward(g.indptr, g.indices, val, dy, si, n, e, a.k, a.dim)
