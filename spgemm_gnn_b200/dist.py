@@ -83,6 +83,28 @@ def allgather_cbsr(sp_data: torch.Tensor, sp_index: torch.Tensor, group=None):
     return full_data, full_index
 
 
+def allgather_many(locals_, group=None):
+    """Several [R, ...] tensors -> their [P*R, ...] gathers in ONE NCCL launch (grouped call);
+    falls back to one call per tensor where the coalescing manager is not available (gloo)."""
+    world = dist.get_world_size(group)
+    fulls = [torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+             for t in locals_]
+    pairs = [(f.view(torch.uint8), t.contiguous().view(torch.uint8)) for f, t in zip(fulls, locals_)]
+    done = False
+    if _backend(group) == "nccl" and hasattr(dist, "_coalescing_manager"):
+        try:
+            with dist._coalescing_manager(group=group, device=locals_[0].device, async_ops=False):
+                for f, t in pairs:
+                    dist.all_gather_into_tensor(f, t, group=group)
+            done = True
+        except Exception:
+            done = False
+    if not done:
+        for f, t in pairs:
+            dist.all_gather_into_tensor(f, t, group=group)
+    return fulls
+
+
 def allgather_rows(local: torch.Tensor, group=None) -> torch.Tensor:
     """[R,k] of any dtype -> [P*R,k] (moved as raw bytes)."""
     world = dist.get_world_size(group)
@@ -133,12 +155,11 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
     part = maxk_kernels.partition(ptr, num_rows)
     if maxk_kernels.use_banked(part.num_parts, idx.numel(), k, dim_origin):
         bk_data, _, bk_slot = maxk_kernels.cbsr_bank(sp_data, sp_index, dim_origin, with_index=False)
-        full_data, full_slot = allgather_cbsr(bk_data, bk_slot, group)
-        full_index = allgather_rows(sp_index, group)
+        full_data, full_slot, full_index = allgather_many([bk_data, bk_slot, sp_index], group)
         out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, full_data, full_slot, num_rows,
                                                  idx.numel(), k, dim_origin)
     else:
-        full_data, full_index = allgather_cbsr(sp_data, sp_index, group)
+        full_data, full_index = allgather_many([sp_data, sp_index], group)
         out, _ = maxk_kernels.spgemm_forward(ptr, idx, val, full_data, full_index, num_rows,
                                              idx.numel(), k, dim_origin, allow_banked=False)
     return out, full_index
