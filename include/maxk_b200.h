@@ -97,6 +97,19 @@ MK_API int mk_cbsr_gather(const float* dense, const void* sp_index, int index_by
 MK_API int mk_partition(const int32_t* ptr, int64_t n_rows, int max_nz, mk_part* parts,
                         int64_t* h_num_parts, int64_t* h_num_slots, void* stream);
 
+/* Column-blocked work list for the backward on graphs whose CBSR gradient (n_src*k*4 B) does not fit
+ * in L2: mk_block_ptr cuts every CSR row (ascending column ids required) at the multiples of
+ * block_width -> blk_ptr [(n_blocks+1) * n_rows]; mk_partition_ranges then builds records over the
+ * n_blocks*n_rows virtual rows (row_start = blk_ptr, row_end = blk_ptr + n_rows, row_mod = n_rows,
+ * skip_empty = 1), block by block, so that one launch of mk_sspmm_bwd walks the destination
+ * blocks in order and its reductions stay L2-resident.  mk_partition(ptr, ...) is
+ * mk_partition_ranges(ptr, ptr + 1, n, 0, max_nz, 0, ...).                                     */
+MK_API int mk_block_ptr(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int n_blocks,
+                        int block_width, int32_t* blk_ptr, void* stream);
+MK_API int mk_partition_ranges(const int32_t* row_start, const int32_t* row_end, int64_t n_rows,
+                               int64_t row_mod, int max_nz, int skip_empty, mk_part* parts,
+                               int64_t* h_num_parts, int64_t* h_num_slots, void* stream);
+
 /* ---- a-3  forward row-wise-product SpGEMM -------------------------------------------
  * Replaces `spgemm_forward` -> `spgemm_forward_cuda` -> `SPMM_MAXK::do_test` ->
  * `spmm_kernel_opt2_sparse_v3` (maxk_cuda_kernels.o@0x1260, so@0x24bf0, so@0x24b60; Python

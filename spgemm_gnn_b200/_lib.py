@@ -25,6 +25,9 @@ SIGNATURES = {
     "mk_cbsr_scatter": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, _i32, _vp]),
     "mk_cbsr_gather": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, _i32, _vp]),
     "mk_partition": (_i32, [_vp, _i64, _i32, _vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp]),
+    "mk_block_ptr": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "mk_partition_ranges": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, ctypes.POINTER(_i64),
+                                   ctypes.POINTER(_i64), _vp]),
     "mk_spgemm_fwd": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _i32, _vp]),
     "mk_sspmm_bwd": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _i32, _vp]),
     "mk_banked_supported": (_i32, [_i32, _i32]),

@@ -13,9 +13,9 @@ constexpr int kPThreads = 256;
 constexpr int kPItems = 4;  // rows per thread
 constexpr int kPTile = kPThreads * kPItems;
 
-__device__ __forceinline__ int chunks_of(int deg, int max_nz) {
+__device__ __forceinline__ int chunks_of(int deg, int max_nz, int skip_empty) {
     const int c = (deg + max_nz - 1) / max_nz;
-    return c < 1 ? 1 : c;
+    return c < 1 ? (skip_empty ? 0 : 1) : c;
 }
 
 struct Pair {
@@ -45,7 +45,8 @@ __device__ __forceinline__ Pair block_reduce(Pair v, Pair* sm) {
 }
 
 __global__ void __launch_bounds__(kPThreads)
-part_block_sums(const int* __restrict__ ptr, int64_t n, int max_nz, Pair* __restrict__ bsum) {
+part_block_sums(const int* __restrict__ rs, const int* __restrict__ re, int64_t n, int max_nz,
+                int skip_empty, Pair* __restrict__ bsum) {
     __shared__ Pair sm[kPThreads / 32];
     const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kPTile + threadIdx.x * kPItems;
     Pair v{0, 0};
@@ -53,7 +54,7 @@ part_block_sums(const int* __restrict__ ptr, int64_t n, int max_nz, Pair* __rest
     for (int i = 0; i < kPItems; ++i) {
         const int64_t r = r0 + i;
         if (r < n) {
-            const int c = chunks_of(ptr[r + 1] - ptr[r], max_nz);
+            const int c = chunks_of(re[r] - rs[r], max_nz, skip_empty);
             v.parts += c;
             v.slots += c > 1 ? c : 0;
         }
@@ -106,8 +107,8 @@ part_scan_blocks(Pair* __restrict__ bsum, int nb, long long* __restrict__ tot) {
 }
 
 __global__ void __launch_bounds__(kPThreads)
-part_fill(const int* __restrict__ ptr, int64_t n, int max_nz, const Pair* __restrict__ boff,
-          mk_part* __restrict__ parts) {
+part_fill(const int* __restrict__ rs, const int* __restrict__ re, int64_t n, int max_nz,
+          int skip_empty, int64_t row_mod, const Pair* __restrict__ boff, mk_part* __restrict__ parts) {
     __shared__ Pair wsum[kPThreads / 32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kPTile + threadIdx.x * kPItems;
@@ -116,7 +117,7 @@ part_fill(const int* __restrict__ ptr, int64_t n, int max_nz, const Pair* __rest
 #pragma unroll
     for (int i = 0; i < kPItems; ++i) {
         const int64_t r = r0 + i;
-        cnt[i] = r < n ? chunks_of(ptr[r + 1] - ptr[r], max_nz) : 0;
+        cnt[i] = r < n ? chunks_of(re[r] - rs[r], max_nz, skip_empty) : 0;
         v.parts += cnt[i];
         v.slots += cnt[i] > 1 ? cnt[i] : 0;
     }
@@ -138,13 +139,13 @@ part_fill(const int* __restrict__ ptr, int64_t n, int max_nz, const Pair* __rest
     for (int i = 0; i < kPItems; ++i) {
         const int64_t r = r0 + i;
         if (r >= n) break;
-        const int lo = ptr[r], hi = ptr[r + 1];
+        const int lo = rs[r], hi = re[r];
         for (int c = 0; c < cnt[i]; ++c) {
             const int loc = lo + c * max_nz;
             int len = hi - loc;
             len = len > max_nz ? max_nz : (len < 0 ? 0 : len);
             mk_part rec;
-            rec.row = static_cast<int>(r);
+            rec.row = static_cast<int>(row_mod > 0 ? r % row_mod : r);
             rec.loc = loc;
             rec.len = len;
             rec.slot = cnt[i] == 1 ? -1 : static_cast<int>(s++);
@@ -153,17 +154,64 @@ part_fill(const int* __restrict__ ptr, int64_t n, int max_nz, const Pair* __rest
     }
 }
 
+// blk[b * n + r] = first position in CSR row r whose column id is >= b * width (b = 0 .. nb);
+// needs ascending column ids inside a row.
+__global__ void __launch_bounds__(256)
+block_ptr_kernel(const int* __restrict__ ptr, const int* __restrict__ idx, int64_t n, int nb,
+                 int width, int* __restrict__ blk) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= n * (nb + 1)) return;
+    const int64_t r = t % n;
+    const int b = static_cast<int>(t / n);
+    int lo = ptr[r], hi = ptr[r + 1];
+    if (b == 0) { blk[t] = lo; return; }
+    if (b == nb) { blk[t] = hi; return; }
+    const long long key = static_cast<long long>(b) * width;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (idx[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    blk[t] = lo;
+}
+
 }  // namespace mk
+
+extern "C" int mk_block_ptr(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int n_blocks,
+                            int block_width, int32_t* blk_ptr, void* stream) {
+    if (n_rows < 0 || n_blocks < 1 || block_width < 1) return MK_EINVAL;
+    if (n_rows == 0) return MK_OK;
+    if (!ptr || !blk_ptr) return MK_EINVAL;
+    const int64_t total = n_rows * (n_blocks + 1);
+    const int64_t blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffffLL) return MK_EUNSUPPORTED;
+    mk::block_ptr_kernel<<<static_cast<unsigned>(blocks), 256, 0, mk::as_stream(stream)>>>(
+        ptr, idx, n_rows, n_blocks, block_width, blk_ptr);
+    MK_LAUNCH_CHECK("block_ptr_kernel");
+    return MK_OK;
+}
+
+extern "C" int mk_partition_ranges(const int32_t* row_start, const int32_t* row_end, int64_t n_rows,
+                                   int64_t row_mod, int max_nz, int skip_empty, mk_part* parts,
+                                   int64_t* h_num_parts, int64_t* h_num_slots, void* stream);
 
 extern "C" int mk_partition(const int32_t* ptr, int64_t n_rows, int max_nz, mk_part* parts,
                             int64_t* h_num_parts, int64_t* h_num_slots, void* stream) {
+    if (n_rows > 0 && !ptr) return MK_EINVAL;
+    return mk_partition_ranges(ptr, ptr ? ptr + 1 : ptr, n_rows, 0, max_nz, 0, parts, h_num_parts,
+                               h_num_slots, stream);
+}
+
+extern "C" int mk_partition_ranges(const int32_t* row_start, const int32_t* row_end, int64_t n_rows,
+                                   int64_t row_mod, int max_nz, int skip_empty, mk_part* parts,
+                                   int64_t* h_num_parts, int64_t* h_num_slots, void* stream) {
+    const int32_t* ptr = row_start;
     if (n_rows < 0 || max_nz < 1) return MK_EINVAL;
     if (n_rows == 0) {
         if (h_num_parts) *h_num_parts = 0;
         if (h_num_slots) *h_num_slots = 0;
         return MK_OK;
     }
-    if (!ptr) return MK_EINVAL;
+    if (!ptr || !row_end) return MK_EINVAL;
     if (!parts && !h_num_parts) return MK_EINVAL;
     cudaStream_t st = mk::as_stream(stream);
     const int64_t nb64 = (n_rows + mk::kPTile - 1) / mk::kPTile;
@@ -173,11 +221,12 @@ extern "C" int mk_partition(const int32_t* ptr, int64_t n_rows, int max_nz, mk_p
     long long* tot = nullptr;
     MK_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&bsum), sizeof(mk::Pair) * nb + 16, st));
     tot = reinterpret_cast<long long*>(bsum + nb);
-    mk::part_block_sums<<<nb, mk::kPThreads, 0, st>>>(ptr, n_rows, max_nz, bsum);
+    mk::part_block_sums<<<nb, mk::kPThreads, 0, st>>>(row_start, row_end, n_rows, max_nz, skip_empty, bsum);
     mk::part_scan_blocks<<<1, 1024, 0, st>>>(bsum, nb, tot);
     int rc = MK_OK;
     if (parts) {
-        mk::part_fill<<<nb, mk::kPThreads, 0, st>>>(ptr, n_rows, max_nz, bsum, parts);
+        mk::part_fill<<<nb, mk::kPThreads, 0, st>>>(row_start, row_end, n_rows, max_nz, skip_empty, row_mod,
+                                                    bsum, parts);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { mk::set_cuda_error(e, "mk_partition launch"); rc = MK_ECUDA; }

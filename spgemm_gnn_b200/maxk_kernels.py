@@ -33,7 +33,8 @@ __all__ = [
     "maxk_forward_cbsr", "cbsr_scatter", "cbsr_gather", "partition",
     "clear_partition_cache", "install_partition", "set_max_nz", "get_max_nz", "launch_count",
     "banked_supported", "cbsr_bank", "maxk_forward_banked", "spgemm_forward_banked",
-    "spgemm_backward_banked", "set_banked", "use_banked",
+    "spgemm_backward_banked", "set_banked", "use_banked", "partition_blocked", "backward_blocks",
+    "set_backward_block_mb",
 ]
 
 _MAX_NZ = int(os.environ.get("MAXK_MAX_NZ", "1024"))
@@ -211,6 +212,7 @@ _part_cache = {}
 
 def clear_partition_cache() -> None:
     _part_cache.clear()
+    _block_cache.clear()
 
 
 def partition(ptr: torch.Tensor, num_nodes: int, max_nz: Optional[int] = None) -> _Partition:
@@ -242,6 +244,80 @@ def partition(ptr: torch.Tensor, num_nodes: int, max_nz: Optional[int] = None) -
     if len(_part_cache) > 64:
         _part_cache.clear()
     _part_cache[key] = p
+    return p
+
+
+_BWD_BLOCK_BYTES = int(os.environ.get("MAXK_BWD_BLOCK_MB", "80")) << 20   # CBSR-gradient bytes per column block
+# Off by default: measured on the products shape (2.45 M nodes, mean degree 51) it does not pay --
+# 6.83 ms plain, 6.58 / 6.62 / 7.48 ms with 2 / 3 / 4 blocks -- because every (row, block) record
+# re-stages dY[r] and the records get too short.  Kept for high-degree graphs with huge node counts.
+_BWD_BLOCKED = os.environ.get("MAXK_BWD_BLOCKED", "0") != "0"
+_block_cache = {}
+
+
+def set_backward_block_mb(mb: int) -> None:
+    """Target size of one destination block of the column-blocked backward (0 disables it)."""
+    global _BWD_BLOCK_BYTES, _BWD_BLOCKED
+    _BWD_BLOCKED = mb > 0
+    _BWD_BLOCK_BYTES = max(int(mb), 1) << 20
+    _block_cache.clear()
+
+
+def backward_blocks(n_src: int, dim_sparse: int, num_nodes: int, num_edges: int) -> int:
+    """How many destination blocks the backward should walk: 1 while the CBSR gradient
+    (n_src*k*4 B) fits in L2 next to the streams, else enough blocks of ~80 MB -- but never so
+    many that a (row, block) record drops below ~64 stored entries (each record re-stages dY[r])."""
+    if not _BWD_BLOCKED:
+        return 1
+    need = -(-(n_src * dim_sparse * 4) // _BWD_BLOCK_BYTES)
+    if need <= 1:
+        return 1
+    cap = max(int(num_edges // max(num_nodes, 1)) // 64, 1)
+    return max(min(need, cap, 16), 1)
+
+
+def partition_blocked(ptr: torch.Tensor, idx: torch.Tensor, num_nodes: int, n_src: int,
+                      n_blocks: int, max_nz: Optional[int] = None) -> _Partition:
+    """Work records ordered by destination block (column range) first, row second: one backward
+    launch then walks the blocks in order and its vector reductions stay L2-resident.  Needs
+    ascending column ids inside every row (checked once; falls back to the row-major records)."""
+    global _launches
+    max_nz = _MAX_NZ if max_nz is None else int(max_nz)
+    key = (ptr.device.index, ptr.data_ptr(), idx.data_ptr(), int(num_nodes), int(n_src), int(n_blocks), max_nz)
+    hit = _block_cache.get(key)
+    if hit is not None and hit.ptr_ref() is ptr and hit.version == ptr._version:
+        return hit
+    e = int(idx.numel())
+    if e > 1:  # ascending inside rows?
+        bad = idx[1:] < idx[:-1]
+        starts = ptr[1:num_nodes].to(torch.int64)
+        starts = starts[(starts > 0) & (starts < e)]
+        bad[starts - 1] = False
+        if bool(bad.any()):
+            return partition(ptr, num_nodes, max_nz)
+    width = -(-n_src // n_blocks)
+    L = _lib.lib()
+    blk = torch.empty(((n_blocks + 1) * num_nodes,), dtype=torch.int32, device=ptr.device)
+    np_, ns_ = ctypes.c_int64(0), ctypes.c_int64(0)
+    with torch.cuda.device(ptr.device):
+        _lib.check(L.mk_block_ptr(ptr.data_ptr(), idx.data_ptr(), num_nodes, n_blocks, width,
+                                  blk.data_ptr(), _stream()), "mk_block_ptr")
+        rs, re = blk.data_ptr(), blk.data_ptr() + 4 * num_nodes
+        vrows = n_blocks * num_nodes
+        _lib.check(L.mk_partition_ranges(rs, re, vrows, num_nodes, max_nz, 1, None, ctypes.byref(np_),
+                                         ctypes.byref(ns_), _stream()), "mk_partition_ranges")
+        p = _Partition()
+        p.num_parts, p.num_slots, p.max_nz = int(np_.value), int(ns_.value), max_nz
+        p.parts = torch.empty((max(p.num_parts, 1), 4), dtype=torch.int32, device=ptr.device)
+        p.partial = None
+        _lib.check(L.mk_partition_ranges(rs, re, vrows, num_nodes, max_nz, 1, p.parts.data_ptr(), None,
+                                         None, _stream()), "mk_partition_ranges")
+    _launches += 6
+    p.ptr_ref = weakref.ref(ptr)
+    p.version = ptr._version
+    if len(_block_cache) > 32:
+        _block_cache.clear()
+    _block_cache[key] = p
     return p
 
 
@@ -321,7 +397,8 @@ def spgemm_backward(ptr, idx, val, grad_output, sp_index, num_nodes, num_edges, 
     _chk(1 <= dim_sparse <= dim_origin, "k must be between 1 and input dimension")
     ib = _index_bytes(sp_index, dim_origin)
     n_src = sp_index.shape[0]
-    part = partition(ptr, num_nodes)
+    nb = backward_blocks(n_src, dim_sparse, num_nodes, num_edges)
+    part = partition(ptr, num_nodes) if nb <= 1 else partition_blocked(ptr, idx, num_nodes, n_src, nb)
     dxs = torch.empty((n_src, dim_sparse), dtype=torch.float32, device=grad_output.device)
     with torch.cuda.device(grad_output.device):
         rc = _lib.lib().mk_sspmm_bwd(

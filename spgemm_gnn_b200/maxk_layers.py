@@ -120,6 +120,23 @@ def maxk_aggregate(graph: CSRGraph, feat: torch.Tensor, k: int, weight_kind: str
     return aggregate_cbsr(graph, sp_data, sp_index, weight_kind, feat.shape[1])
 
 
+def extract_sparse_format(sparse_tensor: torch.Tensor, maxk: int):
+    """`MaxKSAGEConv._extract_sparse_format` (utils/maxk_layers.py:224-265, a per-row Python loop
+    there): CBSR of a dense masked matrix -- the first `maxk` non-zeros of every row in ascending
+    column order, padded with (0.0, index 0).  Kept for callers of the reference method; the hot
+    path never needs it because the MaxK kernel emits CBSR directly.  Plain torch ops."""
+    n, d = sparse_tensor.shape
+    nz = sparse_tensor != 0
+    order = torch.argsort((~nz).to(torch.uint8), dim=1, stable=True)[:, :maxk]
+    vals = torch.gather(sparse_tensor, 1, order)
+    keep = torch.arange(maxk, device=sparse_tensor.device)[None, :] < nz.sum(1, keepdim=True)
+    idx_dtype = torch.uint8 if d <= 256 else torch.int16
+    sp_index = torch.where(keep, order, torch.zeros_like(order)).to(idx_dtype)
+    if d > 256:
+        sp_index = sp_index.view(torch.uint16)
+    return torch.where(keep, vals, torch.zeros_like(vals)), sp_index
+
+
 def _dense_aggregate(graph: CSRGraph, feat: torch.Tensor, weight_kind: str) -> torch.Tensor:
     """Non-MaxK (`--nonlinear relu`) branch: dense SpMM through cuSPARSE, the comparator the
     reference reports its speed-ups against (README.md:136).  Not the hot path."""
@@ -167,6 +184,9 @@ class MaxKSAGEConv(nn.Module):
         nn.init.xavier_uniform_(self.fc_self.weight, gain=gain)
         nn.init.xavier_uniform_(self.fc_neigh.weight, gain=gain)
 
+    def _extract_sparse_format(self, sparse_tensor):
+        return extract_sparse_format(sparse_tensor, self.maxk)
+
     def forward(self, graph, feat):
         h_self = self.fc_self(feat)
         h_neigh = self.fc_neigh(feat)
@@ -207,6 +227,9 @@ class MaxKGCNConv(nn.Module):
             nn.init.xavier_uniform_(self.weight)
         if self.bias is not None:
             nn.init.zeros_(self.bias)
+
+    def _extract_sparse_format(self, sparse_tensor):
+        return extract_sparse_format(sparse_tensor, self.maxk)
 
     def forward(self, graph, feat):
         if not self.allow_zero_in_degree:

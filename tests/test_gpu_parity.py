@@ -439,3 +439,40 @@ def test_graph_file_carries_the_work_records(mk, tmp_path):
     p1 = mk.partition(h.indptr, h.num_nodes(), 256)
     assert mk.launch_count() == before                     # served from the installed records
     assert p1.num_slots == p0.num_slots and torch.equal(p1.parts[: p1.num_parts], p0.parts[: p0.num_parts])
+
+
+@pytest.mark.parametrize("n_blocks", [2, 3, 7])
+def test_column_blocked_backward_matches_oracle(mk, n_blocks):
+    """The destination-blocked record order of the backward (large graphs) changes nothing but
+    the order of the atomic sums."""
+    from oracle import c_oracle
+    n, d, k = 3000, 256, 32
+    ptr, idx, val, x, dy = _problem(n, 40, d, k, seed=77, kind="mean")
+    wd, wi = c_oracle.maxk_cbsr(x, k)
+    tptr, tidx = dev(ptr), dev(idx)
+    part = mk.partition_blocked(tptr, tidx, n, n, n_blocks, 64)
+    recs = part.parts[: part.num_parts].cpu().numpy()
+    # every stored entry exactly once; inside a record all columns belong to one block
+    width = -(-n // n_blocks)
+    cover = np.concatenate([np.arange(l, l + ln) for _, l, ln, _ in recs])
+    assert np.array_equal(np.sort(cover), np.arange(idx.size))
+    for r, l, ln, _ in recs[:: max(len(recs) // 200, 1)]:
+        assert ptr[r] <= l and l + ln <= ptr[r + 1] and ln > 0
+        blocks = idx[l:l + ln] // width
+        assert blocks.min() == blocks.max()
+    first_block = np.array([idx[l] // width for _, l, _, _ in recs])
+    assert np.all(np.diff(first_block) >= 0)                       # blocks in order
+    from spgemm_gnn_b200 import _lib
+    dxs = torch.empty((n, k), dtype=torch.float32, device="cuda")
+    rc = _lib.lib().mk_sspmm_bwd(part.parts.data_ptr(), part.num_parts, tidx.data_ptr(), dev(val).data_ptr(),
+                                 dev(dy).data_ptr(), dev(wi).data_ptr(), 1, dxs.data_ptr(), n, n, k, d,
+                                 torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    want = c_oracle.sspmm_bwd(ptr, idx, val, dy, wi)
+    bound = c_oracle.sspmm_bwd(ptr, idx, np.abs(val), np.abs(dy), wi)
+    assert_rel(dxs, want, bound, "blocked backward")
+    # unsorted rows: falls back to the plain record list
+    perm_idx = idx.copy()
+    perm_idx[ptr[5]:ptr[6]] = perm_idx[ptr[5]:ptr[6]][::-1]
+    p2 = mk.partition_blocked(tptr, dev(perm_idx), n, n, n_blocks, 64)
+    assert p2.num_parts == mk.partition(tptr, n, 64).num_parts

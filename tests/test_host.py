@@ -1,5 +1,6 @@
 """Host-side logic: CSR container, synthetic shapes, edge weights, row partition (no GPU)."""
 import numpy as np
+import numpy as np
 import pytest
 import torch
 
@@ -80,3 +81,19 @@ def test_graph_file_round_trip(tmp_path):
     np.savez(str(tmp_path / "bad.npz"), magic=np.array("nope"))
     with pytest.raises(ValueError):
         G.load_graph(str(tmp_path / "bad.npz"))
+
+
+def test_extract_sparse_format_matches_reference_method(golden):
+    """Vectorised stand-in of MaxKSAGEConv._extract_sparse_format against the reference's own
+    outputs (tests/golden), including the (0.0, idx 0) padding rows."""
+    from spgemm_gnn_b200.maxk_layers import extract_sparse_format, MaxKSAGEConv
+    d, i = extract_sparse_format(torch.from_numpy(golden["pad_x"]), int(golden["pad_k"]))
+    assert np.array_equal(d.numpy(), golden["pad_sp_data"]) and np.array_equal(i.numpy(), golden["pad_sp_index"])
+    for ci in range(int(golden["num_cases"])):
+        pre = f"c{ci}_"
+        if pre + "sp_index" not in golden.files:
+            continue
+        conv = MaxKSAGEConv(8, 8, maxk=int(golden[pre + "k"]))
+        d, i = conv._extract_sparse_format(torch.from_numpy(golden[pre + "maxk_out"]))
+        assert np.array_equal(d.numpy(), golden[pre + "sp_data"])
+        assert np.array_equal(i.numpy(), golden[pre + "sp_index"])

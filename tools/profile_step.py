@@ -20,10 +20,13 @@ ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--max-nz", type=int, default=None)
 ap.add_argument("--plain", action="store_true", help="unbanked kernels")
+ap.add_argument("--bwd-block-mb", type=int, default=None, help="column-block size of the backward (0 = off)")
 ap.add_argument("--banked-bwd", action="store_true", help="banked backward too (default: plain backward)")
 a = ap.parse_args()
 if a.max_nz:
     mk.set_max_nz(a.max_nz)
+if a.bwd_block_mb is not None:
+    mk.set_backward_block_mb(a.bwd_block_mb)
 g = shaped_graph(a.workload, scale=a.scale, device="cuda")
 n, e = g.num_nodes(), g.num_edges()
 val = g.edge_weights("mean")
@@ -49,6 +52,6 @@ for it in range(a.warmup + a.steps):
         dxs = mk.spgemm_backward(g.indptr, g.indices, val, dy, si, n, e, a.k, a.dim)
     ev[3].record()
 torch.cuda.synchronize()
-print(f"{a.workload} N={n} E={e} k={a.k} D={a.dim} max_nz={mk.get_max_nz()} "
+print(f"{a.workload} N={n} E={e} k={a.k} D={a.dim} max_nz={mk.get_max_nz()} bwd_blocks={mk.backward_blocks(n, a.k, n, e)} "
       f"{'banked' if banked else 'plain'}: bank {ev[0].elapsed_time(ev[1]):.3f} ms  "
       f"fwd {ev[1].elapsed_time(ev[2]):.3f} ms  bwd {ev[2].elapsed_time(ev[3]):.3f} ms")
