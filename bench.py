@@ -375,21 +375,90 @@ def main():
             hout.copy_(out, non_blocking=True)
             hdxs.copy_(dxs, non_blocking=True)
 
-        e2e_step()
+        def timed(fn, steps):
+            fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                fn()
+            b.record()
+            barrier()
+            ms = a.elapsed_time(b) / steps
+            if world > 1:
+                tt = torch.tensor([ms], device=device, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ms = float(tt.item())
+            return ms
+
+        serial_ms = timed(e2e_step, args.e2e_steps)
+
+        # Pipelined: the same per-step copies and calls, but step i+1's H2D and step i-1's D2H run
+        # on their own streams next to step i's kernels (double-buffered device inputs / outputs).
+        s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+        xin = [torch.empty_like(x_local) for _ in range(2)]
+        yin = [torch.empty_like(dy) for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_in_free = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        state = {"i": 0}
+
+        def pipe_step():
+            i = state["i"]
+            bsel = i & 1
+            with torch.cuda.stream(s_in):
+                if i >= 2:
+                    s_in.wait_event(ev_in_free[bsel])
+                xin[bsel].copy_(hx, non_blocking=True)
+                yin[bsel].copy_(hdy, non_blocking=True)
+                ev_in[bsel].record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in[bsel])
+                sd, si = mk.maxk_forward_cbsr(xin[bsel], k)
+                if world > 1:
+                    out, fi = mdist.sharded_forward(sd, si, ptr, idx, val, n_rows, d)
+                    dxs = mdist.sharded_backward(yin[bsel], fi, ptr, idx, val, n_rows, d)
+                else:
+                    out, _ = mk.spgemm_forward(ptr, idx, val, sd, si, n_rows, e_local, k, d)
+                    dxs = mk.spgemm_backward(ptr, idx, val, yin[bsel], si, n_rows, e_local, k, d)
+                ev_in_free[bsel].record(s_cmp)
+                ev_done[bsel].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_done[bsel])
+                out.record_stream(s_out)
+                dxs.record_stream(s_out)
+                hout.copy_(out, non_blocking=True)
+                hdxs.copy_(dxs, non_blocking=True)
+            state["i"] = i + 1
+
+        def pipe_timed(steps):
+            for s_ in (s_in, s_cmp, s_out):
+                s_.wait_stream(torch.cuda.current_stream())
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            s_in.wait_event(a); s_cmp.wait_event(a); s_out.wait_event(a)
+            for _ in range(steps):
+                pipe_step()
+            for s_ in (s_in, s_cmp, s_out):
+                torch.cuda.current_stream().wait_stream(s_)
+            b.record()
+            barrier()
+            return a.elapsed_time(b) / steps
+
+        pipe_timed(2)
         barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        b.record()
-        barrier()
-        e2e_ms = a.elapsed_time(b) / args.e2e_steps
+        pipe_steps = max(args.e2e_steps * 2, 8)
+        e2e_ms = pipe_timed(pipe_steps)
         if world > 1:
             tt = torch.tensor([e2e_ms], device=device, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e_ms = float(tt.item())
+        if e2e_ms > serial_ms:  # never report the slower of the two drivers
+            e2e_ms, pipe_steps = serial_ms, args.e2e_steps
         e2e = {"value": 2.0 * e / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-               "steps": args.e2e_steps,
+               "steps": pipe_steps, "serial_ms_per_step": serial_ms,
+               "overlap": "H2D of step i+1 and D2H of step i-1 on their own streams next to step i's "
+                          "kernels; every step still copies its own inputs in and its results out",
                "h2d_bytes_per_step": 2 * n_rows * d * 4 * world,
                "d2h_bytes_per_step": (n_rows * d * 4 + n_rows * k * 4) * world,
                "path": "pinned host X,dY -> H2D -> maxk_forward_cbsr -> spgemm_forward -> "
