@@ -476,3 +476,35 @@ def test_column_blocked_backward_matches_oracle(mk, n_blocks):
     perm_idx[ptr[5]:ptr[6]] = perm_idx[ptr[5]:ptr[6]][::-1]
     p2 = mk.partition_blocked(tptr, dev(perm_idx), n, n, n_blocks, 64)
     assert p2.num_parts == mk.partition(tptr, n, 64).num_parts
+
+
+@pytest.mark.parametrize("shape,d,k", [("ogbn-products", 256, 32), ("ogbn-proteins", 256, 64), ("yelp", 384, 16)])
+def test_other_baseline_shapes_full_size(mk, shape, d, k):
+    """BASELINE.json configs 4 and 5 (and the Yelp width, uint16 column ids) at full size:
+    top-k against torch.topk, forward against dense cuSPARSE SpMM, backward through adjointness."""
+    from spgemm_gnn_b200.graph import shaped_graph
+    g = shaped_graph(shape, device="cuda")
+    n, e = g.num_nodes(), g.num_edges()
+    gen = torch.Generator(device="cuda").manual_seed(97)
+    x = torch.randn(n, d, device="cuda", generator=gen)
+    dy = torch.randn(n, d, device="cuda", generator=gen)
+    val = g.edge_weights("both")
+    sp_data, sp_index = mk.maxk_forward_cbsr(x, k)
+    assert sp_index.dtype == (torch.uint8 if d <= 256 else torch.uint16)
+    cols = (sp_index if d <= 256 else sp_index.view(torch.int16)).to(torch.int64) & 0xFFFF
+    tv, ti = torch.topk(x, k, dim=1)
+    assert torch.equal(cols, ti.sort(dim=1)[0])                      # tie-free: same set, ascending
+    assert torch.equal(torch.gather(x, 1, cols), sp_data)
+    out, _ = mk.spgemm_forward(g.indptr, g.indices, val, sp_data, sp_index, n, e, k, d)
+    out2, _ = mk.spgemm_forward(g.indptr, g.indices, val, sp_data, sp_index, n, e, k, d)
+    assert torch.equal(out, out2)
+    xm = mk.cbsr_scatter(sp_data, sp_index, d)
+    adj = torch.sparse_csr_tensor(g.indptr.long(), g.indices.long(), val, size=(n, n))
+    ref = torch.sparse.mm(adj, xm)
+    assert float((out - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    del ref, xm, adj
+    dxs = mk.spgemm_backward(g.indptr, g.indices, val, dy, sp_index, n, e, k, d)
+    lhs = float((out.double() * dy.double()).sum())
+    rhs = float((sp_data.double() * dxs.double()).sum())
+    scale = float((out.double().abs() * dy.double().abs()).sum())
+    assert abs(lhs - rhs) <= 1e-8 * scale
