@@ -26,13 +26,28 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def _stale() -> bool:
-    if not os.path.exists(SO):
-        return True
-    t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+STAMP = SO + ".srchash"
+
+
+def _source_hash() -> str:
+    """Content hash of everything the library is built from (mtimes do not survive the copy to
+    the GPU box)."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [
         os.path.join(ROOT, "include", "maxk_b200.h"), os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stale() -> bool:
+    if not os.path.exists(SO) or not os.path.exists(STAMP):
+        return True
+    with open(STAMP) as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False, defs=(), out: str = None) -> str:
@@ -68,6 +83,9 @@ def build(force: bool = False, verbose: bool = False, defs=(), out: str = None) 
         raise RuntimeError("nvcc failed")
     subprocess.check_call([nvcc, *ARCH, "-shared", "-cudart", "static", "-ccbin", "/usr/bin/g++",
                            "-o", so] + objs)
+    if so == SO and not defs:
+        with open(STAMP, "w") as f:
+            f.write(_source_hash())
     return so
 
 

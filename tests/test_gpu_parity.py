@@ -17,6 +17,8 @@ REL_TOL = 1e-5
 def mk():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    from spgemm_gnn_b200 import build as _build
+    _build.build()                      # no-op when the in-tree library matches the sources
     import maxk_kernels
     from spgemm_gnn_b200 import _lib
     assert _lib.lib().mk_device_ok() == 0, "not an sm_100 device"
