@@ -84,6 +84,56 @@ def train_epochs(model: nn.Module, g: CSRGraph, feats, labels, train_mask, epoch
     return losses, times
 
 
+def train_epochs_graphed(model: nn.Module, g: CSRGraph, feats, labels, train_mask, epochs: int,
+                         lr: float = 0.01, weight_decay: float = 0.0, warmup: int = 3):
+    """Same training step, captured ONCE in a CUDA graph and replayed: on small graphs (Flickr
+    shape) an epoch is ~60 short kernels and launch overhead, not the GPU, sets the pace.  The
+    hot-path kernels are plain stream launches through the C ABI, so they capture like any other
+    kernel; the work records are built (and synchronised on) before the capture.  Single GPU.
+    The first `warmup` epochs run eagerly on a side stream (they train too)."""
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, capturable=True)
+    idx = train_mask.nonzero(as_tuple=True)[0]
+    target = labels[idx]
+    losses, times = [], []
+    model.train()
+    static_loss = torch.zeros((), device=feats.device)
+
+    def step():
+        logits = model(g, feats)
+        loss = F.cross_entropy(logits.index_select(0, idx), target)
+        opt.zero_grad(set_to_none=False)
+        loss.backward()
+        opt.step()
+        static_loss.copy_(loss.detach())
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(min(warmup, epochs)):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            step()
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+            losses.append(float(static_loss))
+    torch.cuda.current_stream().wait_stream(side)
+    if epochs <= warmup:
+        return losses, times
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    # the capture itself did not execute anything
+    for _ in range(epochs - warmup):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        graph.replay()
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+        losses.append(float(static_loss))
+    return losses, times
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--dataset", default="flickr", choices=sorted(SHAPES))
@@ -104,6 +154,8 @@ def main(argv=None):
                     help="fp32 GEMMs (default: TF32, as the reference sets at maxk_gnn_dgl.py:30-33)")
     ap.add_argument("--eval_every", type=int, default=1, help="eval forward every n epochs (reference: 1)")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--cuda_graph", action="store_true",
+                    help="capture the train step in a CUDA graph (single GPU, no eval forward)")
     a = ap.parse_args(argv)
     if not torch.cuda.is_available():
         raise SystemExit("training needs a CUDA device: the aggregation has no CPU fallback")
@@ -131,13 +183,19 @@ def main(argv=None):
     say = print if rank == 0 else (lambda *_: None)
     say(f"{a.dataset}: {n_nodes} nodes, {n_edges} edges; model {a.model} "
         f"{sum(p.numel() for p in model.parameters())} params; {world} GPU(s)")
-    losses, times = train_epochs(model, g, feats, labels, train_mask, a.epochs, a.w_lr,
-                                 a.w_weight_decay, eval_every=a.eval_every, log=say if a.verbose else None)
+    if a.cuda_graph and world == 1:
+        a.eval_every = 0
+        losses, times = train_epochs_graphed(model, g, feats, labels, train_mask, a.epochs, a.w_lr,
+                                             a.w_weight_decay)
+    else:
+        losses, times = train_epochs(model, g, feats, labels, train_mask, a.epochs, a.w_lr,
+                                     a.w_weight_decay, eval_every=a.eval_every,
+                                     log=say if a.verbose else None)
     steady = sorted(times[len(times) // 5:])
     say(json.dumps({"dataset": a.dataset, "model": a.model, "nonlinear": a.nonlinear, "maxk": a.maxk,
                     "gpus": world, "epochs": a.epochs, "first_loss": losses[0], "final_loss": losses[-1],
                     "epoch_ms_median": steady[len(steady) // 2] * 1e3,
-                    "eval_forward_per_epoch": bool(a.eval_every)}))
+                    "eval_forward_per_epoch": bool(a.eval_every), "cuda_graph": bool(a.cuda_graph)}))
     if world > 1:
         dist.destroy_process_group()
 
