@@ -510,3 +510,49 @@ def test_other_baseline_shapes_full_size(mk, shape, d, k):
     rhs = float((sp_data.double() * dxs.double()).sum())
     scale = float((out.double().abs() * dy.double().abs()).sum())
     assert abs(lhs - rhs) <= 1e-8 * scale
+
+
+def test_empty_and_extreme_inputs(mk):
+    """n = 0, E = 0, k = 1, k = D, one row holding every stored entry."""
+    from oracle import c_oracle
+    dev0 = "cuda"
+    # n = 0
+    d0, i0 = mk.maxk_forward_cbsr(torch.empty((0, 64), device=dev0), 8)
+    assert d0.shape == (0, 8) and i0.shape == (0, 8)
+    assert mk.cbsr_scatter(d0, i0, 64).shape == (0, 64)
+    # graph without stored entries: output rows are zero, gradient is zero
+    n, d, k = 50, 64, 8
+    x = torch.randn(n, d, device=dev0)
+    sd, si = mk.maxk_forward_cbsr(x, k)
+    ptr = torch.zeros(n + 1, dtype=torch.int32, device=dev0)
+    idx = torch.zeros(0, dtype=torch.int32, device=dev0)
+    val = torch.zeros(0, device=dev0)
+    out, _ = mk.spgemm_forward(ptr, idx, val, sd, si, n, 0, k, d)
+    assert out.shape == (n, d) and float(out.abs().max()) == 0.0
+    dxs = mk.spgemm_backward(ptr, idx, val, torch.randn(n, d, device=dev0), si, n, 0, k, d)
+    assert dxs.shape == (n, k) and float(dxs.abs().max()) == 0.0
+    # k = 1 and k = D (CBSR == dense row, identity permutation)
+    rng = np.random.default_rng(3)
+    xh = rng.standard_normal((40, 32)).astype(np.float32)
+    for kk in (1, 32):
+        gd, gi = mk.maxk_forward_cbsr(dev(xh), kk)
+        wd, wi = c_oracle.maxk_cbsr(xh, kk)
+        assert np.array_equal(gi.cpu().numpy(), wi) and np.array_equal(gd.cpu().numpy(), wd)
+    # one row holds all 70,000 stored entries (more than 65,535, many records, partial folding)
+    n, d, k = 5000, 256, 32
+    xh = rng.standard_normal((n, d)).astype(np.float32)
+    wd, wi = c_oracle.maxk_cbsr(xh, k)
+    e = 70000
+    ptr_h = np.zeros(n + 1, np.int32)
+    ptr_h[8:] = e                                    # row 7 owns everything
+    idx_h = rng.integers(0, n, e).astype(np.int32)
+    idx_h.sort()
+    val_h = rng.standard_normal(e).astype(np.float32)
+    dy_h = rng.standard_normal((n, d)).astype(np.float32)
+    out, _ = mk.spgemm_forward(dev(ptr_h), dev(idx_h), dev(val_h), dev(wd), dev(wi), n, e, k, d)
+    want = c_oracle.spgemm_fwd(ptr_h, idx_h, val_h, wd, wi, d)
+    bound = c_oracle.spgemm_fwd(ptr_h, idx_h, np.abs(val_h), np.abs(wd), wi, d)
+    assert_rel(out, want, bound, "single huge row fwd")
+    dxs = mk.spgemm_backward(dev(ptr_h), dev(idx_h), dev(val_h), dev(dy_h), dev(wi), n, e, k, d)
+    assert_rel(dxs, c_oracle.sspmm_bwd(ptr_h, idx_h, val_h, dy_h, wi),
+               c_oracle.sspmm_bwd(ptr_h, idx_h, np.abs(val_h), np.abs(dy_h), wi), "single huge row bwd")
