@@ -347,7 +347,11 @@ static int launch_fwd_vec(const mk_part* parts, int64_t num_parts, const int* id
                           const float* sp_data, const void* sp_index, float* out, float* partial,
                           int d, cudaStream_t st) {
     constexpr int G = 32 / (K / EPL);
-    constexpr int U = 4;
+#ifdef MK_FWD_VEC_U
+    constexpr int U = MK_FWD_VEC_U;
+#else
+    constexpr int U = (EPL >= 4) ? 4 : (32 / G >= 8 ? 8 : 32 / G);  // <= 32 / G steps per slice
+#endif
     const size_t smem = static_cast<size_t>(G) * d * 4;
     if (smem > 200 * 1024) return MK_EUNSUPPORTED;
     auto kern = spgemm_fwd_vec_kernel<K, EPL, IdxT, U>;

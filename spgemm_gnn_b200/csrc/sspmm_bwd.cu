@@ -120,10 +120,12 @@ template <int K, typename IdxT>
 static int launch_bwd_k(const mk_part* parts, int64_t num_parts, const int* idx, const float* val,
                         const float* dy, const void* sp_index, float* dxs, int d,
                         cudaStream_t st) {
+    // steps of column ids in flight; a 32-entry slice holds 32 / G steps (G = 128 / K neighbours per
+    // step), more would only add predicated-off work
 #ifdef MK_BWD_U
     constexpr int U = MK_BWD_U;
 #else
-    constexpr int U = 8;
+    constexpr int U = (K / 4 >= 8) ? 8 : (K / 4);
 #endif
     const int dpad = (d + 3) & ~3;
     const size_t smem = static_cast<size_t>(dpad) * 4;
