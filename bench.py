@@ -183,6 +183,8 @@ def main():
     ap.add_argument("--cpu-rows", type=float, default=1.0 / 32, help="row fraction of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-epoch", action="store_true", help="skip the MaxK-SAGE epoch timing")
+    ap.add_argument("--epochs", type=int, default=8)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -345,6 +347,7 @@ def main():
         "cbsr_scatter_ms": scatter_ms,
         "scatter_alg_GBps": (n_rows * k * (4 + w) + n_rows * d * 4) / (scatter_ms * 1e-3) / 1e9,
         "edges_per_s_fwd": e / (fwd_ms * 1e-3), "edges_per_s_bwd": e / (bwd_ms * 1e-3),
+        "layer_ms_with_maxk_and_scatter": fwd_ms + bwd_ms + topk_ms + scatter_ms,
         "work_records": part.num_parts, "partial_slots": part.num_slots, "max_nz": mk.get_max_nz(),
         "forward_variant": "banked (mk_cbsr_bank + mk_spgemm_fwd_banked, both inside spgemm_fwd_ms)"
         if mk.use_banked(part.num_parts, e_local, k, d) else "plain (mk_spgemm_fwd)",
@@ -464,6 +467,39 @@ def main():
                "path": "pinned host X,dY -> H2D -> maxk_forward_cbsr -> spgemm_forward -> "
                        "spgemm_backward -> D2H out,dXs (graph CSR resident, as g.to(device) in the reference)"}
 
+    # ---- MaxK-SAGE full-graph training epoch on the same graph (second half of BASELINE.json's
+    #      metric: "MaxK-SAGE epoch time 1/2/4/8 GPU"): 3 x 256, k = 32, LayerNorm, dropout 0.5, TF32
+    #      GEMMs like the reference (maxk_gnn_dgl.py:30-33), one train step + one eval forward
+    epoch = None
+    if not args.no_epoch and args.workload in ("reddit", "flickr", "yelp", "ogbn-products", "ogbn-proteins"):
+        from spgemm_gnn_b200.graph import FEATS
+        from spgemm_gnn_b200.models import SAGE
+        from spgemm_gnn_b200.train import train_epochs
+        in_feats, classes = FEATS[args.workload]
+        tf32_was = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        tg = mdist.ShardedGraph(g, rank, world) if world > 1 else g
+        rows_l = tg.num_nodes()
+        gen_e = torch.Generator(device=device).manual_seed(1234 + rank)
+        feats = torch.randn(rows_l, in_feats, device=device, generator=gen_e)
+        labels = torch.randint(0, classes, (rows_l,), device=device, generator=gen_e)
+        tmask = torch.rand(rows_l, device=device, generator=gen_e) < 0.66
+        if world > 1:
+            tmask[r1 - r0:] = False
+        torch.manual_seed(97)
+        model = SAGE(in_feats, d, 3, classes, maxk=k, feat_drop=0.5, norm=True).to(device)
+        _, times = train_epochs(model, tg, feats, labels, tmask, args.epochs, lr=0.01, eval_every=1)
+        steady = sorted(times[2:])
+        ep_ms = torch.tensor([steady[len(steady) // 2] * 1e3], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ep_ms, op=dist.ReduceOp.MAX)
+        torch.backends.cuda.matmul.allow_tf32 = tf32_was
+        epoch = {"ms_per_epoch": float(ep_ms.item()), "epochs": args.epochs,
+                 "model": f"MaxK-SAGE 3x{d}, k={k}, in {in_feats}, classes {classes}, LayerNorm, dropout 0.5, "
+                          "TF32 GEMMs; one train step + one eval forward per epoch (maxk_gnn_dgl.py:98-134)",
+                 "timing": "host wall clock around device-synchronised epochs, median, max over ranks"}
+        del model, feats
+
     # ---- CPU baseline (rank 0, N == 1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -481,6 +517,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world, n, e), "clocks": clk, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
+            "sage_epoch": epoch,
         }
         print(json.dumps(line))
     if world > 1:
