@@ -200,11 +200,11 @@ class _Partition:
     __slots__ = ("parts", "num_parts", "num_slots", "max_nz", "partial", "ptr_ref", "version")
 
     def partial_for(self, d: int, device) -> Optional[torch.Tensor]:
+        """Scratch rows for the records of multi-record rows.  A fresh tensor per call (the caching
+        allocator makes that free) so that calls on different streams never share scratch."""
         if self.num_slots == 0:
             return None
-        if self.partial is None or self.partial.shape[1] != d:
-            self.partial = torch.empty((self.num_slots, d), dtype=torch.float32, device=device)
-        return self.partial
+        return torch.empty((self.num_slots, d), dtype=torch.float32, device=device)
 
 
 _part_cache = {}
