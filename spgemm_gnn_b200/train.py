@@ -89,7 +89,8 @@ def train_epochs_graphed(model: nn.Module, g: CSRGraph, feats, labels, train_mas
     """Same training step, captured ONCE in a CUDA graph and replayed: on small graphs (Flickr
     shape) an epoch is ~60 short kernels and launch overhead, not the GPU, sets the pace.  The
     hot-path kernels are plain stream launches through the C ABI, so they capture like any other
-    kernel; the work records are built (and synchronised on) before the capture.  Single GPU.
+    kernel; the work records are built (and synchronised on) before the capture.  With a
+    `dist.ShardedGraph` the NCCL collectives of the step are captured too.
     The first `warmup` epochs run eagerly on a side stream (they train too)."""
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, capturable=True)
@@ -98,14 +99,27 @@ def train_epochs_graphed(model: nn.Module, g: CSRGraph, feats, labels, train_mas
     losses, times = [], []
     model.train()
     static_loss = torch.zeros((), device=feats.device)
+    sharded = getattr(g, "world", 1) > 1
+    if sharded:
+        import torch.distributed as dist
+        from .dist import allreduce_grads
+        count = train_mask.sum().to(torch.float32)
+        dist.all_reduce(count, group=g.group)
 
     def step():
         logits = model(g, feats)
-        loss = F.cross_entropy(logits.index_select(0, idx), target)
+        if sharded:
+            loss = F.cross_entropy(logits.index_select(0, idx), target, reduction="sum") / count
+        else:
+            loss = F.cross_entropy(logits.index_select(0, idx), target)
         opt.zero_grad(set_to_none=False)
         loss.backward()
-        opt.step()
+        if sharded:
+            allreduce_grads(params, g.group)
         static_loss.copy_(loss.detach())
+        if sharded:
+            dist.all_reduce(static_loss, group=g.group)
+        opt.step()
 
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
@@ -183,7 +197,7 @@ def main(argv=None):
     say = print if rank == 0 else (lambda *_: None)
     say(f"{a.dataset}: {n_nodes} nodes, {n_edges} edges; model {a.model} "
         f"{sum(p.numel() for p in model.parameters())} params; {world} GPU(s)")
-    if a.cuda_graph and world == 1:
+    if a.cuda_graph:
         a.eval_every = 0
         losses, times = train_epochs_graphed(model, g, feats, labels, train_mask, a.epochs, a.w_lr,
                                              a.w_weight_decay)
