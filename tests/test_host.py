@@ -97,3 +97,11 @@ def test_extract_sparse_format_matches_reference_method(golden):
         d, i = conv._extract_sparse_format(torch.from_numpy(golden[pre + "maxk_out"]))
         assert np.array_equal(d.numpy(), golden[pre + "sp_data"])
         assert np.array_equal(i.numpy(), golden[pre + "sp_index"])
+
+
+def test_synthetic_task_shapes_on_cpu():
+    from spgemm_gnn_b200.train import synthetic_task
+    g, feats, labels, tr, va, te, fin, ncls = synthetic_task("flickr", 0.02, "cpu")
+    n = g.num_nodes()
+    assert feats.shape == (n, 500) and (fin, ncls) == (500, 7) and labels.max() < 7
+    assert int(tr.sum() + va.sum() + te.sum()) == n and 0.55 < tr.float().mean() < 0.77
