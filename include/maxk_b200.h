@@ -155,6 +155,21 @@ MK_API int mk_sspmm_bwd_banked(const mk_part* parts, int64_t num_parts, const in
                                const float* val, const float* dy, const uint16_t* bk_slot,
                                float* dxs, int64_t n_rows, int64_t n_src, int k, int d, void* stream);
 
+/* ---- f-3  epilogue of the aggregation: z = a + b + bias, y = LayerNorm(z) * gamma + beta -------
+ * Replaces `output = h_self + aggregated_feat; output = self.norm(output)`
+ * (utils/maxk_layers.py:174-182; nn.LayerNorm in utils/models.py:122, 260, 382) and its autograd.
+ * b, bias, z may be NULL.  d % 4 == 0, d <= 1024, all pointers 16-byte aligned.
+ * Backward: gz = d loss / d z (== d/da == d/db), dgamma, dbeta, dbias (= column sums of gz, may be
+ * NULL); `workspace` holds 3 * mk_layernorm_parts() * d floats; the parameter gradients are folded
+ * in fixed order.                                                                               */
+MK_API int mk_layernorm_parts(void);
+MK_API int mk_add_layernorm_fwd(const float* a, const float* b, const float* bias,
+                                const float* gamma, const float* beta, float* z, float* y,
+                                float* mean, float* rstd, int64_t n, int d, float eps, void* stream);
+MK_API int mk_layernorm_bwd(const float* gy, const float* z, const float* gamma, const float* mean,
+                            const float* rstd, float* gz, float* dgamma, float* dbeta, float* dbias,
+                            float* workspace, int64_t n, int d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

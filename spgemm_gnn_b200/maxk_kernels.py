@@ -34,7 +34,7 @@ __all__ = [
     "clear_partition_cache", "install_partition", "set_max_nz", "get_max_nz", "launch_count",
     "banked_supported", "cbsr_bank", "maxk_forward_banked", "spgemm_forward_banked",
     "spgemm_backward_banked", "set_banked", "use_banked", "partition_blocked", "backward_blocks",
-    "set_backward_block_mb",
+    "set_backward_block_mb", "add_layernorm_supported", "add_layernorm_forward", "layernorm_backward",
 ]
 
 _MAX_NZ = int(os.environ.get("MAXK_MAX_NZ", "1024"))
@@ -495,3 +495,54 @@ def spgemm_backward_banked(ptr, idx, val, grad_output, bk_slot, num_nodes, num_e
     _lib.check(rc, "mk_sspmm_bwd_banked")
     _launches += 2
     return dxs
+
+
+# ---------------------------------------------------------------------------------------
+# f-3: fused  z = a + b + bias ; y = LayerNorm(z)  (csrc/layernorm.cu)
+# ---------------------------------------------------------------------------------------
+def add_layernorm_supported(a: torch.Tensor, d: int) -> bool:
+    return bool(a.is_cuda and a.dtype == torch.float32 and d % 4 == 0 and 4 <= d <= 1024)
+
+
+def add_layernorm_forward(a, b, bias, gamma, beta, eps: float):
+    """(y, z, mean, rstd) with z = a + b + bias (b, bias optional) and y = LayerNorm(z)*gamma+beta."""
+    global _launches
+    _cuda_contig(a, "input")
+    n, d = a.shape
+    _chk(add_layernorm_supported(a, d), "fused LayerNorm needs CUDA float32, dim % 4 == 0, dim <= 1024")
+    for t, name in ((b, "b"), (bias, "bias"), (gamma, "gamma"), (beta, "beta")):
+        if t is not None:
+            _cuda_contig(t, name)
+            _chk(t.dtype == torch.float32, f"{name} must be float32")
+    y = torch.empty_like(a)
+    z = torch.empty_like(a)
+    mean = torch.empty((n,), dtype=torch.float32, device=a.device)
+    rstd = torch.empty((n,), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = _lib.lib().mk_add_layernorm_fwd(
+            a.data_ptr(), b.data_ptr() if b is not None else None,
+            bias.data_ptr() if bias is not None else None, gamma.data_ptr(), beta.data_ptr(),
+            z.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), n, d, float(eps), _stream())
+    _lib.check(rc, "mk_add_layernorm_fwd")
+    _launches += 1
+    return y, z, mean, rstd
+
+
+def layernorm_backward(grad_y, z, gamma, mean, rstd, want_dbias: bool = False):
+    """(gz, dgamma, dbeta, dbias) of the fused LayerNorm; dbias = column sums of gz or None."""
+    global _launches
+    _cuda_contig(grad_y, "grad_output")
+    n, d = z.shape
+    L = _lib.lib()
+    gz = torch.empty_like(z)
+    dgamma = torch.empty((d,), dtype=torch.float32, device=z.device)
+    dbeta = torch.empty((d,), dtype=torch.float32, device=z.device)
+    dbias = torch.empty((d,), dtype=torch.float32, device=z.device) if want_dbias else None
+    ws = torch.empty((3 * L.mk_layernorm_parts() * d,), dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        rc = L.mk_layernorm_bwd(grad_y.data_ptr(), z.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
+                                rstd.data_ptr(), gz.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                dbias.data_ptr() if want_dbias else None, ws.data_ptr(), n, d, _stream())
+    _lib.check(rc, "mk_layernorm_bwd")
+    _launches += 2
+    return gz, dgamma, dbeta, dbias

@@ -102,6 +102,42 @@ class SpGEMMFunction(Function):
         return dxs, None, None, None, None, None, None
 
 
+class AddLayerNormFunction(Function):
+    """y = LayerNorm(a + b + bias) * gamma + beta in one pass (f-3: the epilogue of the
+    aggregation, utils/maxk_layers.py:174-182).  b and bias may be None."""
+
+    @staticmethod
+    def forward(ctx, a, b, bias, gamma, beta, eps):
+        y, z, mean, rstd = maxk_kernels.add_layernorm_forward(
+            a.contiguous(), None if b is None else b.contiguous(),
+            None if bias is None else bias.contiguous(), gamma.contiguous(), beta.contiguous(), eps)
+        ctx.save_for_backward(z, gamma, mean, rstd)
+        ctx.has = (b is not None, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        z, gamma, mean, rstd = ctx.saved_tensors
+        has_b, has_bias = ctx.has
+        gz, dgamma, dbeta, dbias = maxk_kernels.layernorm_backward(grad_y.contiguous(), z, gamma, mean,
+                                                                   rstd, want_dbias=has_bias)
+        return gz, (gz if has_b else None), dbias, dgamma, dbeta, None
+
+
+def add_layer_norm(a, b, bias, norm):
+    """`norm(a + b + bias)` -- fused when `norm` is an affine nn.LayerNorm over the last dim of CUDA
+    float32 rows (what every model of the reference uses, utils/models.py:122), plain torch ops
+    for any other `norm` module (BatchNorm in GNN_res, None)."""
+    if (isinstance(norm, nn.LayerNorm) and norm.elementwise_affine and norm.bias is not None
+            and a.dim() == 2 and len(norm.normalized_shape) == 1
+            and maxk_kernels.add_layernorm_supported(a, a.shape[1])):
+        return AddLayerNormFunction.apply(a, b, bias, norm.weight, norm.bias, norm.eps)
+    out = a if b is None else a + b
+    if bias is not None:
+        out = out + bias
+    return out if norm is None else norm(out)
+
+
 def aggregate_cbsr(graph: CSRGraph, sp_data, sp_index, weight_kind: str, dim_origin: int):
     """A x Xs for a CBSR table; on a `dist.ShardedGraph` the table is row-sharded and the call
     includes the all-gather (forward) and the reduce-scatter (backward)."""
@@ -191,9 +227,7 @@ class MaxKSAGEConv(nn.Module):
         h_self = self.fc_self(feat)
         h_neigh = self.fc_neigh(feat)
         agg = maxk_aggregate(graph, h_neigh, self.maxk, self.aggregator_type)
-        output = h_self + agg
-        if self.norm is not None:
-            output = self.norm(output)
+        output = add_layer_norm(h_self, agg, None, self.norm)
         return self.feat_drop(output)
 
 

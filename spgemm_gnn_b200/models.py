@@ -25,7 +25,7 @@ import torch.nn.init as init
 from torch.nn import Linear
 
 from .maxk_layers import (CBSRToDenseFunction, MaxKCBSRFunction, MaxKFunction, MaxKGCNConv,
-                          MaxKGINConv, MaxKSAGEConv, _dense_aggregate, aggregate_cbsr)
+                          MaxKGINConv, MaxKSAGEConv, _dense_aggregate, add_layer_norm, aggregate_cbsr)
 
 
 def _aggregate_cbsr(g, sp_data, sp_index, kind, dim):
@@ -62,10 +62,7 @@ class _SAGEConvMean(nn.Module):
         else:
             h = self.feat_drop(feat)
             neigh = _dense_aggregate(g, h, "mean")
-        rst = self.fc_self(h) + self.fc_neigh(neigh) + self.bias
-        if self.norm is not None:
-            rst = self.norm(rst)
-        return rst
+        return add_layer_norm(self.fc_self(h), self.fc_neigh(neigh), self.bias, self.norm)
 
 
 class SAGE(nn.Module):
@@ -107,12 +104,18 @@ class _GraphConvBoth(nn.Module):
         self.bias = nn.Parameter(torch.zeros(feats))
         self.feats = feats
 
-    def forward(self, g, feat, cbsr=None):
+    def pieces(self, g, feat, cbsr=None):
+        """(a, b, bias) with conv(feat) == a + b + bias, left unsummed so the caller can fuse the
+        sum into the LayerNorm that follows."""
         if cbsr is not None:
             out = _aggregate_cbsr(g, cbsr[0], cbsr[1], "both", self.feats)
         else:
             out = _dense_aggregate(g, feat, "both")
-        return out + self.bias
+        return out, None, self.bias
+
+    def forward(self, g, feat, cbsr=None):
+        a, _, bias = self.pieces(g, feat, cbsr)
+        return a + bias
 
 
 class _GINConvSum(nn.Module):
@@ -124,12 +127,16 @@ class _GINConvSum(nn.Module):
         super().__init__()
         self.eps = nn.Parameter(torch.zeros(1))
 
-    def forward(self, g, feat, cbsr=None):
+    def pieces(self, g, feat, cbsr=None):
         if cbsr is not None:
             neigh = _aggregate_cbsr(g, cbsr[0], cbsr[1], "sum", feat.shape[1])
         else:
             neigh = _dense_aggregate(g, feat, "sum")
-        return (1 + self.eps) * feat + neigh
+        return (1 + self.eps) * feat, neigh, None
+
+    def forward(self, g, feat, cbsr=None):
+        a, b, _ = self.pieces(g, feat, cbsr)
+        return a + b
 
 
 class _LinMaxKConvStack(nn.Module):
@@ -172,9 +179,8 @@ class _LinMaxKConvStack(nn.Module):
                 if self.nonlinear == "relu":
                     x = F.relu(x)
                 x = drop(x)
-            x = self.gcnlayers[i](g, x, cbsr)
-            if self.norm:
-                x = self.normlayers[i](x)
+            a, b, bias = self.gcnlayers[i].pieces(g, x, cbsr)
+            x = add_layer_norm(a, b, bias, self.normlayers[i] if self.norm else None)
         return self.lin_out(x)
 
 

@@ -556,3 +556,49 @@ def test_empty_and_extreme_inputs(mk):
     dxs = mk.spgemm_backward(dev(ptr_h), dev(idx_h), dev(val_h), dev(dy_h), dev(wi), n, e, k, d)
     assert_rel(dxs, c_oracle.sspmm_bwd(ptr_h, idx_h, val_h, dy_h, wi),
                c_oracle.sspmm_bwd(ptr_h, idx_h, np.abs(val_h), np.abs(dy_h), wi), "single huge row bwd")
+
+
+@pytest.mark.parametrize("n,d", [(1000, 256), (333, 64), (257, 384), (100, 1024), (64, 100)])
+@pytest.mark.parametrize("with_b,with_bias", [(True, True), (True, False), (False, True), (False, False)])
+def test_fused_add_layernorm_matches_torch(mk, n, d, with_b, with_bias):
+    """f-3 epilogue against a plain PyTorch float64 reference of the same op (fp32 kernel:
+    tolerance 2e-5 relative to the largest element)."""
+    import torch.nn.functional as F
+    from spgemm_gnn_b200.maxk_layers import add_layer_norm
+    gen = torch.Generator().manual_seed(n + d)
+    a = torch.randn(n, d, generator=gen) * 3 + 1
+    b = torch.randn(n, d, generator=gen) if with_b else None
+    bias = torch.randn(d, generator=gen) if with_bias else None
+    gy = torch.randn(n, d, generator=gen)
+    norm = torch.nn.LayerNorm(d)
+    with torch.no_grad():
+        norm.weight.copy_(torch.randn(d, generator=gen))
+        norm.bias.copy_(torch.randn(d, generator=gen))
+    # float64 reference
+    ra = a.double().requires_grad_(True)
+    rb = b.double().requires_grad_(True) if with_b else None
+    rbias = bias.double().requires_grad_(True) if with_bias else None
+    rw, rbeta = norm.weight.detach().double().requires_grad_(True), norm.bias.detach().double().requires_grad_(True)
+    z = ra + (rb if with_b else 0) + (rbias if with_bias else 0)
+    ry = F.layer_norm(z, (d,), rw, rbeta, norm.eps)
+    ry.backward(gy.double())
+    # CUDA path
+    norm = norm.cuda()
+    ca = a.cuda().requires_grad_(True)
+    cb = b.cuda().requires_grad_(True) if with_b else None
+    cbias = bias.cuda().requires_grad_(True) if with_bias else None
+    y = add_layer_norm(ca, cb, cbias, norm)
+    y.backward(gy.cuda())
+
+    def close(got, want, what):
+        err = float((got.detach().cpu().double() - want.detach()).abs().max())
+        assert err <= 2e-5 * float(want.detach().abs().max()) + 1e-12, (what, err)
+
+    close(y, ry, "y")
+    close(ca.grad, ra.grad, "grad a")
+    if with_b:
+        close(cb.grad, rb.grad, "grad b")
+    if with_bias:
+        close(cbias.grad, rbias.grad, "grad bias")
+    close(norm.weight.grad, rw.grad, "grad gamma")
+    close(norm.bias.grad, rbeta.grad, "grad beta")
