@@ -20,4 +20,4 @@ train_epochs(model, g, x, y, m, 3, eval_every=1)
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     _, times = train_epochs(model, g, x, y, m, 3, eval_every=1)
 print("epoch ms", [round(t * 1e3, 2) for t in times])
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=32, max_name_column_width=160))
