@@ -85,13 +85,15 @@ def train_epochs(model: nn.Module, g: CSRGraph, feats, labels, train_mask, epoch
 
 
 def train_epochs_graphed(model: nn.Module, g: CSRGraph, feats, labels, train_mask, epochs: int,
-                         lr: float = 0.01, weight_decay: float = 0.0, warmup: int = 3):
+                         lr: float = 0.01, weight_decay: float = 0.0, warmup: int = 3,
+                         eval_forward: bool = False):
     """Same training step, captured ONCE in a CUDA graph and replayed: on small graphs (Flickr
     shape) an epoch is ~60 short kernels and launch overhead, not the GPU, sets the pace.  The
     hot-path kernels are plain stream launches through the C ABI, so they capture like any other
     kernel; the work records are built (and synchronised on) before the capture.  With a
     `dist.ShardedGraph` the NCCL collectives of the step are captured too.
-    The first `warmup` epochs run eagerly on a side stream (they train too)."""
+    The first `warmup` epochs run eagerly on a side stream (they train too).  With `eval_forward`
+    the per-epoch evaluation forward of the reference loop (maxk_gnn_dgl.py:134) is a second graph."""
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, capturable=True)
     idx = train_mask.nonzero(as_tuple=True)[0]
@@ -121,6 +123,12 @@ def train_epochs_graphed(model: nn.Module, g: CSRGraph, feats, labels, train_mas
             dist.all_reduce(static_loss, group=g.group)
         opt.step()
 
+    def eval_step():
+        model.eval()
+        with torch.no_grad():
+            model(g, feats)
+        model.train()
+
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -128,6 +136,8 @@ def train_epochs_graphed(model: nn.Module, g: CSRGraph, feats, labels, train_mas
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             step()
+            if eval_forward:
+                eval_step()
             torch.cuda.synchronize()
             times.append(time.perf_counter() - t0)
             losses.append(float(static_loss))
@@ -137,11 +147,18 @@ def train_epochs_graphed(model: nn.Module, g: CSRGraph, feats, labels, train_mas
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
         step()
-    # the capture itself did not execute anything
+    eval_graph = None
+    if eval_forward:
+        eval_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(eval_graph):
+            eval_step()
+    # the captures themselves did not execute anything
     for _ in range(epochs - warmup):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         graph.replay()
+        if eval_graph is not None:
+            eval_graph.replay()
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
         losses.append(float(static_loss))
@@ -169,7 +186,7 @@ def main(argv=None):
     ap.add_argument("--eval_every", type=int, default=1, help="eval forward every n epochs (reference: 1)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--cuda_graph", action="store_true",
-                    help="capture the train step in a CUDA graph (single GPU, no eval forward)")
+                    help="capture the train step (and the eval forward) in CUDA graphs")
     a = ap.parse_args(argv)
     if not torch.cuda.is_available():
         raise SystemExit("training needs a CUDA device: the aggregation has no CPU fallback")
@@ -198,9 +215,8 @@ def main(argv=None):
     say(f"{a.dataset}: {n_nodes} nodes, {n_edges} edges; model {a.model} "
         f"{sum(p.numel() for p in model.parameters())} params; {world} GPU(s)")
     if a.cuda_graph:
-        a.eval_every = 0
         losses, times = train_epochs_graphed(model, g, feats, labels, train_mask, a.epochs, a.w_lr,
-                                             a.w_weight_decay)
+                                             a.w_weight_decay, eval_forward=bool(a.eval_every))
     else:
         losses, times = train_epochs(model, g, feats, labels, train_mask, a.epochs, a.w_lr,
                                      a.w_weight_decay, eval_every=a.eval_every,
