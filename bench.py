@@ -68,7 +68,7 @@ def ncu_traffic(kernel, workload):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons during the timed region (NVML, 20 ms period)."""
+    """SM clock and throttle reasons during the timed region (NVML, 5 ms period)."""
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
                0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
 
@@ -99,7 +99,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.005)
 
     def start(self):
         if self.nv is not None:
