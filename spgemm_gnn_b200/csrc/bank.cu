@@ -137,21 +137,43 @@ cbsr_bank_kernel(const float* __restrict__ sp_data, const IdxT* __restrict__ sp_
     }
     __syncthreads();
 
-    // ---- phase 2: warp w moves rows [32w, 32w+32) of the block, lane = entry
+    // ---- phase 2: warp w moves rows [32w, 32w+32) of the block, lane = entry; four rows are
+    //      loaded before any is stored so that the row-to-row latency chain is a quarter as long
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r = 0; r < 32; ++r) {
-        const int lr = w * 32 + r;
-        const int64_t grow = row0 + lr;
-        if (grow >= n) break;
+    constexpr int EPT = (K + 31) / 32;  // entries per lane
+    constexpr int RB = 4;
+    for (int r0 = 0; r0 < 32; r0 += RB) {
+        int cc[RB][EPT], dd[RB][EPT];
+        float vv[RB][EPT];
 #pragma unroll
-        for (int e = lane; e < K; e += 32) {
-            const int c = static_cast<int>(sp_index[grow * K + e]);
-            const float v = sp_data[grow * K + e];
-            const int dsc = desc[lr * DSTRIDE + e];
-            const int p = dsc & 0x7f;
-            bk_data[grow * K + p] = v;
-            bk_slot[grow * K + p] = static_cast<uint16_t>((dsc & 0x80) ? bank_slot_b(c, ra) : bank_slot_a(c));
-            if (bk_index) bk_index[grow * K + p] = static_cast<IdxT>(c);
+        for (int q = 0; q < RB; ++q) {
+            const int lr = w * 32 + r0 + q;
+            const int64_t grow = row0 + lr;
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) {
+                const int e = lane + 32 * j;
+                if (grow < n && e < K) {
+                    cc[q][j] = static_cast<int>(sp_index[grow * K + e]);
+                    vv[q][j] = sp_data[grow * K + e];
+                    dd[q][j] = desc[lr * DSTRIDE + e];
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < RB; ++q) {
+            const int64_t grow = row0 + w * 32 + r0 + q;
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) {
+                const int e = lane + 32 * j;
+                if (grow < n && e < K) {
+                    const int c = cc[q][j], dsc = dd[q][j];
+                    const int p = dsc & 0x7f;
+                    bk_data[grow * K + p] = vv[q][j];
+                    bk_slot[grow * K + p] =
+                        static_cast<uint16_t>((dsc & 0x80) ? bank_slot_b(c, ra) : bank_slot_a(c));
+                    if (bk_index) bk_index[grow * K + p] = static_cast<IdxT>(c);
+                }
+            }
         }
     }
 }
