@@ -35,13 +35,11 @@ __device__ __forceinline__ void load_cols4<uint16_t>(const uint16_t* p, int (&c)
     c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w;
 }
 
-// k <= 32: ask for 32 resident CTAs per SM (64 registers): measured 2.60 ms against 2.63 ms at 28
-// CTAs (72 registers) on the Reddit shape; at k = 64 the cap spills and loses (4.96 vs 4.78 ms).
 template <int K, typename IdxT, int U>
-__global__ void __launch_bounds__(32, (K <= 32 ? 32 : 1))
-sspmm_bwd_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
-                 const float* __restrict__ val, const float* __restrict__ dy,
-                 const IdxT* __restrict__ sp_index, float* __restrict__ dxs, int d, int vec_dy) {
+__device__ __forceinline__ void
+sspmm_bwd_body(const mk_part* __restrict__ parts, const int* __restrict__ idx,
+               const float* __restrict__ val, const float* __restrict__ dy,
+               const IdxT* __restrict__ sp_index, float* __restrict__ dxs, int d, int vec_dy) {
     constexpr int LPN = K / 4;     // lanes per neighbour
     constexpr int G = 32 / LPN;    // neighbours per warp step
     static_assert(K % 4 == 0 && (32 % LPN) == 0, "K must be 4, 8, 16, 32, 64 or 128");
@@ -95,6 +93,24 @@ sspmm_bwd_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
     }
 }
 
+// Two entry points over the same body.  k <= 32: 32 resident CTAs per SM (64 registers), measured
+// 2.60 ms against 2.63 ms at 28 CTAs (72 registers) on the Reddit shape; at k = 64 any register cap
+// spills and loses (4.90-4.96 vs 4.78 ms), so the wide variants keep the compiler's own choice.
+template <int K, typename IdxT, int U>
+__global__ void __launch_bounds__(32, 32)
+sspmm_bwd_kernel_occ32(const mk_part* __restrict__ parts, const int* __restrict__ idx,
+                       const float* __restrict__ val, const float* __restrict__ dy,
+                       const IdxT* __restrict__ sp_index, float* __restrict__ dxs, int d, int vec_dy) {
+    sspmm_bwd_body<K, IdxT, U>(parts, idx, val, dy, sp_index, dxs, d, vec_dy);
+}
+template <int K, typename IdxT, int U>
+__global__ void __launch_bounds__(32)
+sspmm_bwd_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
+                 const float* __restrict__ val, const float* __restrict__ dy,
+                 const IdxT* __restrict__ sp_index, float* __restrict__ dxs, int d, int vec_dy) {
+    sspmm_bwd_body<K, IdxT, U>(parts, idx, val, dy, sp_index, dxs, d, vec_dy);
+}
+
 template <typename IdxT>
 __global__ void __launch_bounds__(32)
 sspmm_bwd_generic_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
@@ -132,7 +148,7 @@ static int launch_bwd_k(const mk_part* parts, int64_t num_parts, const int* idx,
     const int dpad = (d + 3) & ~3;
     const size_t smem = static_cast<size_t>(dpad) * 4;
     if (smem > 200 * 1024) return MK_EUNSUPPORTED;
-    auto kern = sspmm_bwd_kernel<K, IdxT, U>;
+    auto kern = K <= 32 ? sspmm_bwd_kernel_occ32<K, IdxT, U> : sspmm_bwd_kernel<K, IdxT, U>;
     if (smem > 48 * 1024)
         MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
