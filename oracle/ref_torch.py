@@ -12,7 +12,6 @@ tie-free inputs.
 """
 from __future__ import annotations
 
-import math
 import warnings
 
 import torch

@@ -17,7 +17,7 @@ module is the B200 answer BASELINE.json asks for.  One process per GPU, `torch.d
 """
 from __future__ import annotations
 
-from typing import Iterable, Optional, Tuple
+from typing import Iterable, Tuple
 
 import torch
 import torch.distributed as dist

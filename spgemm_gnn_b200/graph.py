@@ -17,7 +17,6 @@ agree, and the container is explicit about which one it stores.
 from __future__ import annotations
 
 import contextlib
-import math
 from dataclasses import dataclass, field
 from typing import Dict, Optional, Tuple
 
