@@ -72,13 +72,14 @@ def _worker(rank, world, port, ret):
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_row_partition_gloo():
-    world = 2
-    port = 29500 + (os.getpid() % 2000)
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_partition_gloo(world):
+    """world 2: 1001 rows -> 501 + 500 (+1 padded); world 3: 334 + 334 + 333 (+1 padded)."""
+    port = 29500 + (os.getpid() % 2000) + world
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
-    assert dict(ret) == {0: "ok", 1: "ok"}, dict(ret)
+    assert dict(ret) == {r: "ok" for r in range(world)}, dict(ret)
 
 
 def test_random_relabel_keeps_the_graph_and_balances_shards():
