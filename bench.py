@@ -116,6 +116,11 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def _peer_on():
+    from spgemm_gnn_b200 import peer
+    return peer.enabled()
+
+
 def workload_config(args, world, n, e):
     return {"workload": f"{args.workload}-shaped synthetic graph, {n} nodes, {e} stored entries "
                         f"(symmetric, self-loops, seed 97), dim_origin {args.dim}, k {args.k}, "
@@ -123,7 +128,9 @@ def workload_config(args, world, n, e):
             "graph": args.workload, "nodes": n, "edges": e, "dim_origin": args.dim, "k": args.k,
             "scale": args.scale,
             "parallelism": "1 GPU" if world == 1 else f"1-D row partition over {world} GPUs, "
-                           "CBSR all-gather fwd + CBSR-grad reduce-scatter bwd (NCCL)",
+                           "CBSR all-gather fwd + CBSR-grad reduce-scatter bwd "
+                           + ("(own NVLink kernels over peer windows, MAXK_PEER_EXCHANGE=1)"
+                              if _peer_on() else "(NCCL)"),
             "l2": "no explicit flush: every step streams inputs larger than L2 "
                   "(edge arrays 8 B/entry + dense rows); the CBSR table is re-used inside one "
                   "launch by construction"}
@@ -285,7 +292,8 @@ def main():
     # ---- timed region: exactly K steps, CUDA events on the launching (current) stream
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     clocks = ClockSampler(local_rank)
-    launches0 = mk.launch_count()
+    from spgemm_gnn_b200 import peer as mpeer
+    launches0 = mk.launch_count() + mpeer.launch_count()
     clocks.start()
     barrier()
     t_start = torch.cuda.Event(enable_timing=True)
@@ -299,7 +307,7 @@ def main():
     t_stop.record()
     barrier()
     clk = clocks.stop()
-    launches = mk.launch_count() - launches0
+    launches = mk.launch_count() + mpeer.launch_count() - launches0
     total_ms = t_start.elapsed_time(t_stop)
     if world > 1:
         tt = torch.tensor([total_ms], device=device, dtype=torch.float64)

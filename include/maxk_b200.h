@@ -170,6 +170,50 @@ MK_API int mk_layernorm_bwd(const float* gy, const float* z, const float* gamma,
                             const float* rstd, float* gz, float* dgamma, float* dbeta, float* dbias,
                             float* workspace, int64_t n, int d, void* stream);
 
+/* ---- e  peer-memory exchange of the row-partitioned path (multi-GPU, one process per GPU) ------
+ * Not in the reference (single GPU; README_INTEGRATED.md:382 lists "Multi-GPU support with NCCL" as
+ * future work).  SURVEY.md section 8e: 1-D row partition, all-gather of the CBSR table in front of
+ * the forward SpGEMM, reduce-scatter of the CBSR gradient behind the backward SSpMM.  These entry
+ * points are that pair as this library's own kernels over peer-mapped memory (NVLink loads/stores),
+ * next to the torch.distributed/NCCL form in spgemm_gnn_b200/dist.py.
+ *
+ * A WINDOW is one device buffer per rank (same size on every rank) that every peer process maps
+ * with CUDA IPC.  Its first MK_PEER_HEADER_BYTES are flags owned by the library (zeroed by
+ * mk_peer_alloc, never to be written by the caller); payload offsets below count from the window
+ * base and must be >= MK_PEER_HEADER_BYTES and 16-byte aligned.  `h_windows[q]` is rank q's window
+ * in the caller's address space (own window: the mk_peer_alloc pointer; others: mk_peer_open).
+ * All ranks must issue the same collectives on a window in the same order.  Kernels that wait for
+ * a peer longer than `timeout_ms` (<= 0: 30 s) set the header's error word and trap.              */
+#define MK_PEER_MAX_RANKS 16
+#define MK_PEER_HEADER_BYTES 1024
+#define MK_PEER_HANDLE_BYTES 64
+MK_API int mk_peer_alloc(int64_t bytes, void** window);
+MK_API int mk_peer_free(void* window);
+MK_API int mk_peer_export(void* window, unsigned char* h_handle /* [MK_PEER_HANDLE_BYTES] */);
+MK_API int mk_peer_open(const unsigned char* h_handle, void** window);
+MK_API int mk_peer_close(void* window);
+/* collectives completed through the window and its error word (synchronises the stream)          */
+MK_API int mk_peer_epoch(const void* window, uint32_t* h_epoch, uint32_t* h_error, void* stream);
+/* All-gather by stores: segment g of this rank (h_src[g], h_bytes[g] bytes, a multiple of 16) lands
+ * at h_offsets[g] + rank * h_bytes[g] in EVERY rank's window.  Up to 4 segments per launch.  When
+ * the call's kernel has finished, this rank's window holds every rank's segments.               */
+MK_API int mk_peer_allgather(void* const* h_windows, int world, int rank, int n_seg,
+                             const void* const* h_src, const int64_t* h_bytes,
+                             const int64_t* h_offsets, int grid, int timeout_ms, void* stream);
+/* mk_cbsr_bank fused with the all-gather: the banked values (fp32), cell offsets (uint16) and the
+ * SORTED column ids of this rank's n rows are written into rows [rank*n, rank*n + n) of the three
+ * [world*n, k] tables at off_data / off_slot / off_index of every rank's window.                */
+MK_API int mk_peer_bank_push(const float* sp_data, const void* sp_index, int index_bytes,
+                             void* const* h_windows, int world, int rank, int64_t off_data,
+                             int64_t off_slot, int64_t off_index, int64_t n, int k, int d,
+                             int timeout_ms, void* stream);
+/* Reduce-scatter by loads: out[0 .. block_bytes/4) = sum over q (rank order, fixed) of the floats at
+ * offset + rank * block_bytes of rank q's window.  When the call's kernel has finished, no peer
+ * reads this rank's window any more (it may be overwritten).                                     */
+MK_API int mk_peer_reduce_scatter(void* const* h_windows, int world, int rank, int64_t offset,
+                                  int64_t block_bytes, float* out, int grid, int timeout_ms,
+                                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@
 // 32*row + bank of every entry.  The assignment is sequential in nature, so it runs one thread
 // per row (32 rows per warp side by side); the data movement runs one warp per row.
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace mk {
 
@@ -43,12 +44,29 @@ __device__ __forceinline__ int bank_slot_b(int c, int ra) {
 // Phase 1 (one thread per row): choose copy and position of every entry, leave one descriptor
 // byte per entry (position | copy << 7) in shared memory.  Phase 2 (one warp per row): move the
 // row with coalesced loads and stores.  bk_index may be null (the forward kernel does not need it).
-template <int K, typename IdxT>
+//
+// PUSH = true is the fused "bank -> all-gather" form of the row-partitioned forward (section 8e):
+// phase 2 stores every row -- banked values, cell offsets and the SORTED column ids the backward
+// needs -- straight into the table of EVERY rank (rows [row_base, row_base + n) of the windows in
+// `pa`), each row leaving as full 128 / 64 / 32-byte lines over NVLink, under the flag protocol of
+// peer.cuh.  The sequential phase 1 runs before the first remote store, so waiting for the peers'
+// ready flags costs nothing.  bk_data / bk_index / bk_slot are not used in that form.
+struct BankPushArgs {
+    PeerSet ps;
+    int world, rank;
+    int64_t off_data, off_slot, off_index;  // byte offsets of the three tables inside a window
+    int64_t row_base;                       // first table row of this rank
+    uint64_t timeout_ns;
+};
+
+template <int K, typename IdxT, bool PUSH>
 __global__ void __launch_bounds__(128)
 cbsr_bank_kernel(const float* __restrict__ sp_data, const IdxT* __restrict__ sp_index,
                  float* __restrict__ bk_data, IdxT* __restrict__ bk_index,
-                 uint16_t* __restrict__ bk_slot, int64_t n, int d) {
+                 uint16_t* __restrict__ bk_slot, int64_t n, int d, const BankPushArgs pa) {
     using Mask = typename BankMask<K>::type;
+    uint32_t epoch = 0;
+    if (PUSH) epoch = peer_begin(pa.ps, pa.world, pa.rank);
     constexpr int CAP = K / 8;  // entries per bank when perfectly balanced == steps per neighbour
     constexpr int DSTRIDE = K + 4;
     __shared__ uint8_t desc[128 * DSTRIDE];
@@ -136,6 +154,7 @@ cbsr_bank_kernel(const float* __restrict__ sp_data, const IdxT* __restrict__ sp_
         }
     }
     __syncthreads();
+    if (PUSH) peer_wait_all_ready(pa.ps, pa.world, pa.rank, epoch, pa.timeout_ns);
 
     // ---- phase 2: warp w moves rows [32w, 32w+32) of the block, lane = entry; four rows are
     //      loaded before any is stored so that the row-to-row latency chain is a quarter as long
@@ -168,29 +187,42 @@ cbsr_bank_kernel(const float* __restrict__ sp_data, const IdxT* __restrict__ sp_
                 if (grow < n && e < K) {
                     const int c = cc[q][j], dsc = dd[q][j];
                     const int p = dsc & 0x7f;
-                    bk_data[grow * K + p] = vv[q][j];
-                    bk_slot[grow * K + p] =
+                    const uint16_t cell =
                         static_cast<uint16_t>((dsc & 0x80) ? bank_slot_b(c, ra) : bank_slot_a(c));
-                    if (bk_index) bk_index[grow * K + p] = static_cast<IdxT>(c);
+                    if (!PUSH) {
+                        bk_data[grow * K + p] = vv[q][j];
+                        bk_slot[grow * K + p] = cell;
+                        if (bk_index) bk_index[grow * K + p] = static_cast<IdxT>(c);
+                    } else {
+                        const int64_t trow = (pa.row_base + grow) * K;
+                        for (int s = 0; s < pa.world; ++s) {  // own copy first, then rank+1, ...
+                            unsigned char* wq = pa.ps.win[(pa.rank + s) % pa.world];
+                            reinterpret_cast<float*>(wq + pa.off_data)[trow + p] = vv[q][j];
+                            reinterpret_cast<uint16_t*>(wq + pa.off_slot)[trow + p] = cell;
+                            reinterpret_cast<IdxT*>(wq + pa.off_index)[trow + e] = static_cast<IdxT>(c);
+                        }
+                    }
                 }
             }
         }
     }
+    if (PUSH) peer_end(pa.ps, pa.world, pa.rank, epoch, pa.timeout_ns);
 }
 
-template <typename IdxT>
+template <typename IdxT, bool PUSH>
 static int launch_bank(const float* sp_data, const void* sp_index, float* bk_data, void* bk_index,
-                       uint16_t* bk_slot, int64_t n, int k, int d, cudaStream_t st) {
-    const int64_t blocks = (n + 127) / 128;
+                       uint16_t* bk_slot, int64_t n, int k, int d, const BankPushArgs& pa,
+                       cudaStream_t st) {
+    const int64_t blocks = PUSH && n == 0 ? 1 : (n + 127) / 128;  // the flag protocol is collective
     if (blocks > 0x7fffffffLL) return MK_EUNSUPPORTED;
     const IdxT* si = static_cast<const IdxT*>(sp_index);
     IdxT* bi = static_cast<IdxT*>(bk_index);
     const unsigned nb = static_cast<unsigned>(blocks);
     switch (k) {
-        case 8: cbsr_bank_kernel<8, IdxT><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d); break;
-        case 16: cbsr_bank_kernel<16, IdxT><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d); break;
-        case 32: cbsr_bank_kernel<32, IdxT><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d); break;
-        case 64: cbsr_bank_kernel<64, IdxT><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d); break;
+        case 8: cbsr_bank_kernel<8, IdxT, PUSH><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d, pa); break;
+        case 16: cbsr_bank_kernel<16, IdxT, PUSH><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d, pa); break;
+        case 32: cbsr_bank_kernel<32, IdxT, PUSH><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d, pa); break;
+        case 64: cbsr_bank_kernel<64, IdxT, PUSH><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d, pa); break;
         default: return MK_EUNSUPPORTED;
     }
     MK_LAUNCH_CHECK("cbsr_bank_kernel");
@@ -215,7 +247,38 @@ extern "C" int mk_cbsr_bank(const float* sp_data, const void* sp_index, int inde
     if (n == 0) return MK_OK;
     if (!sp_data || !sp_index || !bk_data || !bk_slot) return MK_EINVAL;
     cudaStream_t st = mk::as_stream(stream);
+    const mk::BankPushArgs none{};
     return index_bytes == 1
-               ? mk::launch_bank<uint8_t>(sp_data, sp_index, bk_data, bk_index, bk_slot, n, k, d, st)
-               : mk::launch_bank<uint16_t>(sp_data, sp_index, bk_data, bk_index, bk_slot, n, k, d, st);
+               ? mk::launch_bank<uint8_t, false>(sp_data, sp_index, bk_data, bk_index, bk_slot, n, k, d, none, st)
+               : mk::launch_bank<uint16_t, false>(sp_data, sp_index, bk_data, bk_index, bk_slot, n, k, d, none, st);
+}
+
+extern "C" int mk_peer_bank_push(const float* sp_data, const void* sp_index, int index_bytes,
+                                 void* const* h_windows, int world, int rank, int64_t off_data,
+                                 int64_t off_slot, int64_t off_index, int64_t n, int k, int d,
+                                 int timeout_ms, void* stream) {
+    if (n < 0 || d < 1 || k < 1 || k > d) return MK_EINVAL;
+    if (index_bytes != 1 && index_bytes != 2) return MK_EINVAL;
+    if ((index_bytes == 1 && d > 256)) return MK_EINVAL;
+    if (!mk_banked_supported(k, d)) return MK_EUNSUPPORTED;
+    if (world < 1 || world > mk::kMaxPeers || rank < 0 || rank >= world || !h_windows) return MK_EINVAL;
+    if (off_data < mk::kHdrBytes || off_slot < mk::kHdrBytes || off_index < mk::kHdrBytes) return MK_EINVAL;
+    if ((off_data & 15) || (off_slot & 15) || (off_index & 15)) return MK_EINVAL;
+    if (n > 0 && (!sp_data || !sp_index)) return MK_EINVAL;
+    mk::BankPushArgs pa{};
+    for (int q = 0; q < world; ++q) {
+        if (!h_windows[q]) return MK_EINVAL;
+        pa.ps.win[q] = static_cast<unsigned char*>(h_windows[q]);
+    }
+    pa.world = world;
+    pa.rank = rank;
+    pa.off_data = off_data;
+    pa.off_slot = off_slot;
+    pa.off_index = off_index;
+    pa.row_base = static_cast<int64_t>(rank) * n;
+    pa.timeout_ns = static_cast<uint64_t>(timeout_ms > 0 ? timeout_ms : 30000) * 1000000ull;
+    cudaStream_t st = mk::as_stream(stream);
+    return index_bytes == 1
+               ? mk::launch_bank<uint8_t, true>(sp_data, sp_index, nullptr, nullptr, nullptr, n, k, d, pa, st)
+               : mk::launch_bank<uint16_t, true>(sp_data, sp_index, nullptr, nullptr, nullptr, n, k, d, pa, st);
 }

@@ -145,15 +145,46 @@ def allreduce_grads(params: Iterable[torch.nn.Parameter], group=None) -> None:
 # ---------------------------------------------------------------------------------------
 # the sharded hot path as an autograd Function
 # ---------------------------------------------------------------------------------------
-def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, group=None):
+def _peer_path(group, *row_bytes) -> bool:
+    """Peer-memory kernels (peer.py) instead of NCCL: opted in, NCCL group on one box, and every
+    per-rank segment a multiple of 16 bytes (same answer on every rank: same shapes)."""
+    from . import peer
+    return peer.enabled() and peer.available(group) and all(b % 16 == 0 for b in row_bytes)
+
+
+def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, group=None,
+                    keep_index: bool = True):
     """Exchange + local forward SpGEMM of one rank.  Returns (out [num_rows, D], gathered sorted
     column ids [P*R, k] for the backward).  Where the banked kernels apply, the LOCAL rows are
     banked first and the banked values + cell offsets are gathered next to the sorted column ids
-    (7 bytes per entry instead of 5), so that no rank re-banks rows it does not own."""
-    from . import maxk_kernels
-    k = sp_data.shape[1]
+    (7 bytes per entry instead of 5), so that no rank re-banks rows it does not own.
+
+    With `MAXK_PEER_EXCHANGE=1` the exchange runs as this library's own kernels over peer-mapped
+    windows: the banking kernel stores its rows into every rank's table (`peer.bank_push`), the
+    un-banked table goes through `peer.allgather`.  The table window is shared by all layers of a
+    shape, so the column ids are copied out of it when the backward will need them."""
+    from . import maxk_kernels, peer
+    r, k = sp_data.shape
+    ib = sp_index.element_size()
+    world = dist.get_world_size(group)
     part = maxk_kernels.partition(ptr, num_rows)
-    if maxk_kernels.use_banked(part.num_parts, idx.numel(), k, dim_origin):
+    banked = maxk_kernels.use_banked(part.num_parts, idx.numel(), k, dim_origin)
+    if _peer_path(group, r * k * 4, r * k * 2, r * k * ib):
+        rows = world * r
+        if banked:
+            offs, total = peer.layout([rows * k * 4, rows * k * 2, rows * k * ib])
+            win = peer.window("table_banked", total, group)
+            full_data, full_slot, full_index = peer.bank_push(win, sp_data, sp_index, dim_origin, offs)
+            out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, full_data, full_slot, num_rows,
+                                                     idx.numel(), k, dim_origin)
+        else:
+            offs, total = peer.layout([rows * k * 4, rows * k * ib])
+            win = peer.window("table_plain", total, group)
+            full_data, full_index = peer.allgather(win, [sp_data, sp_index], offs)
+            out, _ = maxk_kernels.spgemm_forward(ptr, idx, val, full_data, full_index, num_rows,
+                                                 idx.numel(), k, dim_origin, allow_banked=False)
+        return out, (full_index.clone() if keep_index else full_index)
+    if banked:
         bk_data, _, bk_slot = maxk_kernels.cbsr_bank(sp_data, sp_index, dim_origin, with_index=False)
         full_data, full_slot, full_index = allgather_many([bk_data, bk_slot, sp_index], group)
         out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, full_data, full_slot, num_rows,
@@ -166,9 +197,19 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
 
 
 def sharded_backward(grad_out, full_index, ptr, idx, val, num_rows, dim_origin, group=None):
-    """Local push-form SSpMM into a full-height buffer, folded by one reduce-scatter."""
-    from . import maxk_kernels
-    k = full_index.shape[1]
+    """Local push-form SSpMM into a full-height buffer, folded by one reduce-scatter (NCCL, or
+    with `MAXK_PEER_EXCHANGE=1` by loads from every rank's buffer in fixed rank order)."""
+    from . import maxk_kernels, peer
+    n_src, k = full_index.shape
+    world = dist.get_world_size(group)
+    r = n_src // world
+    if _peer_path(group, r * k * 4):
+        offs, total = peer.layout([n_src * k * 4])
+        win = peer.window("dxs", total, group)
+        dxs_full = win.view(offs[0], (n_src, k), torch.float32)
+        maxk_kernels.spgemm_backward(ptr, idx, val, grad_out, full_index, num_rows, idx.numel(), k,
+                                     dim_origin, out=dxs_full)
+        return peer.reduce_scatter(win, offs[0], r, k)
     dxs_full = maxk_kernels.spgemm_backward(ptr, idx, val, grad_out, full_index, num_rows,
                                             idx.numel(), k, dim_origin)
     return reduce_scatter_rows(dxs_full, group)
@@ -181,7 +222,7 @@ class DistSpGEMMFunction(Function):
     @staticmethod
     def forward(ctx, sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, group):
         out, full_index = sharded_forward(sp_data.contiguous(), sp_index, ptr, idx, val, num_rows,
-                                          dim_origin, group)
+                                          dim_origin, group, keep_index=ctx.needs_input_grad[0])
         k = sp_data.shape[1]
         ctx.save_for_backward(full_index, ptr, idx, val)
         ctx.meta = (num_rows, k, dim_origin, group)

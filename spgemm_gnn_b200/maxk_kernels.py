@@ -382,9 +382,12 @@ def spgemm_forward(ptr, idx, val, sp_data, sp_index, num_nodes, num_edges, dim_s
     return out, sp_index
 
 
-def spgemm_backward(ptr, idx, val, grad_output, sp_index, num_nodes, num_edges, dim_sparse, dim_origin):
+def spgemm_backward(ptr, idx, val, grad_output, sp_index, num_nodes, num_edges, dim_sparse, dim_origin,
+                    *, out: Optional[torch.Tensor] = None):
     """dXs[j,t] = sum over stored e=(r<-j) of val[e] * grad_output[r, sp_index[j,t]]; fp32
-    [sp_index.size(0), dim_sparse] (spgemm_backward_cuda, maxk_cuda_kernels.o@0x1550)."""
+    [sp_index.size(0), dim_sparse] (spgemm_backward_cuda, maxk_cuda_kernels.o@0x1550).
+    `out` (keyword, not in the reference): write into this fp32 [n_src, dim_sparse] buffer, e.g. a
+    peer window (peer.py), instead of a new tensor."""
     global _launches
     _check_graph(ptr, idx, val)
     _cuda_contig(grad_output, "grad_output")
@@ -399,7 +402,13 @@ def spgemm_backward(ptr, idx, val, grad_output, sp_index, num_nodes, num_edges, 
     n_src = sp_index.shape[0]
     nb = backward_blocks(n_src, dim_sparse, num_nodes, num_edges)
     part = partition(ptr, num_nodes) if nb <= 1 else partition_blocked(ptr, idx, num_nodes, n_src, nb)
-    dxs = torch.empty((n_src, dim_sparse), dtype=torch.float32, device=grad_output.device)
+    if out is None:
+        dxs = torch.empty((n_src, dim_sparse), dtype=torch.float32, device=grad_output.device)
+    else:
+        _cuda_contig(out, "out")
+        _chk(out.dtype == torch.float32 and tuple(out.shape) == (n_src, dim_sparse),
+             "out must be float32 [sp_index.size(0), dim_sparse]")
+        dxs = out
     with torch.cuda.device(grad_output.device):
         rc = _lib.lib().mk_sspmm_bwd(
             part.parts.data_ptr(), part.num_parts, idx.data_ptr(), val.data_ptr(),

@@ -59,6 +59,43 @@ def test_argument_validation_without_a_device(built_lib):
     assert L.mk_partition(None, 10, 0, None, None, None, None) == _lib.MK_EINVAL
 
 
+def test_peer_argument_validation_without_a_device(built_lib):
+    """The peer-exchange entry points reject bad windows / offsets before any CUDA call."""
+    L = _lib.lib()
+    VP = ctypes.c_void_p
+    wins = (VP * 16)()
+    wins[0], wins[1] = 0x1000, 0x2000
+    src, nb, off = (VP * 1)(), (ctypes.c_int64 * 1)(64), (ctypes.c_int64 * 1)(1024)
+    src[0] = 0x3000
+    E = _lib.MK_EINVAL
+    assert L.mk_peer_allgather(wins, 0, 0, 1, src, nb, off, 0, 0, None) == E        # world < 1
+    assert L.mk_peer_allgather(wins, 17, 0, 1, src, nb, off, 0, 0, None) == E       # world > 16
+    assert L.mk_peer_allgather(wins, 2, 2, 1, src, nb, off, 0, 0, None) == E        # rank >= world
+    assert L.mk_peer_allgather(wins, 3, 0, 1, src, nb, off, 0, 0, None) == E        # window 2 missing
+    assert L.mk_peer_allgather(wins, 2, 0, 5, src, nb, off, 0, 0, None) == E        # > 4 segments
+    off[0] = 512
+    assert L.mk_peer_allgather(wins, 2, 0, 1, src, nb, off, 0, 0, None) == E        # inside the header
+    off[0], nb[0] = 1024, 24
+    assert L.mk_peer_allgather(wins, 2, 0, 1, src, nb, off, 0, 0, None) == E        # not 16-byte units
+    assert L.mk_peer_reduce_scatter(wins, 2, 0, 1000, 64, None, 0, 0, None) == E     # offset in header
+    assert L.mk_peer_reduce_scatter(wins, 2, 0, 1024, 64, None, 0, 0, None) == E     # no output
+    assert L.mk_peer_bank_push(None, None, 1, wins, 2, 0, 1024, 2048, 4096, 4, 7, 256, 0, None) == _lib.MK_EUNSUPPORTED
+    assert L.mk_peer_bank_push(None, None, 1, wins, 2, 0, 1024, 2048, 4096, 4, 32, 256, 0, None) == E  # null rows
+    assert L.mk_peer_bank_push(None, None, 1, wins, 2, 0, 8, 2048, 4096, 0, 32, 256, 0, None) == E     # header
+    p = VP(0)
+    assert L.mk_peer_alloc(16, ctypes.byref(p)) == E                                # smaller than the header
+    assert L.mk_peer_free(None) == _lib.MK_OK and L.mk_peer_close(None) == _lib.MK_OK
+
+
+def test_peer_layout_and_gating():
+    from spgemm_gnn_b200 import peer
+    offs, total = peer.layout([1000, 4096, 1])
+    assert offs == [1024, 2048, 6144] and total == 6400
+    assert all(o % 256 == 0 for o in offs) and total % 256 == 0
+    assert not peer.enabled()            # opt-in: dist.py stays on NCCL unless asked
+    assert not peer.available()          # no process group here
+
+
 def test_entry_points_refuse_cpu_tensors(built_lib):
     """TORCH_CHECK messages of the reference binding."""
     import maxk_kernels as mk

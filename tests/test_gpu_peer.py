@@ -1,0 +1,46 @@
+"""Peer-memory exchange kernels (csrc/peer.cu, bank.cu PUSH form) on the GPU.
+
+The checks live in tools/peer_check.py and run in a subprocess: a kernel that gives up waiting
+for a peer traps, which would poison this process's CUDA context for every later test."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _run(cmd, timeout=600):
+    # virtual ranks share one device: every stream needs its own hardware queue to run concurrently
+    env = dict(os.environ, MAXK_PEER_TIMEOUT_MS="20000", CUDA_DEVICE_MAX_CONNECTIONS="32")
+    p = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       timeout=timeout)
+    out = p.stdout.decode()
+    assert p.returncode == 0, out[-4000:]
+    return out
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_virtual_ranks_on_one_gpu(built_lib, world):
+    """All-gather by stores, fused bank + push, reduce-scatter by loads: WORLD virtual ranks on one
+    device, one stream each, three rounds through the same windows (epoch / ready / done flags)."""
+    out = _run([sys.executable, "tools/peer_check.py", "virtual", str(world)])
+    assert "virtual peer check: OK" in out
+
+
+def test_sharded_path_through_peer_windows_world1(built_lib):
+    """dist.sharded_forward / sharded_backward with MAXK_PEER_EXCHANGE on an NCCL group of one rank:
+    IPC export, window views, index copy-out, `out=` of spgemm_backward -- against the NCCL path."""
+    out = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "1",
+                "--master-addr", "127.0.0.1", "--master-port", "29641", "tools/peer_check.py", "dist"])
+    assert "dist peer check: OK" in out
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sharded_path_through_peer_windows_two_gpus(built_lib):
+    out = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                "--master-addr", "127.0.0.1", "--master-port", "29642", "tools/peer_check.py", "dist"])
+    assert "dist peer check: OK" in out
