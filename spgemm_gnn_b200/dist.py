@@ -171,19 +171,19 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
     banked = maxk_kernels.use_banked(part.num_parts, idx.numel(), k, dim_origin)
     if _peer_path(group, r * k * 4, r * k * 2, r * k * ib):
         rows = world * r
-        if banked:
-            offs, total = peer.layout([rows * k * 4, rows * k * 2, rows * k * ib])
-            win = peer.window("table_banked", total, group)
-            full_data, full_slot, full_index = peer.bank_push(win, sp_data, sp_index, dim_origin, offs)
-            out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, full_data, full_slot, num_rows,
-                                                     idx.numel(), k, dim_origin)
-        else:
-            offs, total = peer.layout([rows * k * 4, rows * k * ib])
-            win = peer.window("table_plain", total, group)
-            full_data, full_index = peer.allgather(win, [sp_data, sp_index], offs)
-            out, _ = maxk_kernels.spgemm_forward(ptr, idx, val, full_data, full_index, num_rows,
-                                                 idx.numel(), k, dim_origin, allow_banked=False)
-        return out, (full_index.clone() if keep_index else full_index)
+        sizes = [rows * k * 4, rows * k * 2, rows * k * ib] if banked else [rows * k * 4, rows * k * ib]
+        offs, total = peer.layout(sizes)
+        win = peer.window("table_banked" if banked else "table_plain", total, group)
+        if win is not None:
+            if banked:
+                full_data, full_slot, full_index = peer.bank_push(win, sp_data, sp_index, dim_origin, offs)
+                out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, full_data, full_slot, num_rows,
+                                                         idx.numel(), k, dim_origin)
+            else:
+                full_data, full_index = peer.allgather(win, [sp_data, sp_index], offs)
+                out, _ = maxk_kernels.spgemm_forward(ptr, idx, val, full_data, full_index, num_rows,
+                                                     idx.numel(), k, dim_origin, allow_banked=False)
+            return out, (full_index.clone() if keep_index else full_index)
     if banked:
         bk_data, _, bk_slot = maxk_kernels.cbsr_bank(sp_data, sp_index, dim_origin, with_index=False)
         full_data, full_slot, full_index = allgather_many([bk_data, bk_slot, sp_index], group)
@@ -206,10 +206,11 @@ def sharded_backward(grad_out, full_index, ptr, idx, val, num_rows, dim_origin, 
     if _peer_path(group, r * k * 4):
         offs, total = peer.layout([n_src * k * 4])
         win = peer.window("dxs", total, group)
-        dxs_full = win.view(offs[0], (n_src, k), torch.float32)
-        maxk_kernels.spgemm_backward(ptr, idx, val, grad_out, full_index, num_rows, idx.numel(), k,
-                                     dim_origin, out=dxs_full)
-        return peer.reduce_scatter(win, offs[0], r, k)
+        if win is not None:
+            dxs_full = win.view(offs[0], (n_src, k), torch.float32)
+            maxk_kernels.spgemm_backward(ptr, idx, val, grad_out, full_index, num_rows, idx.numel(), k,
+                                         dim_origin, out=dxs_full)
+            return peer.reduce_scatter(win, offs[0], r, k)
     dxs_full = maxk_kernels.spgemm_backward(ptr, idx, val, grad_out, full_index, num_rows,
                                             idx.numel(), k, dim_origin)
     return reduce_scatter_rows(dxs_full, group)

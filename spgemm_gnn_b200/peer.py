@@ -34,7 +34,7 @@ HANDLE_BYTES = 64            # MK_PEER_HANDLE_BYTES
 MAX_RANKS = 16               # MK_PEER_MAX_RANKS
 _ALIGN = 256
 
-_ENABLED = os.environ.get("MAXK_PEER_EXCHANGE", "0") != "0"
+_ENABLED = os.environ.get("MAXK_PEER_EXCHANGE", "0") != "0"   # "1": peer kernels, "0": NCCL
 _TIMEOUT_MS = int(os.environ.get("MAXK_PEER_TIMEOUT_MS", "30000"))
 _launches = 0
 
@@ -102,28 +102,48 @@ class PeerWindow:
         return w
 
     @classmethod
-    def create(cls, nbytes: int, group=None, device=None) -> "PeerWindow":
-        """Collective over `group`: allocate, export, exchange handles, map every peer."""
+    def create(cls, nbytes: int, group=None, device=None) -> Optional["PeerWindow"]:
+        """Collective over `group`: allocate, export, exchange handles, map every peer.  A failure
+        on any rank (no IPC in this sandbox, out of memory, ...) is agreed on by all ranks, which
+        then all return None -- nobody is left waiting in a collective."""
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if world > MAX_RANKS:
             raise RuntimeError(f"peer windows support at most {MAX_RANKS} ranks")
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
-        w = cls._alloc(nbytes, world, rank, device)
         L = _lib.lib()
-        buf = ctypes.create_string_buffer(HANDLE_BYTES)
-        _lib.check(L.mk_peer_export(w.local, buf), "mk_peer_export")
-        handles: List[Optional[bytes]] = [None] * world
-        dist.all_gather_object(handles, (bytes(buf.raw), w.nbytes), group=group)
-        with torch.cuda.device(w.device):
-            for q, (h, nb) in enumerate(handles):
-                if nb != w.nbytes:
-                    raise RuntimeError("peer window sizes differ between ranks")
-                if q == rank:
-                    continue
-                p = ctypes.c_void_p(0)
-                _lib.check(L.mk_peer_open(h, ctypes.byref(p)), "mk_peer_open")
-                w.opened.append(int(p.value))
-                w.ptrs[q] = int(p.value)
+        w, handle, why = None, None, ""
+        try:
+            w = cls._alloc(nbytes, world, rank, device)
+            buf = ctypes.create_string_buffer(HANDLE_BYTES)
+            _lib.check(L.mk_peer_export(w.local, buf), "mk_peer_export")
+            handle = bytes(buf.raw)
+        except Exception as exc:  # noqa: BLE001 -- reported below, after everybody has met
+            why = f"rank {rank}: {exc}"
+        got: List[Optional[tuple]] = [None] * world
+        dist.all_gather_object(got, (handle, int(nbytes), why), group=group)
+        ok = all(h is not None and nb == int(nbytes) for h, nb, _ in got)
+        if ok:
+            try:
+                with torch.cuda.device(device):
+                    for q, (h, _, _) in enumerate(got):
+                        if q == rank:
+                            continue
+                        p = ctypes.c_void_p(0)
+                        _lib.check(L.mk_peer_open(h, ctypes.byref(p)), "mk_peer_open")
+                        w.opened.append(int(p.value))
+                        w.ptrs[q] = int(p.value)
+            except Exception as exc:  # noqa: BLE001
+                ok, why = False, f"rank {rank}: {exc}"
+        flag = torch.tensor([1 if ok else 0], device=device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            reasons = "; ".join(r for _, _, r in got if r) or why or "a peer failed to map the window"
+            if w is not None:
+                w.close()
+            if rank == 0:
+                import warnings
+                warnings.warn(f"peer windows unavailable ({reasons}); staying on NCCL collectives")
+            return None
         return w
 
     @classmethod
@@ -178,15 +198,20 @@ class PeerWindow:
 _windows: Dict[tuple, PeerWindow] = {}
 
 
-def window(kind: str, nbytes: int, group=None) -> PeerWindow:
+def window(kind: str, nbytes: int, group=None) -> Optional[PeerWindow]:
     """Cached window of exactly `nbytes` for `kind`; creating one is a collective, so every rank
-    must ask for the same windows in the same order (they do: same model, same shapes)."""
+    must ask for the same windows in the same order (they do: same model, same shapes).  Returns
+    None -- on every rank -- when the windows cannot be set up; the peer path is then switched off
+    for the rest of the process and dist.py stays on its NCCL collectives."""
     key = (kind, int(nbytes), id(group) if group is not None else 0, torch.cuda.current_device())
     w = _windows.get(key)
     if w is None:
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("peer windows must exist before CUDA graph capture (run one eager step first)")
         w = PeerWindow.create(nbytes, group)
+        if w is None:
+            set_enabled(False)
+            return None
         _windows[key] = w
     return w
 
