@@ -2,7 +2,7 @@
 """Checks of the peer-memory exchange kernels (csrc/peer.cu, bank.cu PUSH form, peer.py).
 
     python tools/peer_check.py virtual [WORLD]     one GPU: WORLD virtual ranks, one stream each
-    torchrun --nproc-per-node N tools/peer_check.py dist [--bench]     N GPUs, NCCL group
+    torchrun --nproc-per-node N tools/peer_check.py dist [--bench] [--products]    N GPUs, NCCL group
 
 `virtual` exercises the kernels and their flag protocol inside one process (every "peer" window
 is a local buffer), `dist` runs the sharded forward/backward of dist.py with the peer path and
@@ -114,8 +114,12 @@ def distributed(bench: bool) -> int:
     cases = [("small k32", synthetic_graph(20001, 20001 * 150, seed=97, device=dev), 32, 256),
              ("small k16 plain", synthetic_graph(9001, 9001 * 20, seed=3, device=dev), 16, 128)]
     if bench:
-        cases.append(("reddit k32", shaped_graph("reddit", device=dev), 32, 256))
+        cases.append(("reddit k32", "reddit", 32, 256))
+    if "--products" in sys.argv:
+        cases.append(("ogbn-products k32", "ogbn-products", 32, 256))
     for name, g, k, d in cases:
+        if isinstance(g, str):
+            g = shaped_graph(g, device=dev)
         local, r0, r1 = mdist.shard_graph(g, rank, world)
         val = mdist.shard_edge_weights(g, local, r0, r1, "mean")
         n_rows = local.num_nodes()
@@ -160,6 +164,8 @@ def distributed(bench: bool) -> int:
             if bench:
                 msg += f" | ms/layer NCCL {times[False]:.3f}  peer {times[True]:.3f}"
             print(msg, "OK" if good.item() else "FAIL", flush=True)
+        del g, local, val, x, dy, sd, si, res
+        torch.cuda.empty_cache()
     peer.set_enabled(False)
     torch.cuda.synchronize()
     dist.barrier()
