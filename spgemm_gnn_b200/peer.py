@@ -14,9 +14,10 @@ A `PeerWindow` is one device buffer per rank, mapped into every process of the g
 (`mk_peer_export` / `mk_peer_open`, handles exchanged with `all_gather_object`).  The kernels keep
 their flags and epoch counters in the window's header, so captured CUDA graphs replay correctly.
 
-Opt-in: `MAXK_PEER_EXCHANGE=1` (or `set_enabled(True)`); dist.py keeps NCCL as the default until
-the peer path has been measured at the same world size.  There is no CPU form: on a gloo group
-`available()` is False and dist.py stays on its collectives.
+On by default for NCCL groups of 2..16 ranks (checked against the NCCL path at 2 and 8 GPUs:
+forward bit-equal, profiles/r1_peer_exchange.md); `MAXK_PEER_EXCHANGE=0` (or `set_enabled(False)`)
+keeps dist.py on NCCL, and so does any failure to map the windows (agreed on by all ranks).  There
+is no CPU form: on a gloo group `available()` is False and dist.py stays on its collectives.
 """
 from __future__ import annotations
 
@@ -34,8 +35,8 @@ HANDLE_BYTES = 64            # MK_PEER_HANDLE_BYTES
 MAX_RANKS = 16               # MK_PEER_MAX_RANKS
 _ALIGN = 256
 
-_ENABLED = os.environ.get("MAXK_PEER_EXCHANGE", "0") != "0"   # "1": peer kernels, "0": NCCL
-_TIMEOUT_MS = int(os.environ.get("MAXK_PEER_TIMEOUT_MS", "30000"))
+_ENABLED = os.environ.get("MAXK_PEER_EXCHANGE", "1") != "0"   # "0": stay on NCCL collectives
+_TIMEOUT_MS = int(os.environ.get("MAXK_PEER_TIMEOUT_MS", "120000"))
 _launches = 0
 
 
@@ -56,7 +57,7 @@ def available(group=None) -> bool:
     """The peer kernels need CUDA devices of one box under an NCCL group of at most 16 ranks."""
     if not (dist.is_available() and dist.is_initialized() and torch.cuda.is_available()):
         return False
-    return dist.get_backend(group) == "nccl" and dist.get_world_size(group) <= MAX_RANKS
+    return dist.get_backend(group) == "nccl" and 1 <= dist.get_world_size(group) <= MAX_RANKS
 
 
 def layout(segment_bytes: Sequence[int]) -> Tuple[List[int], int]:

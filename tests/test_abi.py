@@ -92,8 +92,7 @@ def test_peer_layout_and_gating():
     offs, total = peer.layout([1000, 4096, 1])
     assert offs == [1024, 2048, 6144] and total == 6400
     assert all(o % 256 == 0 for o in offs) and total % 256 == 0
-    assert not peer.enabled()            # opt-in: dist.py stays on NCCL unless asked
-    assert not peer.available()          # no process group here
+    assert not peer.available()          # no NCCL process group here: dist.py stays on its collectives
 
 
 def test_entry_points_refuse_cpu_tensors(built_lib):
