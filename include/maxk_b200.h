@@ -134,6 +134,15 @@ MK_API int mk_sspmm_bwd(const mk_part* parts, int64_t num_parts, const int32_t* 
                         const float* val, const float* dy, const void* sp_index, int index_bytes,
                         float* dxs, int64_t n_rows, int64_t n_src, int k, int d, void* stream);
 
+/* Experimental form of mk_sspmm_bwd (same contract, k in {32, 64}, uint8 ids): `tma_neighbours` of the
+ * 128/k neighbours a warp handles per step send their k contributions as ONE bulk reduction from
+ * shared memory (cp.reduce.async.bulk, the TMA unit) instead of k/4 vector reductions through
+ * L1TEX -- the backward is bound by the SM -> L2 request path.  Off by default (MAXK_BWD_TMA).      */
+MK_API int mk_sspmm_bwd_tma(const mk_part* parts, int64_t num_parts, const int32_t* idx,
+                            const float* val, const float* dy, const void* sp_index, int index_bytes,
+                            float* dxs, int64_t n_rows, int64_t n_src, int k, int d,
+                            int tma_neighbours, void* stream);
+
 /* ---- banked CBSR: the conflict-free internal form of the hot path ----------------------------
  * Not in the reference.  The forward / backward kernels above are bound by shared-memory bank
  * conflicts (3.6 wavefronts per access measured); mk_cbsr_bank re-orders the k entries of every

@@ -111,6 +111,112 @@ sspmm_bwd_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
     sspmm_bwd_body<K, IdxT, U>(parts, idx, val, dy, sp_index, dxs, d, vec_dy);
 }
 
+// ---- experimental: part of the reductions through the TMA unit ---------------------------------
+// The kernel above is bound by the SM -> L2 request path (l1tex__m_l1tex2xbar_req_cycles_active 91 %,
+// profiles/r1_final_*): every stored entry costs k/4 lane-level REDG.128.  Here NT of the G
+// neighbours of a warp step take another road: their k contributions are staged in shared memory
+// (one STS.128 per lane) and leave as ONE bulk reduction per neighbour,
+// `cp.reduce.async.bulk.global.shared::cta.add.f32` (SASS UBLKRED), issued by the first lane of
+// the group -- k*4 bytes per request through the TMA unit instead of k/4 requests through L1TEX.
+// NBUF staging buffers per group; the issuing lane waits for the bulk group of NBUF steps ago to
+// have READ its buffer before the group overwrites it.  NT = G sends everything through TMA,
+// smaller NT splits the traffic between the two paths.  Not the default: to be measured
+// (tools/kernel_sweep.py --bwd-tma).
+__device__ __forceinline__ void bulk_red_add_f32(float* gdst, const float* ssrc, int bytes) {
+    const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(ssrc));
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(sa), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <int K, typename IdxT, int U, int NT>
+__global__ void __launch_bounds__(32)
+sspmm_bwd_tma_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
+                     const float* __restrict__ val, const float* __restrict__ dy,
+                     const IdxT* __restrict__ sp_index, float* __restrict__ dxs, int d, int vec_dy,
+                     int stage_off) {
+    constexpr int LPN = K / 4;   // lanes per neighbour
+    constexpr int G = 32 / LPN;  // neighbours per warp step
+    constexpr int NBUF = 4;
+    static_assert(NT >= 1 && NT <= G, "NT counts neighbours of a step");
+    extern __shared__ __align__(16) float dys[];   // dynamic shared memory starts 128-byte aligned
+    float* __restrict__ stage = dys + stage_off;  // [NBUF][NT][K]; stage_off is a multiple of 32 floats
+    const int lane = lane_id();
+    const int g = lane / LPN;
+    const int t = lane % LPN;
+    const bool via_tma = g < NT;
+    const bool issuer = via_tma && t == 0;
+    const mk_part rec = parts[blockIdx.x];
+    if (rec.len == 0) return;
+
+    const float* __restrict__ dyr = dy + static_cast<int64_t>(rec.row) * d;
+    if (vec_dy) {
+        for (int c = lane * 4; c < d; c += 128)
+            *reinterpret_cast<float4*>(dys + c) = ld_stream_f4(dyr + c);
+    } else {
+        for (int c = lane; c < d; c += 32) dys[c] = ld_stream_f1(dyr + c);
+    }
+    __syncwarp();
+
+    const int end = rec.loc + rec.len;
+    for (int base = rec.loc; base < end; base += 32) {
+        const int n_here = min(32, end - base);
+        int my_nz = 0;
+        float my_v = 0.f;
+        if (lane < n_here) {
+            my_nz = ld_stream_i1(idx + base + lane);
+            my_v = ld_stream_f1(val + base + lane);
+        }
+        for (int i = 0; i < n_here; i += G * U) {
+            int cv[U][4];
+            int nzv[U];
+            float vv[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = i + u * G + g;
+                nzv[u] = __shfl_sync(kFull, my_nz, e & 31);
+                vv[u] = __shfl_sync(kFull, my_v, e & 31);
+                ok[u] = e < n_here;
+                if (ok[u]) load_cols4<IdxT>(sp_index + static_cast<int64_t>(nzv[u]) * K + 4 * t, cv[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float v = vv[u];
+                float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok[u]) c = make_float4(v * dys[cv[u][0]], v * dys[cv[u][1]], v * dys[cv[u][2]], v * dys[cv[u][3]]);
+                float* __restrict__ buf = stage + ((u % NBUF) * NT + g) * K;
+                // the bulk reduction that read this buffer NBUF steps ago must be done with it
+                if (issuer) bulk_wait_read<NBUF - 1>();
+                __syncwarp();
+                if (via_tma) {
+                    if (ok[u]) {
+                        *reinterpret_cast<float4*>(buf + 4 * t) = c;
+                        fence_async_smem();
+                    }
+                } else if (ok[u]) {
+                    red_add_f4(dxs + static_cast<int64_t>(nzv[u]) * K + 4 * t, c.x, c.y, c.z, c.w);
+                }
+                __syncwarp();
+                if (issuer) {
+                    if (ok[u]) bulk_red_add_f32(dxs + static_cast<int64_t>(nzv[u]) * K, buf, K * 4);
+                    bulk_commit();
+                }
+            }
+        }
+    }
+    if (issuer) bulk_wait_all();
+}
+
 template <typename IdxT>
 __global__ void __launch_bounds__(32)
 sspmm_bwd_generic_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
@@ -207,4 +313,61 @@ extern "C" int mk_sspmm_bwd(const mk_part* parts, int64_t num_parts, const int32
     return index_bytes == 1
                ? mk::launch_bwd<uint8_t>(parts, num_parts, idx, val, dy, sp_index, dxs, k, d, st)
                : mk::launch_bwd<uint16_t>(parts, num_parts, idx, val, dy, sp_index, dxs, k, d, st);
+}
+
+namespace mk {
+
+template <int K, typename IdxT, int NT>
+static int launch_bwd_tma_k(const mk_part* parts, int64_t num_parts, const int* idx, const float* val,
+                            const float* dy, const void* sp_index, float* dxs, int d, cudaStream_t st) {
+    constexpr int U = (K / 4 >= 8) ? 8 : (K / 4);
+    constexpr int G = 128 / K;
+    static_assert(U % 4 == 0 || U < 4, "staging buffers are indexed by u % 4");
+    const int stage_off = (d + 31) & ~31;  // floats; keeps the staging area 128-byte aligned
+    const size_t smem = (static_cast<size_t>(stage_off) + 4 * NT * K) * 4;
+    if (smem > 200 * 1024) return MK_EUNSUPPORTED;
+    auto kern = sspmm_bwd_tma_kernel<K, IdxT, U, (NT <= G ? NT : G)>;
+    if (smem > 48 * 1024)
+        MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    const int vec_dy = (d % 4 == 0) && (reinterpret_cast<uintptr_t>(dy) % 16 == 0);
+    kern<<<static_cast<unsigned>(num_parts), 32, smem, st>>>(
+        parts, idx, val, dy, static_cast<const IdxT*>(sp_index), dxs, d, vec_dy, stage_off);
+    MK_LAUNCH_CHECK("sspmm_bwd_tma_kernel");
+    return MK_OK;
+}
+
+template <int K, typename IdxT>
+static int launch_bwd_tma(const mk_part* parts, int64_t num_parts, const int* idx, const float* val,
+                          const float* dy, const void* sp_index, float* dxs, int d, int nt,
+                          cudaStream_t st) {
+    switch (nt) {
+        case 1: return launch_bwd_tma_k<K, IdxT, 1>(parts, num_parts, idx, val, dy, sp_index, dxs, d, st);
+        case 2: return launch_bwd_tma_k<K, IdxT, 2>(parts, num_parts, idx, val, dy, sp_index, dxs, d, st);
+        case 4: return launch_bwd_tma_k<K, IdxT, 4>(parts, num_parts, idx, val, dy, sp_index, dxs, d, st);
+        default: return MK_EUNSUPPORTED;
+    }
+}
+
+}  // namespace mk
+
+extern "C" int mk_sspmm_bwd_tma(const mk_part* parts, int64_t num_parts, const int32_t* idx,
+                                const float* val, const float* dy, const void* sp_index,
+                                int index_bytes, float* dxs, int64_t n_rows, int64_t n_src, int k,
+                                int d, int tma_neighbours, void* stream) {
+    if (n_rows < 0 || n_src < 0 || num_parts < 0 || d < 1 || k < 1 || k > d) return MK_EINVAL;
+    if (index_bytes != 1 || d > 256) return MK_EUNSUPPORTED;
+    if (k != 32 && k != 64) return MK_EUNSUPPORTED;
+    if (tma_neighbours < 1 || tma_neighbours > 128 / k) return MK_EUNSUPPORTED;
+    if (n_src == 0) return MK_OK;
+    if (!dxs || (reinterpret_cast<uintptr_t>(dxs) & 15) || (reinterpret_cast<uintptr_t>(sp_index) & 3))
+        return MK_EINVAL;
+    cudaStream_t st = mk::as_stream(stream);
+    MK_CUDA_TRY(cudaMemsetAsync(dxs, 0, static_cast<size_t>(n_src) * k * sizeof(float), st));
+    if (n_rows == 0 || num_parts == 0) return MK_OK;
+    if (!parts || !dy || !sp_index) return MK_EINVAL;
+    if (num_parts > 0x7fffffffLL) return MK_EUNSUPPORTED;
+    if (k == 32)
+        return mk::launch_bwd_tma<32, uint8_t>(parts, num_parts, idx, val, dy, sp_index, dxs, d, tma_neighbours, st);
+    return mk::launch_bwd_tma<64, uint8_t>(parts, num_parts, idx, val, dy, sp_index, dxs, d, tma_neighbours, st);
 }

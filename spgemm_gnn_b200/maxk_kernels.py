@@ -33,13 +33,16 @@ __all__ = [
     "maxk_forward_cbsr", "cbsr_scatter", "cbsr_gather", "partition",
     "clear_partition_cache", "install_partition", "set_max_nz", "get_max_nz", "launch_count",
     "banked_supported", "cbsr_bank", "maxk_forward_banked", "spgemm_forward_banked",
-    "spgemm_backward_banked", "set_banked", "use_banked", "partition_blocked", "backward_blocks",
+    "spgemm_backward_banked", "set_banked", "set_backward_tma", "use_banked", "partition_blocked", "backward_blocks",
     "set_backward_block_mb", "add_layernorm_supported", "add_layernorm_forward", "layernorm_backward",
 ]
 
 _MAX_NZ = int(os.environ.get("MAXK_MAX_NZ", "1024"))
 _BANKED = os.environ.get("MAXK_BANKED", "1") != "0"
 _BANKED_MIN_RECORD = 96   # mean stored entries per work record below which banking does not pay
+# experimental backward: this many of the 128/k neighbours of a warp step reduce through the TMA unit
+# (csrc/sspmm_bwd.cu, mk_sspmm_bwd_tma); 0 = the shipped kernel
+_BWD_TMA = int(os.environ.get("MAXK_BWD_TMA", "0"))
 _launches = 0  # kernels launched through this module (bench.py reports it)
 
 
@@ -58,6 +61,13 @@ def set_max_nz(max_nz: int) -> None:
 
 def get_max_nz() -> int:
     return _MAX_NZ
+
+
+def set_backward_tma(neighbours: int) -> None:
+    """Experimental: route `neighbours` (1, 2 or 4) of the 128/k neighbours a warp handles per step
+    of the backward through bulk shared->global reductions (TMA) instead of REDG.  0 switches back."""
+    global _BWD_TMA
+    _BWD_TMA = int(neighbours)
 
 
 def set_banked(on: bool) -> None:
@@ -409,11 +419,18 @@ def spgemm_backward(ptr, idx, val, grad_output, sp_index, num_nodes, num_edges, 
         _chk(out.dtype == torch.float32 and tuple(out.shape) == (n_src, dim_sparse),
              "out must be float32 [sp_index.size(0), dim_sparse]")
         dxs = out
+    tma = _BWD_TMA if (ib == 1 and dim_sparse in (32, 64) and 1 <= _BWD_TMA <= 128 // dim_sparse) else 0
     with torch.cuda.device(grad_output.device):
-        rc = _lib.lib().mk_sspmm_bwd(
-            part.parts.data_ptr(), part.num_parts, idx.data_ptr(), val.data_ptr(),
-            grad_output.data_ptr(), sp_index.data_ptr(), ib, dxs.data_ptr(), num_nodes, n_src,
-            dim_sparse, dim_origin, _stream())
+        if tma:
+            rc = _lib.lib().mk_sspmm_bwd_tma(
+                part.parts.data_ptr(), part.num_parts, idx.data_ptr(), val.data_ptr(),
+                grad_output.data_ptr(), sp_index.data_ptr(), ib, dxs.data_ptr(), num_nodes, n_src,
+                dim_sparse, dim_origin, tma, _stream())
+        else:
+            rc = _lib.lib().mk_sspmm_bwd(
+                part.parts.data_ptr(), part.num_parts, idx.data_ptr(), val.data_ptr(),
+                grad_output.data_ptr(), sp_index.data_ptr(), ib, dxs.data_ptr(), num_nodes, n_src,
+                dim_sparse, dim_origin, _stream())
     _lib.check(rc, "mk_sspmm_bwd")
     _launches += 2  # memset + kernel
     return dxs
