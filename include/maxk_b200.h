@@ -134,10 +134,11 @@ MK_API int mk_sspmm_bwd(const mk_part* parts, int64_t num_parts, const int32_t* 
                         const float* val, const float* dy, const void* sp_index, int index_bytes,
                         float* dxs, int64_t n_rows, int64_t n_src, int k, int d, void* stream);
 
-/* Experimental form of mk_sspmm_bwd (same contract, k in {32, 64}, uint8 ids): `tma_neighbours` of the
- * 128/k neighbours a warp handles per step send their k contributions as ONE bulk reduction from
+/* Experimental form of mk_sspmm_bwd (same contract, k == 32, uint8 ids): `tma_neighbours` (1, 2 or 4)
+ * of the 4 neighbours a warp handles per step send their k contributions as ONE bulk reduction from
  * shared memory (cp.reduce.async.bulk, the TMA unit) instead of k/4 vector reductions through
- * L1TEX -- the backward is bound by the SM -> L2 request path.  Off by default (MAXK_BWD_TMA).      */
+ * L1TEX -- the backward is bound by the SM -> L2 request path.  Measured slower on a B200 (2.61 ms ->
+ * 4.0-4.4 ms on the Reddit shape); off by default (MAXK_BWD_TMA), kept as the record of the experiment. */
 MK_API int mk_sspmm_bwd_tma(const mk_part* parts, int64_t num_parts, const int32_t* idx,
                             const float* val, const float* dy, const void* sp_index, int index_bytes,
                             float* dxs, int64_t n_rows, int64_t n_src, int k, int d,

@@ -120,8 +120,11 @@ sspmm_bwd_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
 // the group -- k*4 bytes per request through the TMA unit instead of k/4 requests through L1TEX.
 // NBUF staging buffers per group; the issuing lane waits for the bulk group of NBUF steps ago to
 // have READ its buffer before the group overwrites it.  NT = G sends everything through TMA,
-// smaller NT splits the traffic between the two paths.  Not the default: to be measured
-// (tools/kernel_sweep.py --bwd-tma).
+// smaller NT splits the traffic between the two paths.
+// MEASURED SLOWER on a B200 (tools/bwd_tma_probe.py, profiles/peer_r1/bwd_tma_probe.log; Reddit shape,
+// k = 32): 2.61 ms shipped kernel, 4.02 / 4.26 / 4.43 ms with NT = 1 / 2 / 4 -- about 11 cycles per
+// 128-byte bulk reduction and SM, against 6.6 cycles per stored entry for the eight REDG.128.  Kept
+// behind MAXK_BWD_TMA as the record of that experiment; not a product path.
 __device__ __forceinline__ void bulk_red_add_f32(float* gdst, const float* ssrc, int bytes) {
     const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(ssrc));
     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
@@ -357,8 +360,8 @@ extern "C" int mk_sspmm_bwd_tma(const mk_part* parts, int64_t num_parts, const i
                                 int d, int tma_neighbours, void* stream) {
     if (n_rows < 0 || n_src < 0 || num_parts < 0 || d < 1 || k < 1 || k > d) return MK_EINVAL;
     if (index_bytes != 1 || d > 256) return MK_EUNSUPPORTED;
-    if (k != 32 && k != 64) return MK_EUNSUPPORTED;
-    if (tma_neighbours < 1 || tma_neighbours > 128 / k) return MK_EUNSUPPORTED;
+    if (k != 32) return MK_EUNSUPPORTED;  // the only width measured on a B200 so far
+    if (tma_neighbours != 1 && tma_neighbours != 2 && tma_neighbours != 4) return MK_EUNSUPPORTED;
     if (n_src == 0) return MK_OK;
     if (!dxs || (reinterpret_cast<uintptr_t>(dxs) & 15) || (reinterpret_cast<uintptr_t>(sp_index) & 3))
         return MK_EINVAL;
@@ -367,7 +370,5 @@ extern "C" int mk_sspmm_bwd_tma(const mk_part* parts, int64_t num_parts, const i
     if (n_rows == 0 || num_parts == 0) return MK_OK;
     if (!parts || !dy || !sp_index) return MK_EINVAL;
     if (num_parts > 0x7fffffffLL) return MK_EUNSUPPORTED;
-    if (k == 32)
-        return mk::launch_bwd_tma<32, uint8_t>(parts, num_parts, idx, val, dy, sp_index, dxs, d, tma_neighbours, st);
-    return mk::launch_bwd_tma<64, uint8_t>(parts, num_parts, idx, val, dy, sp_index, dxs, d, tma_neighbours, st);
+    return mk::launch_bwd_tma<32, uint8_t>(parts, num_parts, idx, val, dy, sp_index, dxs, d, tma_neighbours, st);
 }

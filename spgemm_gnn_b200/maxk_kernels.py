@@ -40,8 +40,8 @@ __all__ = [
 _MAX_NZ = int(os.environ.get("MAXK_MAX_NZ", "1024"))
 _BANKED = os.environ.get("MAXK_BANKED", "1") != "0"
 _BANKED_MIN_RECORD = 96   # mean stored entries per work record below which banking does not pay
-# experimental backward: this many of the 128/k neighbours of a warp step reduce through the TMA unit
-# (csrc/sspmm_bwd.cu, mk_sspmm_bwd_tma); 0 = the shipped kernel
+# experimental backward: this many of the 4 neighbours of a warp step (k = 32) reduce through the TMA
+# unit (csrc/sspmm_bwd.cu, mk_sspmm_bwd_tma; measured slower); 0 = the shipped kernel
 _BWD_TMA = int(os.environ.get("MAXK_BWD_TMA", "0"))
 _launches = 0  # kernels launched through this module (bench.py reports it)
 
@@ -419,7 +419,7 @@ def spgemm_backward(ptr, idx, val, grad_output, sp_index, num_nodes, num_edges, 
         _chk(out.dtype == torch.float32 and tuple(out.shape) == (n_src, dim_sparse),
              "out must be float32 [sp_index.size(0), dim_sparse]")
         dxs = out
-    tma = _BWD_TMA if (ib == 1 and dim_sparse in (32, 64) and 1 <= _BWD_TMA <= 128 // dim_sparse) else 0
+    tma = _BWD_TMA if (ib == 1 and dim_sparse == 32 and _BWD_TMA in (1, 2, 4)) else 0
     with torch.cuda.device(grad_output.device):
         if tma:
             rc = _lib.lib().mk_sspmm_bwd_tma(

@@ -202,6 +202,29 @@ def test_spgemm_forward_and_sspmm_backward(mk, n, avg_deg, d, k, max_nz, kind):
         mk.set_max_nz(1024)
 
 
+@pytest.mark.parametrize("nt", [1, 2, 4])
+def test_backward_bulk_reduction_variant_and_out_buffer(mk, nt):
+    """The experimental backward (part of the reductions as bulk shared->global reductions) and the
+    `out=` form of spgemm_backward compute what the shipped kernel computes."""
+    from oracle import c_oracle
+    n, d, k = 3000, 256, 32
+    ptr, idx, val, x, dy = _problem(n, 60, d, k, seed=nt, kind="mean")
+    wd, wi = c_oracle.maxk_cbsr(x, k)
+    tptr, tidx, tval, sp_index = dev(ptr), dev(idx), dev(val), dev(wi)
+    want_b = c_oracle.sspmm_bwd(ptr, idx, val, dy, wi)
+    bound_b = c_oracle.sspmm_bwd(ptr, idx, np.abs(val), np.abs(dy), wi)
+    buf = torch.full((n, k), float("nan"), device="cuda")
+    mk.set_backward_tma(nt)
+    try:
+        dxs = mk.spgemm_backward(tptr, tidx, tval, dev(dy), sp_index, n, idx.size, k, d, out=buf)
+    finally:
+        mk.set_backward_tma(0)
+    assert dxs is buf
+    assert_rel(dxs, want_b, bound_b, f"spgemm_backward tma={nt}")
+    with pytest.raises(RuntimeError, match="out must be float32"):
+        mk.spgemm_backward(tptr, tidx, tval, dev(dy), sp_index, n, idx.size, k, d, out=buf[:, :8].contiguous())
+
+
 def test_degree_edge_cases_and_empty_rows(mk):
     """degrees 0 / 1 / 64 / 65 / > 10^4 in one graph (SURVEY.md section 4 implication)."""
     from oracle import c_oracle
