@@ -11,13 +11,18 @@ Parity status:
     and `MaxKSAGEConv._extract_sparse_format`), run in the build container with a stub
     `dgl` module by `tests/golden/make_golden.py`; the vectors are committed under
     `tests/golden/`.
-  * The aggregation arithmetic lives in DGL (`graph.update_all(copy_u, mean|sum)`; conda
-    `dglteam/label/cu121`, version unpinned, README.md:47), which is absent from
-    /root/reference and from this image, and the reference's CUDA kernels ship as an
-    sm_80-only binary without sources.  For SpGEMM / SSpMM / partitioning the parity is
-    therefore UNPINNED by the reference: the formulas below restate the SASS decode in
-    SURVEY.md section 2.3 (K3, K4) and are cross-checked against dense linear algebra
-    (`A @ dense(Xs)`, `(A^T @ dY)` sampled) and scipy.
+  * SpGEMM forward, the per-edge weights and the SSpMM backward are ANCHORED ON THE REFERENCE'S OWN
+    CALL SITES: `tests/golden/make_golden_layers.py` runs the reference's `MaxKSAGEConv` /
+    `MaxKGCNConv` code (utils/maxk_layers.py:47-447) through its DGL branch and through its
+    `maxk_kernels.spgemm_forward` call site (with this oracle as the kernel stand-in and a
+    message-passing stand-in for DGL's `update_all`), checks that the two agree, and commits the
+    recorded call arguments, the layer outputs and the layer backward under `tests/golden/`.
+  * What nothing in /root/reference can pin: DGL's own float32 arithmetic (`update_all` is library
+    code; conda `dglteam/label/cu121`, version unpinned, README.md:47; absent from the image) and
+    the native kernels' arithmetic (sm_80-only binary without sources).  There the formulas below
+    restate the SASS decode in SURVEY.md section 2.3 (K3, K4) and are cross-checked against dense
+    linear algebra (`A @ dense(Xs)`, `(A^T @ dY)` sampled) and scipy.  Partitioning (a-5) is
+    oracle-anchored only: PARITY UNPINNED for it.
 
 All sums are carried in float64.
 """

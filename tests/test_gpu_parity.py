@@ -271,6 +271,41 @@ def test_identity_adjacency_and_reference_padding(mk, golden):
     assert np.array_equal(out.cpu().numpy().astype(np.float64), want)
 
 
+def test_reference_layer_call_sites_through_the_cuda_path(mk, golden_layers):
+    """The arguments the reference's own MaxKSAGEConv / MaxKGCNConv code passes to
+    `maxk_kernels.spgemm_forward` (recorded by tests/golden/make_golden_layers.py), through the CUDA
+    entry point of the same name: + the layer's epilogue == what the layer computes through
+    `graph.update_all` in the reference."""
+    from conftest import layer_cases
+    from oracle import c_oracle
+    from spgemm_gnn_b200.graph import CSRGraph
+    from spgemm_gnn_b200.maxk_layers import aggregate_cbsr
+    for name, c, y, add in layer_cases(golden_layers):
+        args = (dev(c["ptr"]), dev(c["idx"]), dev(c["val"]), dev(c["sp_data"]), dev(c["sp_index"]))
+        out, _ = mk.spgemm_forward(*args, c["n"], c["e"], c["k"], c["d"])
+        bound = c_oracle.spgemm_fwd(c["ptr"], c["idx"], np.abs(c["val"]), np.abs(c["sp_data"]),
+                                    c["sp_index"], c["d"]) + np.abs(add)
+        # the golden output is float32 from float64 sums: half an ulp of y on top of the kernel bar
+        assert_rel(out + dev(np.broadcast_to(add, y.shape).astype(np.float32)), y.astype(np.float64),
+                   bound + 0.01 * np.abs(y), name)
+        if name.startswith("sage"):   # the layer's own graph code builds the same weights (a-7)
+            g = CSRGraph(args[0], args[1])
+            kind = "sum" if name == "sage_sum" else "mean"
+            agg = aggregate_cbsr(g, args[3], args[4], kind, c["d"])
+            assert torch.equal(agg, out) or torch.allclose(agg, out, rtol=1e-6, atol=0)
+            # backward of the reference layer (autograd through update_all, then grad * mask):
+            # spgemm_backward + CBSR scatter == the gradient at the input of the MaxK
+            dy, want = golden_layers[f"{name}_dy"], golden_layers[f"{name}_grad_maxk_in"]
+            dxs = mk.spgemm_backward(args[0], args[1], args[2], dev(dy), args[4], c["n"], c["e"],
+                                     c["k"], c["d"])
+            bound_b = c_oracle.sspmm_bwd(c["ptr"], c["idx"], np.abs(c["val"]), np.abs(dy), c["sp_index"])
+            want_k = np.take_along_axis(want, c["sp_index"].astype(np.int64), axis=1)
+            assert_rel(dxs, want_k.astype(np.float64), bound_b + 0.01 * np.abs(want_k), name + " backward")
+            dense = mk.cbsr_scatter(dxs, args[4], c["d"])
+            assert int((dense != 0).sum()) <= c["n"] * c["k"]
+            assert torch.equal(mk.cbsr_gather(dense, args[4]), dxs)
+
+
 def test_rectangular_shard_with_global_columns(mk):
     """Row shard of a bigger graph: n_rows < n_src (the 1-D partition of SURVEY.md section 8e)."""
     from oracle import c_oracle, maxk_oracle as mo

@@ -105,3 +105,17 @@ def test_synthetic_task_shapes_on_cpu():
     n = g.num_nodes()
     assert feats.shape == (n, 500) and (fin, ncls) == (500, 7) and labels.max() < 7
     assert int(tr.sum() + va.sum() + te.sum()) == n and 0.55 < tr.float().mean() < 0.77
+
+
+def test_edge_weights_match_the_reference_layer_loop(golden_layers):
+    """CSRGraph.edge_weights against the per-node `.item()` loop of the reference
+    (utils/maxk_layers.py:148-157), as recorded by tests/golden/make_golden_layers.py."""
+    from conftest import layer_cases
+    from spgemm_gnn_b200.graph import CSRGraph
+    for name, c, _, _ in layer_cases(golden_layers):
+        if not name.startswith("sage"):
+            continue
+        g = CSRGraph(torch.from_numpy(c["ptr"]), torch.from_numpy(c["idx"]))
+        kind = "sum" if name == "sage_sum" else "mean"
+        got = g.edge_weights(kind).numpy()
+        np.testing.assert_allclose(got, c["val"], rtol=1e-7)

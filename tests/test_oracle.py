@@ -38,6 +38,48 @@ def test_cbsr_layout_matches_reference_extract(golden):
     assert seen >= 4
 
 
+def test_spgemm_as_the_reference_layers_call_it(golden_layers):
+    """The reference's own call sites (utils/maxk_layers.py:166-171, 380-385) with the arguments its
+    own code builds: the oracle's SpGEMM + the layer's epilogue reproduces what the same layer
+    computes through `graph.update_all(copy_u, mean|sum)` (utils/maxk_layers.py:208-222, 392-405)."""
+    from conftest import layer_cases
+    seen = 0
+    for name, c, y, add in layer_cases(golden_layers):
+        seen += 1
+        assert c["ptr"].dtype == np.int32 and c["sp_index"].dtype == np.uint8
+        assert c["ptr"].size == c["n"] + 1 and c["idx"].size == c["e"] == c["val"].size
+        assert c["sp_data"].shape == (c["n"], c["k"]) and y.shape == (c["n"], c["d"])
+        for impl in (mo.spgemm_fwd, c_oracle.spgemm_fwd):
+            out = impl(c["ptr"], c["idx"], c["val"], c["sp_data"], c["sp_index"], c["d"]) + add
+            np.testing.assert_allclose(out, y, rtol=0, atol=2e-6 * np.abs(y).max())
+        # the CBSR rows the reference extracts are what the MaxK contract says: ascending, distinct
+        assert (np.diff(c["sp_index"].astype(np.int64), axis=1) > 0).all()
+        # and its per-edge weights are the ones this repo's graph code produces (section 8 a-7)
+        kind = {"sage_mean": "mean", "sage_sum": "sum", "sage_mean_wide": "mean"}.get(name)
+        if kind:
+            np.testing.assert_allclose(mo.edge_weights(c["ptr"], c["idx"], kind), c["val"], rtol=1e-7)
+    assert seen == 4
+
+
+def test_sspmm_against_the_backward_of_the_reference_layer(golden_layers):
+    """Backward of the reference's DGL branch (autograd through `update_all`, then
+    `MaxKFunction.backward` = grad * mask, utils/maxk_layers.py:37-45): the gradient at the input
+    of the MaxK is the oracle's SSpMM scattered to the kept columns, and zero elsewhere."""
+    from conftest import layer_cases
+    seen = 0
+    for name, c, _, _ in layer_cases(golden_layers):
+        if f"{name}_dy" not in golden_layers.files:
+            continue
+        seen += 1
+        dy, want = golden_layers[f"{name}_dy"], golden_layers[f"{name}_grad_maxk_in"]
+        for impl in (mo.sspmm_bwd, c_oracle.sspmm_bwd):
+            dxs = impl(c["ptr"], c["idx"], c["val"], dy, c["sp_index"])
+            dense = mo.cbsr_scatter(dxs, c["sp_index"], c["d"])
+            np.testing.assert_allclose(dense, want, rtol=0, atol=2e-6 * np.abs(want).max())
+        assert np.count_nonzero(want) <= c["n"] * c["k"]
+    assert seen == 3
+
+
 def test_padding_convention_is_harmless(golden):
     """Rows with fewer than k non-zeros are padded with (0.0, idx 0) by the reference; the
     accumulating dense view ignores them."""
