@@ -6,9 +6,11 @@
  * cpu_baseline leg of bench.py may load this library.
  *
  * Parity status: MaxK / CBSR layout pinned by tests/golden (vectors produced by the
- * reference's own Python); SpGEMM / SSpMM / partitioning UNPINNED by the reference (its
- * kernel sources are absent and DGL, which holds the real aggregation arithmetic, is not
- * vendored) -- see the header of maxk_oracle.py and DESIGN.md.
+ * reference's own Python); SpGEMM forward / SSpMM backward anchored on the reference's own
+ * layer code and call sites (tests/golden/make_golden_layers.py, layers_reference.npz);
+ * DGL's and the native kernels' own arithmetic cannot be pinned (neither is in
+ * /root/reference in runnable form) and partitioning is PARITY UNPINNED -- see the header
+ * of maxk_oracle.py and DESIGN.md section 3.
  *
  * Reference anchors (paths relative to /root/reference, SASS offsets as quoted in
  * SURVEY.md section 2.3):
