@@ -97,7 +97,11 @@ class PeerWindow:
         w = cls(nbytes, world, rank, device)
         p = ctypes.c_void_p(0)
         with torch.cuda.device(w.device):
-            _lib.check(_lib.lib().mk_peer_alloc(w.nbytes, ctypes.byref(p)), "mk_peer_alloc")
+            rc = _lib.lib().mk_peer_alloc(w.nbytes, ctypes.byref(p))
+            if rc == _lib.MK_ECUDA:  # cudaMalloc next to torch's caching allocator: give its cache back once
+                torch.cuda.empty_cache()
+                rc = _lib.lib().mk_peer_alloc(w.nbytes, ctypes.byref(p))
+            _lib.check(rc, "mk_peer_alloc")
         w.local = int(p.value)
         w.ptrs[rank] = w.local
         return w
