@@ -2,7 +2,7 @@
 """Checks of the peer-memory exchange kernels (csrc/peer.cu, bank.cu PUSH form, peer.py).
 
     python tools/peer_check.py virtual [WORLD]     one GPU: WORLD virtual ranks, one stream each
-    torchrun --nproc-per-node N tools/peer_check.py dist [--bench] [--products]    N GPUs, NCCL group
+    torchrun --nproc-per-node N tools/peer_check.py dist [--bench] [--products] [--stress]    N GPUs
 
 `virtual` exercises the kernels and their flag protocol inside one process (every "peer" window
 is a local buffer), `dist` runs the sharded forward/backward of dist.py with the peer path and
@@ -154,6 +154,10 @@ def distributed(bench: bool) -> int:
         o0, f0, b0 = res[False]
         o1, f1, b1 = res[True]
         fwd_equal = torch.equal(o0, o1) and torch.equal(f0, f1)
+        if "--stress" in sys.argv:   # back-to-back collectives through the same windows: the forward
+            for _ in range(200):    # is deterministic, so every repetition must reproduce it bit for bit
+                o, f, _b = step()
+                fwd_equal &= torch.equal(o, o1) and torch.equal(f, f1)
         scale = b0.abs().max().clamp_min(1e-20)
         bwd_err = float(((b0 - b1).abs().max() / scale).item())
         good = torch.tensor([1 if (fwd_equal and bwd_err < 1e-5) else 0], device=dev)
