@@ -18,6 +18,8 @@ comparator of the reference's speed-up figures), not the hot path.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -30,6 +32,49 @@ from .maxk_layers import (CBSRToDenseFunction, MaxKCBSRFunction, MaxKFunction, M
 
 def _aggregate_cbsr(g, sp_data, sp_index, kind, dim):
     return aggregate_cbsr(g, sp_data, sp_index, kind, dim)
+
+
+# The first and last Linear of every model have extents that are not multiples of 4 on the real
+# datasets (Reddit: 602 inputs, 41 classes), which sends cuBLAS to its unaligned kernels
+# (`..._align1`: 0.66 ms for the 602 -> 256 GEMM on the Reddit shape against ~0.08 ms for a
+# 256 -> 256 one, gpurun_out/epoch_profile.txt).  With MAXK_ALIGN_GEMM=1 the node features are
+# padded ONCE with zero columns (`pad_features`) and the two weights are padded on the fly inside
+# the call -- same parameters, same state dict, same result up to summation order.  Off by default
+# until measured.
+_ALIGN_GEMM = os.environ.get("MAXK_ALIGN_GEMM", "0") != "0"
+_ALIGN = 8
+
+
+def set_align_gemm(on: bool) -> None:
+    global _ALIGN_GEMM
+    _ALIGN_GEMM = bool(on)
+
+
+def align_gemm() -> bool:
+    return _ALIGN_GEMM
+
+
+def pad_features(x: torch.Tensor, multiple: int = _ALIGN) -> torch.Tensor:
+    """Node features with zero columns appended up to a multiple of `multiple` (done once per
+    dataset); the models accept them in the place of the unpadded matrix."""
+    pad = (-x.shape[1]) % multiple
+    return x if pad == 0 else F.pad(x, (0, pad))
+
+
+def aligned_linear(lin: nn.Linear, x: torch.Tensor) -> torch.Tensor:
+    """`lin(x)`.  `x` may carry zero columns beyond `lin.in_features` (pad_features); with
+    MAXK_ALIGN_GEMM the output extent is padded to a multiple of 8 inside the GEMM as well and the
+    result sliced back."""
+    extra_in = x.shape[1] - lin.in_features
+    if extra_in < 0:
+        raise RuntimeError(f"input has {x.shape[1]} columns, the layer expects {lin.in_features}")
+    extra_out = (-lin.out_features) % _ALIGN if _ALIGN_GEMM else 0
+    if extra_in == 0 and extra_out == 0:
+        return lin(x)
+    w = F.pad(lin.weight, (0, extra_in, 0, extra_out))
+    b = None if lin.bias is None else F.pad(lin.bias, (0, extra_out))
+    y = F.linear(x, w, b)
+    return y if extra_out == 0 else y[:, :lin.out_features]
 
 
 # ---------------------------------------------------------------------------------------
@@ -82,7 +127,7 @@ class SAGE(nn.Module):
         self.nonlinear = nonlinear
 
     def forward(self, g, x):
-        x = self.lin_in(x)
+        x = aligned_linear(self.lin_in, x)
         for i in range(self.num_layers):
             if self.nonlinear == "maxk":
                 cbsr = MaxKCBSRFunction.apply(x, self.k)
@@ -91,7 +136,7 @@ class SAGE(nn.Module):
                 if self.nonlinear == "relu":
                     x = F.relu(x)
                 x = self.layers[i](g, x)
-        return self.lin_out(x)
+        return aligned_linear(self.lin_out, x)
 
 
 class _GraphConvBoth(nn.Module):
@@ -163,7 +208,7 @@ class _LinMaxKConvStack(nn.Module):
         self.nonlinear = nonlinear
 
     def forward(self, g, x):
-        x = self.lin_in(x).relu()
+        x = aligned_linear(self.lin_in, x).relu()
         for i in range(self.num_layers):
             x = self.linlayers[i](x)
             cbsr = None
@@ -181,7 +226,7 @@ class _LinMaxKConvStack(nn.Module):
                 x = drop(x)
             a, b, bias = self.gcnlayers[i].pieces(g, x, cbsr)
             x = add_layer_norm(a, b, bias, self.normlayers[i] if self.norm else None)
-        return self.lin_out(x)
+        return aligned_linear(self.lin_out, x)
 
 
 class GCN(_LinMaxKConvStack):
@@ -226,12 +271,12 @@ class MaxKSAGE(nn.Module):
         init.xavier_uniform_(self.lin_out.weight)
 
     def forward(self, g, x):
-        x = self.lin_in(x)
+        x = aligned_linear(self.lin_in, x)
         for layer in self.layers:
             if self.nonlinear == "relu":
                 x = F.relu(x)
             x = layer(g, x)
-        return self.lin_out(x)
+        return aligned_linear(self.lin_out, x)
 
 
 class _IntegratedStack(nn.Module):
@@ -261,7 +306,7 @@ class _IntegratedStack(nn.Module):
             init.xavier_uniform_(linear.weight)
 
     def forward(self, g, x):
-        x = self.lin_in(x).relu()
+        x = aligned_linear(self.lin_in, x).relu()
         convs = getattr(self, self.conv_attr)
         for i in range(self.num_layers):
             x = self.linlayers[i](x)
@@ -271,7 +316,7 @@ class _IntegratedStack(nn.Module):
             x = convs[i](g, x)
             if self.norm:
                 x = self.normlayers[i](x)
-        return self.lin_out(x)
+        return aligned_linear(self.lin_out, x)
 
 
 class MaxKGCN(_IntegratedStack):

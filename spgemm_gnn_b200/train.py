@@ -47,6 +47,9 @@ def train_epochs(model: nn.Module, g: CSRGraph, feats, labels, train_mask, epoch
     opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=lr,
                            weight_decay=weight_decay)
     losses, times = [], []
+    from .models import align_gemm, pad_features
+    if align_gemm():
+        feats = pad_features(feats)      # zero columns up to a multiple of 8, once (MAXK_ALIGN_GEMM)
     cuda = feats.is_cuda
     sharded = getattr(g, "world", 1) > 1
     if sharded:
@@ -100,6 +103,9 @@ def train_epochs_graphed(model: nn.Module, g: CSRGraph, feats, labels, train_mas
     target = labels[idx]
     losses, times = [], []
     model.train()
+    from .models import align_gemm, pad_features
+    if align_gemm():
+        feats = pad_features(feats)      # zero columns up to a multiple of 8, once (MAXK_ALIGN_GEMM)
     static_loss = torch.zeros((), device=feats.device)
     sharded = getattr(g, "world", 1) > 1
     if sharded:

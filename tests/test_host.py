@@ -1,6 +1,5 @@
 """Host-side logic: CSR container, synthetic shapes, edge weights, row partition (no GPU)."""
 import numpy as np
-import numpy as np
 import pytest
 import torch
 
@@ -119,3 +118,34 @@ def test_edge_weights_match_the_reference_layer_loop(golden_layers):
         kind = "sum" if name == "sage_sum" else "mean"
         got = g.edge_weights(kind).numpy()
         np.testing.assert_allclose(got, c["val"], rtol=1e-7)
+
+
+def test_aligned_linear_is_the_same_layer():
+    """MAXK_ALIGN_GEMM: zero-padded features and on-the-fly padded weights give the output and the
+    gradients of the plain nn.Linear (Reddit's 602 inputs / 41 classes are not multiples of 4)."""
+    import torch.nn as nn
+    from spgemm_gnn_b200 import models
+    torch.manual_seed(0)
+    lin = nn.Linear(602, 41).double()
+    x = torch.randn(50, 602, dtype=torch.float64)
+    gy = torch.randn(50, 41, dtype=torch.float64)
+    y0 = lin(x)
+    y0.backward(gy)
+    g0 = (lin.weight.grad.clone(), lin.bias.grad.clone())
+    lin.zero_grad()
+    xp = models.pad_features(x)
+    assert xp.shape == (50, 608) and not xp[:, 602:].any() and models.pad_features(xp) is xp
+    assert not models.align_gemm()
+    assert torch.equal(models.aligned_linear(lin, x), y0)             # no padding asked for, none needed
+    models.set_align_gemm(True)
+    try:
+        y1 = models.aligned_linear(lin, xp)
+        assert y1.shape == (50, 41)
+        y1.backward(gy)
+    finally:
+        models.set_align_gemm(False)
+    torch.testing.assert_close(y1, y0, rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(lin.weight.grad, g0[0], rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(lin.bias.grad, g0[1], rtol=1e-12, atol=1e-12)
+    with pytest.raises(RuntimeError, match="expects 602"):
+        models.aligned_linear(lin, x[:, :600])
