@@ -17,7 +17,8 @@ autograd; torch.sparse.mm in the place of DGL, which is not in the image) on the
 bounded row sample of the same workload.
 
 N > 1 (torchrun): the same graph, 1-D row partition, CBSR all-gather forward and CBSR-gradient
-reduce-scatter backward over NCCL inside the timed step ("scaling": "strong").
+reduce-scatter backward inside the timed step ("scaling": "strong") -- the library's own NVLink
+kernels over peer windows by default, NCCL with MAXK_PEER_EXCHANGE=0.
 """
 from __future__ import annotations
 
@@ -129,7 +130,7 @@ def workload_config(args, world, n, e):
             "scale": args.scale,
             "parallelism": "1 GPU" if world == 1 else f"1-D row partition over {world} GPUs, "
                            "CBSR all-gather fwd + CBSR-grad reduce-scatter bwd "
-                           + ("(own NVLink kernels over peer windows, MAXK_PEER_EXCHANGE=1)"
+                           + ("(own NVLink kernels over CUDA-IPC peer windows)"
                               if _peer_on() else "(NCCL)"),
             "l2": "no explicit flush: every step streams inputs larger than L2 "
                   "(edge arrays 8 B/entry + dense rows); the CBSR table is re-used inside one "

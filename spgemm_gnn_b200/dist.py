@@ -14,6 +14,10 @@ module is the B200 answer BASELINE.json asks for.  One process per GPU, `torch.d
   * backward: the push-form SSpMM produces contributions to every node's CBSR gradient, folded
     by ONE reduce-scatter of N*k*4 bytes (the column ids are already resident from the forward);
   * weights are replicated, their gradients all-reduced in one flat bucket.
+
+The two exchanges have two forms: the `torch.distributed` calls in this file (gloo on CPU, NCCL
+with MAXK_PEER_EXCHANGE=0) and the library's own NVLink kernels over CUDA-IPC windows (peer.py,
+csrc/peer.cu, the PUSH form of csrc/bank.cu), which NCCL groups use by default.
 """
 from __future__ import annotations
 
@@ -146,8 +150,9 @@ def allreduce_grads(params: Iterable[torch.nn.Parameter], group=None) -> None:
 # the sharded hot path as an autograd Function
 # ---------------------------------------------------------------------------------------
 def _peer_path(group, *row_bytes) -> bool:
-    """Peer-memory kernels (peer.py) instead of NCCL: opted in, NCCL group on one box, and every
-    per-rank segment a multiple of 16 bytes (same answer on every rank: same shapes)."""
+    """Peer-memory kernels (peer.py) instead of NCCL calls: not switched off (MAXK_PEER_EXCHANGE=0),
+    NCCL group on one box, and every per-rank segment a multiple of 16 bytes (same answer on every
+    rank: same shapes)."""
     from . import peer
     return peer.enabled() and peer.available(group) and all(b % 16 == 0 for b in row_bytes)
 
@@ -159,9 +164,9 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
     banked first and the banked values + cell offsets are gathered next to the sorted column ids
     (7 bytes per entry instead of 5), so that no rank re-banks rows it does not own.
 
-    With `MAXK_PEER_EXCHANGE=1` the exchange runs as this library's own kernels over peer-mapped
-    windows: the banking kernel stores its rows into every rank's table (`peer.bank_push`), the
-    un-banked table goes through `peer.allgather`.  The table window is shared by all layers of a
+    On an NCCL group the exchange runs as this library's own kernels over peer-mapped windows
+    (default; `MAXK_PEER_EXCHANGE=0` keeps the NCCL calls below): the banking kernel stores its rows
+    into every rank's table (`peer.bank_push`), the un-banked table goes through `peer.allgather`.  The table window is shared by all layers of a
     shape, so the column ids are copied out of it when the backward will need them."""
     from . import maxk_kernels, peer
     r, k = sp_data.shape
@@ -197,8 +202,9 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
 
 
 def sharded_backward(grad_out, full_index, ptr, idx, val, num_rows, dim_origin, group=None):
-    """Local push-form SSpMM into a full-height buffer, folded by one reduce-scatter (NCCL, or
-    with `MAXK_PEER_EXCHANGE=1` by loads from every rank's buffer in fixed rank order)."""
+    """Local push-form SSpMM into a full-height buffer, folded by one reduce-scatter: loads from
+    every rank's peer window in fixed rank order (`peer.reduce_scatter`), or NCCL's
+    (`MAXK_PEER_EXCHANGE=0`, gloo, or windows that could not be mapped)."""
     from . import maxk_kernels, peer
     n_src, k = full_index.shape
     world = dist.get_world_size(group)
