@@ -13,6 +13,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
+def _free_port() -> str:
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return str(s.getsockname()[1])
+
+
 def _run(cmd, timeout=600):
     # virtual ranks share one device: every stream needs its own hardware queue to run concurrently
     env = dict(os.environ, MAXK_PEER_TIMEOUT_MS="20000", CUDA_DEVICE_MAX_CONNECTIONS="32")
@@ -35,12 +42,12 @@ def test_sharded_path_through_peer_windows_world1(built_lib):
     """dist.sharded_forward / sharded_backward with MAXK_PEER_EXCHANGE on an NCCL group of one rank:
     IPC export, window views, index copy-out, `out=` of spgemm_backward -- against the NCCL path."""
     out = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "1",
-                "--master-addr", "127.0.0.1", "--master-port", "29641", "tools/peer_check.py", "dist"])
+                "--master-addr", "127.0.0.1", "--master-port", _free_port(), "tools/peer_check.py", "dist"])
     assert "dist peer check: OK" in out
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_sharded_path_through_peer_windows_two_gpus(built_lib):
     out = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                "--master-addr", "127.0.0.1", "--master-port", "29642", "tools/peer_check.py", "dist"])
+                "--master-addr", "127.0.0.1", "--master-port", _free_port(), "tools/peer_check.py", "dist", "--stress"])
     assert "dist peer check: OK" in out
