@@ -117,6 +117,34 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+class gpu_local_cpus:
+    """Run a block on the CPUs NVML names as local to GPU `index` (restored afterwards): pinned host
+    buffers allocated inside land on the GPU's NUMA node, which is what a PCIe copy wants.  A no-op
+    where NVML or the affinity call is unavailable."""
+
+    def __init__(self, index):
+        self.index, self.saved = index, None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            saved = os.sched_getaffinity(0)
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(self.index))
+            self.saved = saved
+        except Exception:
+            self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except Exception:
+                pass
+        return False
+
+
 def _peer_on():
     from spgemm_gnn_b200 import peer
     return peer.enabled()
@@ -365,12 +393,13 @@ def main():
     # ---- end to end through the public entry points with HOST buffers
     e2e = None
     if not args.no_e2e:
-        hx = torch.empty((n_rows, d), dtype=torch.float32).pin_memory()
-        hdy = torch.empty((n_rows, d), dtype=torch.float32).pin_memory()
-        hx.copy_(x_local)
-        hdy.copy_(dy)
-        hout = torch.empty((n_rows, d), dtype=torch.float32).pin_memory()
-        hdxs = torch.empty((n_rows, k), dtype=torch.float32).pin_memory()
+        with gpu_local_cpus(local_rank):   # first touch on the GPU's NUMA node
+            hx = torch.empty((n_rows, d), dtype=torch.float32).pin_memory()
+            hdy = torch.empty((n_rows, d), dtype=torch.float32).pin_memory()
+            hx.copy_(x_local)
+            hdy.copy_(dy)
+            hout = torch.empty((n_rows, d), dtype=torch.float32).pin_memory().zero_()
+            hdxs = torch.empty((n_rows, k), dtype=torch.float32).pin_memory().zero_()
         dx_dev = torch.empty_like(x_local)
         dy_dev = torch.empty_like(dy)
 
