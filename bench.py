@@ -393,13 +393,16 @@ def main():
     # ---- end to end through the public entry points with HOST buffers
     e2e = None
     if not args.no_e2e:
-        with gpu_local_cpus(local_rank):   # first touch on the GPU's NUMA node
-            hx = torch.empty((n_rows, d), dtype=torch.float32).pin_memory()
-            hdy = torch.empty((n_rows, d), dtype=torch.float32).pin_memory()
-            hx.copy_(x_local)
-            hdy.copy_(dy)
-            hout = torch.empty((n_rows, d), dtype=torch.float32).pin_memory().zero_()
-            hdxs = torch.empty((n_rows, k), dtype=torch.float32).pin_memory().zero_()
+        # cudaHostAlloc pins (and therefore places) its pages at allocation time: allocate on the
+        # GPU-local CPUs, and do nothing else there -- a CPU thread pool born inside the block would
+        # keep the narrowed affinity and handicap the CPU baseline below
+        with gpu_local_cpus(local_rank):
+            hx = torch.empty((n_rows, d), dtype=torch.float32, pin_memory=True)
+            hdy = torch.empty((n_rows, d), dtype=torch.float32, pin_memory=True)
+            hout = torch.empty((n_rows, d), dtype=torch.float32, pin_memory=True)
+            hdxs = torch.empty((n_rows, k), dtype=torch.float32, pin_memory=True)
+        hx.copy_(x_local)
+        hdy.copy_(dy)
         dx_dev = torch.empty_like(x_local)
         dy_dev = torch.empty_like(dy)
 
