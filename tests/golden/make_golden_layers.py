@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Generates tests/golden/layers_reference.npz by running the REFERENCE'S OWN layer code
-(`utils/maxk_layers.py::MaxKSAGEConv`, `MaxKGCNConv`) in the build container, both ways:
+(`utils/maxk_layers.py::MaxKSAGEConv`, `MaxKGCNConv`; `utils/integrated_models.py::MaxKGINConv` at the
+end of main) in the build container, the first two both ways:
 
   (A) the branch that trains in the reference's logs: `_aggregate_with_dgl`
       (utils/maxk_layers.py:208-222, 392-405) -> `graph.update_all(fn.copy_u, fn.mean|sum)`;
@@ -234,6 +235,35 @@ def main():
         out[f"{name}_call_dims"] = np.array([call["num_nodes"], call["num_edges"], call["dim_sparse"],
                                              call["dim_origin"]], dtype=np.int64)
         print(f"{name}: N={n} E={g.e} {d_in}->{d_out} k={k}: branch (B) vs (A) max rel diff {err:.2e}")
+    # utils/integrated_models.py::MaxKGINConv (221-270): (1 + eps) * feat + sum_j MaxK(feat)[j] -> mlp.
+    # The module uses `fn.copy_u` / `fn.sum` without importing `dgl.function as fn` (NameError as
+    # shipped); the name is injected here, nothing else is touched.  No GEMM precedes the MaxK, so
+    # the layer is reproducible bit for bit up to the aggregation and can be pinned END TO END.
+    from utils import integrated_models as ref_int   # noqa: E402
+    ref_int.fn = sys.modules["dgl.function"]
+    n, deg, d_in, d_out, k = 160, 14, 128, 64, 32
+    src, dst = symmetric_graph(n, deg, rng)
+    g = FakeDGLGraph(src, dst, n)
+    feat = torch.randn(n, d_in)
+    conv = ref_int.MaxKGINConv(d_in, d_out, learn_eps=True, maxk=k)
+    with torch.no_grad():
+        conv.eps.fill_(0.25)
+        for layer in conv.mlp:
+            if isinstance(layer, nn.Linear):
+                nn.init.normal_(layer.bias, std=0.1)
+    pre = []
+    conv.mlp.register_forward_pre_hook(lambda _m, inp: pre.append(inp[0].detach().clone()))
+    with torch.no_grad():
+        y = conv(g, feat)
+    out["gin_ptr"] = g.in_csr.indptr.astype(np.int32)
+    out["gin_idx"] = g.in_csr.indices.astype(np.int32)
+    out["gin_feat"] = feat.numpy()
+    out["gin_dims"] = np.array([n, d_in, d_out, k], dtype=np.int64)
+    out["gin_pre_mlp"] = pre[0].numpy()
+    out["gin_y"] = y.numpy()
+    for key, val in conv.state_dict().items():
+        out["gin_sd_" + key] = val.numpy()
+    print(f"gin: N={n} E={g.e} {d_in}->{d_out} k={k}: state dict {sorted(conv.state_dict())}")
     out["names"] = np.array([c[0] for c in cases])
     path = os.path.join(HERE, "layers_reference.npz")
     np.savez_compressed(path, **out)

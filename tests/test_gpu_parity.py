@@ -306,6 +306,36 @@ def test_reference_layer_call_sites_through_the_cuda_path(mk, golden_layers):
             assert torch.equal(mk.cbsr_gather(dense, args[4]), dxs)
 
 
+def test_gin_layer_matches_the_reference_class_end_to_end(mk, golden_layers):
+    """This repo's MaxKGINConv with the reference's state dict against the output of the reference's
+    own class (utils/integrated_models.py:221-270, run by tests/golden/make_golden_layers.py): MaxK on
+    the raw features (bit-exact selection), sum over in-neighbours on the kernels, then the MLP."""
+    from spgemm_gnn_b200.graph import CSRGraph
+    from spgemm_gnn_b200.maxk_layers import MaxKGINConv
+    gl = golden_layers
+    n, d_in, d_out, k = (int(v) for v in gl["gin_dims"])
+    conv = MaxKGINConv(d_in, d_out, learn_eps=True, maxk=k)
+    conv.load_state_dict({key[len("gin_sd_"):]: torch.from_numpy(gl[key]) for key in gl.files
+                          if key.startswith("gin_sd_")})
+    conv = conv.cuda().eval()
+    g = CSRGraph(dev(gl["gin_ptr"]), dev(gl["gin_idx"]))
+    seen = []
+    hook = conv.mlp.register_forward_pre_hook(lambda _m, inp: seen.append(inp[0].detach()))
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False      # the MLP is compared in plain fp32
+    try:
+        with torch.no_grad():
+            y = conv(g, dev(gl["gin_feat"]))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        hook.remove()
+    want_pre, want_y = gl["gin_pre_mlp"], gl["gin_y"]
+    assert y.shape == (n, d_out) and len(seen) == 1
+    np.testing.assert_allclose(seen[0].cpu().numpy(), want_pre, rtol=0, atol=1e-5 * np.abs(want_pre).max())
+    # two fp32 GEMMs (K = 128, 64) on different hardware: summation order only
+    np.testing.assert_allclose(y.cpu().numpy(), want_y, rtol=0, atol=1e-4 * np.abs(want_y).max())
+
+
 def test_rectangular_shard_with_global_columns(mk):
     """Row shard of a bigger graph: n_rows < n_src (the 1-D partition of SURVEY.md section 8e)."""
     from oracle import c_oracle, maxk_oracle as mo

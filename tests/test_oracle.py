@@ -80,6 +80,21 @@ def test_sspmm_against_the_backward_of_the_reference_layer(golden_layers):
     assert seen == 3
 
 
+def test_gin_layer_of_the_reference_end_to_end(golden_layers):
+    """utils/integrated_models.py::MaxKGINConv: (1 + eps) * feat + sum over in-neighbours of MaxK(feat);
+    no GEMM precedes the MaxK, so the oracle reproduces the input of the MLP from the raw features."""
+    gl = golden_layers
+    n, d_in, _, k = (int(v) for v in gl["gin_dims"])
+    feat, ptr, idx = gl["gin_feat"], gl["gin_ptr"], gl["gin_idx"]
+    eps = float(gl["gin_sd_eps"][0])
+    assert eps == 0.25
+    for topk, fwd in ((mo.maxk_cbsr, mo.spgemm_fwd), (c_oracle.maxk_cbsr, c_oracle.spgemm_fwd)):
+        sp_data, sp_index = topk(feat, k)
+        neigh = fwd(ptr, idx, np.ones(idx.size, np.float32), sp_data, sp_index, d_in)
+        pre = (1 + eps) * feat.astype(np.float64) + neigh
+        np.testing.assert_allclose(pre, gl["gin_pre_mlp"], rtol=0, atol=2e-6 * np.abs(pre).max())
+
+
 def test_padding_convention_is_harmless(golden):
     """Rows with fewer than k non-zeros are padded with (0.0, idx 0) by the reference; the
     accumulating dense view ignores them."""
