@@ -33,7 +33,7 @@ extern "C" {
 #define MK_API __attribute__((visibility("default")))
 #endif
 
-#define MK_VERSION 100 /* major*100 + minor */
+#define MK_VERSION 101 /* major*100 + minor; 1.01 added the mk_peer_* exchange and mk_sspmm_bwd_tma */
 
 enum {
     MK_OK = 0,
@@ -193,7 +193,8 @@ MK_API int mk_layernorm_bwd(const float* gy, const float* z, const float* gamma,
  * base and must be >= MK_PEER_HEADER_BYTES and 16-byte aligned.  `h_windows[q]` is rank q's window
  * in the caller's address space (own window: the mk_peer_alloc pointer; others: mk_peer_open).
  * All ranks must issue the same collectives on a window in the same order.  Kernels that wait for
- * a peer longer than `timeout_ms` (<= 0: 30 s) set the header's error word and trap.              */
+ * a peer longer than `timeout_ms` (<= 0: 30 s) set the header's error word and trap.  `grid` is the
+ * number of thread blocks (0: the library's choice for the device).                               */
 #define MK_PEER_MAX_RANKS 16
 #define MK_PEER_HEADER_BYTES 1024
 #define MK_PEER_HANDLE_BYTES 64

@@ -39,7 +39,7 @@ def test_library_is_sm100a_and_has_no_torch_dependency(built_lib):
 
 def test_version_and_error_strings(built_lib):
     L = _lib.lib()
-    assert L.mk_version() == 100
+    assert L.mk_version() == 101
     assert L.mk_error_string(0) == b"ok"
     assert L.mk_error_string(-1) == b"invalid argument"
     assert b"CUDA" in L.mk_error_string(-3)
