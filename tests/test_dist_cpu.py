@@ -20,7 +20,7 @@ def _worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from oracle import c_oracle, maxk_oracle as mo
+        from oracle import c_oracle
         from spgemm_gnn_b200 import dist as mdist
         from spgemm_gnn_b200.graph import synthetic_graph
 

@@ -1,6 +1,6 @@
 import sys, os
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
-import numpy as np, torch, torch.nn.functional as F
+import torch, torch.nn.functional as F
 import test_gpu_models as T
 from oracle import ref_torch
 torch.backends.cuda.matmul.allow_tf32 = False
