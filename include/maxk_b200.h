@@ -213,11 +213,14 @@ MK_API int mk_peer_allgather(void* const* h_windows, int world, int rank, int n_
                              const int64_t* h_offsets, int grid, int timeout_ms, void* stream);
 /* mk_cbsr_bank fused with the all-gather: the banked values (fp32), cell offsets (uint16) and the
  * SORTED column ids of this rank's n rows are written into rows [rank*n, rank*n + n) of the three
- * [world*n, k] tables at off_data / off_slot / off_index of every rank's window.                */
+ * [world*n, k] tables at off_data / off_slot / off_index of every rank's window.  mode 1: every row
+ * is stored straight into all tables (measured, the default); mode 2: rows go to the own table,
+ * then each block copies its contiguous range to the peers with 16-byte stores (experimental;
+ * needs n*k*index_bytes % 16 == 0).                                                             */
 MK_API int mk_peer_bank_push(const float* sp_data, const void* sp_index, int index_bytes,
                              void* const* h_windows, int world, int rank, int64_t off_data,
                              int64_t off_slot, int64_t off_index, int64_t n, int k, int d,
-                             int timeout_ms, void* stream);
+                             int mode, int timeout_ms, void* stream);
 /* Reduce-scatter by loads: out[0 .. block_bytes/4) = sum over q (rank order, fixed) of the floats at
  * offset + rank * block_bytes of rank q's window.  When the call's kernel has finished, no peer
  * reads this rank's window any more (it may be overwritten).                                     */

@@ -48,7 +48,7 @@ SIGNATURES = {
     "mk_peer_allgather": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _i32, ctypes.POINTER(_vp),
                                  ctypes.POINTER(_i64), ctypes.POINTER(_i64), _i32, _i32, _vp]),
     "mk_peer_bank_push": (_i32, [_vp, _vp, _i32, ctypes.POINTER(_vp), _i32, _i32, _i64, _i64, _i64,
-                                 _i64, _i32, _i32, _i32, _vp]),
+                                 _i64, _i32, _i32, _i32, _i32, _vp]),
     "mk_peer_reduce_scatter": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _i64, _i64, _vp, _i32, _i32, _vp]),
 }
 

@@ -45,12 +45,16 @@ __device__ __forceinline__ int bank_slot_b(int c, int ra) {
 // byte per entry (position | copy << 7) in shared memory.  Phase 2 (one warp per row): move the
 // row with coalesced loads and stores.  bk_index may be null (the forward kernel does not need it).
 //
-// PUSH = true is the fused "bank -> all-gather" form of the row-partitioned forward (section 8e):
-// phase 2 stores every row -- banked values, cell offsets and the SORTED column ids the backward
-// needs -- straight into the table of EVERY rank (rows [row_base, row_base + n) of the windows in
-// `pa`), each row leaving as full 128 / 64 / 32-byte lines over NVLink, under the flag protocol of
-// peer.cuh.  The sequential phase 1 runs before the first remote store, so waiting for the peers'
-// ready flags costs nothing.  bk_data / bk_index / bk_slot are not used in that form.
+// PUSH != 0 is the fused "bank -> all-gather" form of the row-partitioned forward (section 8e):
+// every row -- banked values, cell offsets and the SORTED column ids the backward needs -- ends up
+// in the table of EVERY rank (rows [row_base, row_base + n) of the windows in `pa`), under the flag
+// protocol of peer.cuh.  The sequential phase 1 runs before the first remote store, so waiting for
+// the peers' ready flags costs nothing.  bk_data / bk_index / bk_slot are not used in that form.
+//   PUSH == 1  phase 2 stores each row straight into all P tables: 128 / 64 / 32-byte lines per
+//              row and destination over NVLink (measured, the default);
+//   PUSH == 2  phase 2 stores the rows into the OWN table only; the block then copies its 128 rows
+//              (one contiguous range per table) to the P-1 peers with 16-byte vector stores, 512
+//              bytes per warp instruction on the wire (experimental, MAXK_PEER_PUSH_MODE=2).
 struct BankPushArgs {
     PeerSet ps;
     int world, rank;
@@ -59,7 +63,16 @@ struct BankPushArgs {
     uint64_t timeout_ns;
 };
 
-template <int K, typename IdxT, bool PUSH>
+__device__ __forceinline__ uint4 ld_cg_16(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p)
+                 : "memory");
+    return r;
+}
+
+template <int K, typename IdxT, int PUSH>
 __global__ void __launch_bounds__(128)
 cbsr_bank_kernel(const float* __restrict__ sp_data, const IdxT* __restrict__ sp_index,
                  float* __restrict__ bk_data, IdxT* __restrict__ bk_index,
@@ -189,10 +202,16 @@ cbsr_bank_kernel(const float* __restrict__ sp_data, const IdxT* __restrict__ sp_
                     const int p = dsc & 0x7f;
                     const uint16_t cell =
                         static_cast<uint16_t>((dsc & 0x80) ? bank_slot_b(c, ra) : bank_slot_a(c));
-                    if (!PUSH) {
+                    if (PUSH == 0) {
                         bk_data[grow * K + p] = vv[q][j];
                         bk_slot[grow * K + p] = cell;
                         if (bk_index) bk_index[grow * K + p] = static_cast<IdxT>(c);
+                    } else if (PUSH == 2) {
+                        const int64_t trow = (pa.row_base + grow) * K;
+                        unsigned char* wq = pa.ps.win[pa.rank];
+                        reinterpret_cast<float*>(wq + pa.off_data)[trow + p] = vv[q][j];
+                        reinterpret_cast<uint16_t*>(wq + pa.off_slot)[trow + p] = cell;
+                        reinterpret_cast<IdxT*>(wq + pa.off_index)[trow + e] = static_cast<IdxT>(c);
                     } else {
                         const int64_t trow = (pa.row_base + grow) * K;
                         for (int s = 0; s < pa.world; ++s) {  // own copy first, then rank+1, ...
@@ -206,10 +225,30 @@ cbsr_bank_kernel(const float* __restrict__ sp_data, const IdxT* __restrict__ sp_
             }
         }
     }
+    if (PUSH == 2) {
+        // the block's rows now sit in the own table: one contiguous byte range per table (every
+        // range a multiple of 16 bytes, checked by the host), copied to the peers rank+1, rank+2, ...
+        __syncthreads();
+        const int64_t nrows = min(static_cast<int64_t>(128), n - row0);
+        const int64_t first = pa.row_base + row0;
+        const int64_t tab_off[3] = {pa.off_data, pa.off_slot, pa.off_index};
+        const int64_t row_bytes[3] = {K * 4, K * 2, K * static_cast<int64_t>(sizeof(IdxT))};
+        for (int s = 1; s < pa.world && nrows > 0; ++s) {
+            unsigned char* wq = pa.ps.win[(pa.rank + s) % pa.world];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int64_t b0 = tab_off[a] + first * row_bytes[a];
+                const int64_t n16 = nrows * row_bytes[a] / 16;
+                const uint4* src = reinterpret_cast<const uint4*>(pa.ps.win[pa.rank] + b0);
+                uint4* dst = reinterpret_cast<uint4*>(wq + b0);
+                for (int64_t i = threadIdx.x; i < n16; i += 128) st_peer_16(dst + i, ld_cg_16(src + i));
+            }
+        }
+    }
     if (PUSH) peer_end(pa.ps, pa.world, pa.rank, epoch, pa.timeout_ns);
 }
 
-template <typename IdxT, bool PUSH>
+template <typename IdxT, int PUSH>
 static int launch_bank(const float* sp_data, const void* sp_index, float* bk_data, void* bk_index,
                        uint16_t* bk_slot, int64_t n, int k, int d, const BankPushArgs& pa,
                        cudaStream_t st) {
@@ -249,14 +288,16 @@ extern "C" int mk_cbsr_bank(const float* sp_data, const void* sp_index, int inde
     cudaStream_t st = mk::as_stream(stream);
     const mk::BankPushArgs none{};
     return index_bytes == 1
-               ? mk::launch_bank<uint8_t, false>(sp_data, sp_index, bk_data, bk_index, bk_slot, n, k, d, none, st)
-               : mk::launch_bank<uint16_t, false>(sp_data, sp_index, bk_data, bk_index, bk_slot, n, k, d, none, st);
+               ? mk::launch_bank<uint8_t, 0>(sp_data, sp_index, bk_data, bk_index, bk_slot, n, k, d, none, st)
+               : mk::launch_bank<uint16_t, 0>(sp_data, sp_index, bk_data, bk_index, bk_slot, n, k, d, none, st);
 }
 
 extern "C" int mk_peer_bank_push(const float* sp_data, const void* sp_index, int index_bytes,
                                  void* const* h_windows, int world, int rank, int64_t off_data,
                                  int64_t off_slot, int64_t off_index, int64_t n, int k, int d,
-                                 int timeout_ms, void* stream) {
+                                 int mode, int timeout_ms, void* stream) {
+    if (mode != 1 && mode != 2) return MK_EINVAL;
+    if (mode == 2 && (n * k * index_bytes) % 16 != 0) return MK_EINVAL;
     if (n < 0 || d < 1 || k < 1 || k > d) return MK_EINVAL;
     if (index_bytes != 1 && index_bytes != 2) return MK_EINVAL;
     if ((index_bytes == 1 && d > 256)) return MK_EINVAL;
@@ -278,7 +319,11 @@ extern "C" int mk_peer_bank_push(const float* sp_data, const void* sp_index, int
     pa.row_base = static_cast<int64_t>(rank) * n;
     pa.timeout_ns = static_cast<uint64_t>(timeout_ms > 0 ? timeout_ms : 30000) * 1000000ull;
     cudaStream_t st = mk::as_stream(stream);
+    if (mode == 2)
+        return index_bytes == 1
+                   ? mk::launch_bank<uint8_t, 2>(sp_data, sp_index, nullptr, nullptr, nullptr, n, k, d, pa, st)
+                   : mk::launch_bank<uint16_t, 2>(sp_data, sp_index, nullptr, nullptr, nullptr, n, k, d, pa, st);
     return index_bytes == 1
-               ? mk::launch_bank<uint8_t, true>(sp_data, sp_index, nullptr, nullptr, nullptr, n, k, d, pa, st)
-               : mk::launch_bank<uint16_t, true>(sp_data, sp_index, nullptr, nullptr, nullptr, n, k, d, pa, st);
+               ? mk::launch_bank<uint8_t, 1>(sp_data, sp_index, nullptr, nullptr, nullptr, n, k, d, pa, st)
+               : mk::launch_bank<uint16_t, 1>(sp_data, sp_index, nullptr, nullptr, nullptr, n, k, d, pa, st);
 }

@@ -37,6 +37,9 @@ _ALIGN = 256
 
 _ENABLED = os.environ.get("MAXK_PEER_EXCHANGE", "1") != "0"   # "0": stay on NCCL collectives
 _TIMEOUT_MS = int(os.environ.get("MAXK_PEER_TIMEOUT_MS", "120000"))
+# how bank_push reaches the peers: 1 = every row stored straight into all tables (measured),
+# 2 = own table first, then each block copies its rows with 16-byte stores (experimental)
+_PUSH_MODE = int(os.environ.get("MAXK_PEER_PUSH_MODE", "1"))
 _launches = 0
 
 
@@ -272,7 +275,7 @@ def bank_push(win: PeerWindow, sp_data: torch.Tensor, sp_index: torch.Tensor, di
     with torch.cuda.device(win.device):
         rc = _lib.lib().mk_peer_bank_push(sp_data.data_ptr(), sp_index.data_ptr(), sp_index.element_size(),
                                           win.ptrs, win.world, win.rank, od, os_, oi, r, k, dim_origin,
-                                          _TIMEOUT_MS, _stream())
+                                          2 if _PUSH_MODE == 2 else 1, _TIMEOUT_MS, _stream())
     _lib.check(rc, "mk_peer_bank_push")
     _launches += 1
     rows = win.world * r

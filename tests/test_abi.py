@@ -79,9 +79,11 @@ def test_peer_argument_validation_without_a_device(built_lib):
     assert L.mk_peer_allgather(wins, 2, 0, 1, src, nb, off, 0, 0, None) == E        # not 16-byte units
     assert L.mk_peer_reduce_scatter(wins, 2, 0, 1000, 64, None, 0, 0, None) == E     # offset in header
     assert L.mk_peer_reduce_scatter(wins, 2, 0, 1024, 64, None, 0, 0, None) == E     # no output
-    assert L.mk_peer_bank_push(None, None, 1, wins, 2, 0, 1024, 2048, 4096, 4, 7, 256, 0, None) == _lib.MK_EUNSUPPORTED
-    assert L.mk_peer_bank_push(None, None, 1, wins, 2, 0, 1024, 2048, 4096, 4, 32, 256, 0, None) == E  # null rows
-    assert L.mk_peer_bank_push(None, None, 1, wins, 2, 0, 8, 2048, 4096, 0, 32, 256, 0, None) == E     # header
+    assert L.mk_peer_bank_push(None, None, 1, wins, 2, 0, 1024, 2048, 4096, 4, 7, 256, 1, 0, None) == _lib.MK_EUNSUPPORTED
+    assert L.mk_peer_bank_push(None, None, 1, wins, 2, 0, 1024, 2048, 4096, 4, 32, 256, 1, 0, None) == E  # null rows
+    assert L.mk_peer_bank_push(None, None, 1, wins, 2, 0, 8, 2048, 4096, 0, 32, 256, 1, 0, None) == E     # header
+    assert L.mk_peer_bank_push(None, None, 1, wins, 2, 0, 1024, 2048, 4096, 4, 32, 256, 3, 0, None) == E  # mode
+    assert L.mk_peer_bank_push(None, None, 1, wins, 2, 0, 1024, 2048, 4096, 3, 8, 256, 2, 0, None) == E   # 24-byte block
     p = VP(0)
     assert L.mk_peer_alloc(16, ctypes.byref(p)) == E                                # smaller than the header
     assert L.mk_peer_free(None) == _lib.MK_OK and L.mk_peer_close(None) == _lib.MK_OK

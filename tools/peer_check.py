@@ -3,6 +3,7 @@
 
     python tools/peer_check.py virtual [WORLD]     one GPU: WORLD virtual ranks, one stream each
     torchrun --nproc-per-node N tools/peer_check.py dist [--bench] [--products] [--stress]    N GPUs
+    (either form: --push-mode 2 selects the experimental vector-copy form of the fused bank + push)
 
 `virtual` exercises the kernels and their flag protocol inside one process (every "peer" window
 is a local buffer), `dist` runs the sharded forward/backward of dist.py with the peer path and
@@ -181,7 +182,10 @@ def distributed(bench: bool) -> int:
 
 
 if __name__ == "__main__":
+    if "--push-mode" in sys.argv:   # 2 = experimental "own table first, then block copies" bank_push
+        from spgemm_gnn_b200 import peer as _peer
+        _peer._PUSH_MODE = int(sys.argv[sys.argv.index("--push-mode") + 1])
     mode = sys.argv[1] if len(sys.argv) > 1 else "virtual"
     if mode == "virtual":
-        sys.exit(virtual(int(sys.argv[2]) if len(sys.argv) > 2 else 4))
+        sys.exit(virtual(int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 4))
     sys.exit(distributed("--bench" in sys.argv))

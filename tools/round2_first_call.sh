@@ -10,12 +10,15 @@ one)
     MAXK_ALIGN_GEMM=$a python -m spgemm_gnn_b200.train --dataset reddit --model sage --maxk 32 --epochs 12 --norm --cuda_graph \
       > $OUT/epoch_align$a.log 2>&1; tail -1 $OUT/epoch_align$a.log
   done
+  CUDA_DEVICE_MAX_CONNECTIONS=32 python tools/peer_check.py virtual 4 --push-mode 2 > $OUT/peer_virtual_mode2.log 2>&1; tail -1 $OUT/peer_virtual_mode2.log
   CUDA_DEVICE_MAX_CONNECTIONS=32 ncu --set full --clock-control none --import-source on -k regex:'peer_|cbsr_bank_kernel' \
     -o $OUT/peer_virtual python tools/peer_check.py virtual 4 > $OUT/ncu_peer_virtual.log 2>&1
   ;;
 eight)
   $TR --nproc-per-node 8 --master-port 29661 tools/peer_check.py dist --bench --products --stress > $OUT/peer_stress8.log 2>&1
   grep -v '^\*\|OMP_NUM' $OUT/peer_stress8.log | tail -8
+  $TR --nproc-per-node 8 --master-port 29662 tools/peer_check.py dist --bench --products --stress --push-mode 2 > $OUT/peer_stress8_mode2.log 2>&1
+  grep -v '^\*\|OMP_NUM' $OUT/peer_stress8_mode2.log | tail -8
   for p in 1 0; do for n in 2 4 8; do
     MAXK_PEER_EXCHANGE=$p $TR --nproc-per-node $n --master-port $((29670 + n)) bench.py --gpus $n --steps 30 --warmup 5 \
       > $OUT/bench_peer$p.$n.log 2>&1
