@@ -363,6 +363,33 @@ def main():
     dxs_probe = torch.randn(n_rows, k, device=device)
     scatter_ms = time_op(lambda: mk.cbsr_scatter(dxs_probe, sp_index, d))
 
+    # "cold" figures: one launch at a time with L2 overwritten in between, so
+    # the CBSR table / the gradient rows start in HBM.  1 GPU only (N > 1 has the exchange inside).
+    cold = {}
+    if world == 1:
+        try:
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+            def time_cold(fn, reps=7):
+                ts = []
+                for _ in range(reps):
+                    flush.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    fn()
+                    b.record()
+                    torch.cuda.synchronize()
+                    ts.append(a.elapsed_time(b))
+                return statistics.median(ts)
+
+            cold["spgemm_fwd_cold_ms"] = time_cold(
+                lambda: mk.spgemm_forward(ptr, idx, val, sp_data, sp_index, n_rows, e_local, k, d))
+            cold["sspmm_bwd_cold_ms"] = time_cold(
+                lambda: mk.spgemm_backward(ptr, idx, val, dy, sp_index, n_rows, e_local, k, d))
+            del flush
+        except Exception as exc:  # the headline numbers above do not depend on this
+            cold = {"cold_error": str(exc)[:200]}
+
     # ---- roofline of the dominant kernel
     peak, peak_src = measured_peak()
     bf, bb = algorithmic_bytes(n_rows, n_src, e_local, part.num_parts, k, d, w)
@@ -389,6 +416,7 @@ def main():
         "forward_variant": "banked (mk_cbsr_bank + mk_spgemm_fwd_banked, both inside spgemm_fwd_ms)"
         if mk.use_banked(part.num_parts, e_local, k, d) else "plain (mk_spgemm_fwd)",
     }
+    kernels.update(cold)
 
     # ---- end to end through the public entry points with HOST buffers
     e2e = None
