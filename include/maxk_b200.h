@@ -10,7 +10,7 @@
  * Each entry point names the reference interface it replaces.  Paths are relative to
  * julius-sk/spgemm-gnn; `so@0x...` / `.o@0x...` are addresses inside the only form the
  * reference ships its native code in (`maxk_kernels.cpython-39-x86_64-linux-gnu.so`,
- * `build/temp.linux-x86_64-cpython-39/kernels/*.o`) as decoded in SURVEY.md section 2.3.
+ * the objects under `build/temp.linux-x86_64-cpython-39/kernels/`) as decoded in SURVEY.md section 2.3.
  *
  * CBSR ("compressed balanced sparse row"): a matrix with exactly k kept entries per row,
  *   sp_data  float32 [n, k]  row-major, the kept values,

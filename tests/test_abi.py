@@ -29,6 +29,18 @@ def test_header_symbols_are_exported_and_bound(built_lib):
     assert exported == names                          # and nothing else leaks out
 
 
+def test_header_is_plain_c_and_links(built_lib, tmp_path):
+    """A C99 host (tests/c/abi_smoke.c) compiles against include/maxk_b200.h, links the library and
+    gets the documented return codes -- the boundary needs neither Python nor C++."""
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(built_lib)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe,
+                           "-L", libdir, "-lmaxk_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([exe]).decode()
+    assert "c abi ok: version 101" in out
+
+
 def test_library_is_sm100a_and_has_no_torch_dependency(built_lib):
     out = subprocess.check_output(["cuobjdump", "-lelf", built_lib]).decode()
     assert "sm_100a" in out and "sm_80" not in out
