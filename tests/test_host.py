@@ -149,3 +149,16 @@ def test_aligned_linear_is_the_same_layer():
     torch.testing.assert_close(lin.bias.grad, g0[1], rtol=1e-12, atol=1e-12)
     with pytest.raises(RuntimeError, match="expects 602"):
         models.aligned_linear(lin, x[:, :600])
+
+
+def test_tools_and_drivers_compile():
+    """Every script the GPU runs use (tools/, bench.py, __graft_entry__.py) at least byte-compiles."""
+    import glob
+    import os
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "tools", "*.py")) + [os.path.join(root, "bench.py"),
+                                                              os.path.join(root, "__graft_entry__.py")]
+    assert len(files) >= 8
+    for f in files:
+        py_compile.compile(f, doraise=True)
