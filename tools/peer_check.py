@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Checks of the peer-memory exchange kernels (csrc/peer.cu, bank.cu PUSH form, peer.py).
 
-    python tools/peer_check.py virtual [WORLD]     one GPU: WORLD virtual ranks, one stream each
+    python tools/peer_check.py virtual [WORLD] [--all-k]    one GPU: WORLD virtual ranks, one stream each
     torchrun --nproc-per-node N tools/peer_check.py dist [--bench] [--products] [--stress]    N GPUs
     (either form: --push-mode 2 selects the experimental vector-copy form of the fused bank + push)
 
@@ -53,25 +53,28 @@ def virtual(world: int) -> int:
             ok &= good
         print(f"allgather round {rnd}: {'OK' if ok else 'FAIL'}")
 
-    # ---- fused bank + push against cbsr_bank + concatenation
-    offs3, total3 = peer.layout([rows * k * 4, rows * k * 2, rows * k])
-    wins3 = peer.PeerWindow.create_virtual(total3, world, dev)
-    for rnd in range(2):
-        xs = [torch.randn(r, d, device=dev, generator=gen) for _ in range(world)]
-        cb = [mk.maxk_forward_cbsr(x, k) for x in xs]
-        ref = [mk.cbsr_bank(sd, si, d, with_index=False) for sd, si in cb]
-        torch.cuda.synchronize()
-        outs = []
-        for q in range(world):
-            with torch.cuda.stream(streams[q]):
-                outs.append(peer.bank_push(wins3[q], cb[q][0], cb[q][1], d, offs3))
-        torch.cuda.synchronize()
-        want = (torch.cat([a for a, _, _ in ref]), torch.cat([c for _, _, c in ref]),
-                torch.cat([si for _, si in cb]))
-        for q in range(world):
-            good = all(torch.equal(a, b) for a, b in zip(outs[q], want))
-            ok &= good
-        print(f"bank_push round {rnd}: {'OK' if ok else 'FAIL'}")
+    # ---- fused bank + push against cbsr_bank + concatenation (--all-k: every banked width)
+    wins3 = []
+    for kk in ((8, 16, 32, 64) if "--all-k" in sys.argv else (k,)):
+        offs3, total3 = peer.layout([rows * kk * 4, rows * kk * 2, rows * kk])
+        wk = peer.PeerWindow.create_virtual(total3, world, dev)
+        wins3 += wk
+        for rnd in range(2):
+            xs = [torch.randn(r, d, device=dev, generator=gen) for _ in range(world)]
+            cb = [mk.maxk_forward_cbsr(x, kk) for x in xs]
+            ref = [mk.cbsr_bank(sd, si, d, with_index=False) for sd, si in cb]
+            torch.cuda.synchronize()
+            outs = []
+            for q in range(world):
+                with torch.cuda.stream(streams[q]):
+                    outs.append(peer.bank_push(wk[q], cb[q][0], cb[q][1], d, offs3))
+            torch.cuda.synchronize()
+            want = (torch.cat([a for a, _, _ in ref]), torch.cat([c for _, _, c in ref]),
+                    torch.cat([si for _, si in cb]))
+            for q in range(world):
+                good = all(torch.equal(a, b) for a, b in zip(outs[q], want))
+                ok &= good
+            print(f"bank_push k={kk} round {rnd}: {'OK' if ok else 'FAIL'}")
 
     # ---- reduce-scatter by loads: fixed rank order, so bit-equal to the same fold in torch
     offs1, total1 = peer.layout([rows * k * 4])

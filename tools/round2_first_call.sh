@@ -10,7 +10,8 @@ one)
     MAXK_ALIGN_GEMM=$a python -m spgemm_gnn_b200.train --dataset reddit --model sage --maxk 32 --epochs 12 --norm --cuda_graph \
       > $OUT/epoch_align$a.log 2>&1; tail -1 $OUT/epoch_align$a.log
   done
-  CUDA_DEVICE_MAX_CONNECTIONS=32 python tools/peer_check.py virtual 4 --push-mode 2 > $OUT/peer_virtual_mode2.log 2>&1; tail -1 $OUT/peer_virtual_mode2.log
+  CUDA_DEVICE_MAX_CONNECTIONS=32 python tools/peer_check.py virtual 4 --all-k > $OUT/peer_virtual_allk.log 2>&1; tail -1 $OUT/peer_virtual_allk.log
+  CUDA_DEVICE_MAX_CONNECTIONS=32 python tools/peer_check.py virtual 4 --all-k --push-mode 2 > $OUT/peer_virtual_mode2.log 2>&1; tail -1 $OUT/peer_virtual_mode2.log
   CUDA_DEVICE_MAX_CONNECTIONS=32 ncu --set full --clock-control none --import-source on -k regex:'peer_|cbsr_bank_kernel' \
     -o $OUT/peer_virtual python tools/peer_check.py virtual 4 > $OUT/ncu_peer_virtual.log 2>&1
   ;;
