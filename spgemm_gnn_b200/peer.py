@@ -10,6 +10,10 @@ kernels over NVLink instead of NCCL calls:
   * `reduce_scatter`  every rank loads its block from every rank's partial buffer and folds it in
                       rank order (bit-reproducible).
 
+Rules of use: every rank issues the same collectives through a window in the same order, and a
+rank issues them from one stream at a time (stream order is what tells the peers that the rank is
+done with its copy; two streams racing through one window would break that).
+
 A `PeerWindow` is one device buffer per rank, mapped into every process of the group with CUDA IPC
 (`mk_peer_export` / `mk_peer_open`, handles exchanged with `all_gather_object`).  The kernels keep
 their flags and epoch counters in the window's header, so captured CUDA graphs replay correctly.
