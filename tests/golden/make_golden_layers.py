@@ -264,6 +264,26 @@ def main():
     for key, val in conv.state_dict().items():
         out["gin_sd_" + key] = val.numpy()
     print(f"gin: N={n} E={g.e} {d_in}->{d_out} k={k}: state dict {sorted(conv.state_dict())}")
+    # MaxKSAGEConv END TO END: with scaled permutation matrices as weights both Linear layers are
+    # exact on any hardware (one non-zero product per output), so the MaxK selects the same entries
+    # everywhere and the whole layer (utils/maxk_layers.py:82-99 + 208-222) can be compared as one.
+    n, deg, d, k = 140, 16, 64, 16
+    src, dst = symmetric_graph(n, deg, rng)
+    g = FakeDGLGraph(src, dst, n)
+    feat = torch.randn(n, d)
+    conv = ref.MaxKSAGEConv(d, d, aggregator_type="mean", maxk=k)
+    with torch.no_grad():
+        conv.fc_self.weight.copy_(0.5 * torch.eye(d)[torch.randperm(d)])
+        conv.fc_neigh.weight.copy_(2.0 * torch.eye(d)[torch.randperm(d)])
+        y = conv(g, feat)
+    out["sagex_ptr"] = g.in_csr.indptr.astype(np.int32)
+    out["sagex_idx"] = g.in_csr.indices.astype(np.int32)
+    out["sagex_feat"] = feat.numpy()
+    out["sagex_dims"] = np.array([n, d, k], dtype=np.int64)
+    out["sagex_y"] = y.numpy()
+    for key, val in conv.state_dict().items():
+        out["sagex_sd_" + key] = val.numpy()
+    print(f"sage end to end: N={n} E={g.e} d={d} k={k}: state dict {sorted(conv.state_dict())}")
     out["names"] = np.array([c[0] for c in cases])
     path = os.path.join(HERE, "layers_reference.npz")
     np.savez_compressed(path, **out)

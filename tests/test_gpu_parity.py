@@ -336,6 +336,31 @@ def test_gin_layer_matches_the_reference_class_end_to_end(mk, golden_layers):
     np.testing.assert_allclose(y.cpu().numpy(), want_y, rtol=0, atol=1e-4 * np.abs(want_y).max())
 
 
+def test_sage_layer_matches_the_reference_class_end_to_end(mk, golden_layers):
+    """This repo's MaxKSAGEConv with the reference's state dict against the output of the reference's
+    own class (utils/maxk_layers.py:47-222).  The weights are scaled permutation matrices, so both
+    Linear layers are exact on any hardware and the MaxK selects the same entries as on the CPU."""
+    from spgemm_gnn_b200.graph import CSRGraph
+    from spgemm_gnn_b200.maxk_layers import MaxKSAGEConv
+    gl = golden_layers
+    n, d, k = (int(v) for v in gl["sagex_dims"])
+    conv = MaxKSAGEConv(d, d, aggregator_type="mean", maxk=k)
+    conv.load_state_dict({key[len("sagex_sd_"):]: torch.from_numpy(gl[key]) for key in gl.files
+                          if key.startswith("sagex_sd_")})
+    conv = conv.cuda().eval()
+    g = CSRGraph(dev(gl["sagex_ptr"]), dev(gl["sagex_idx"]))
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False      # exactness of the two Linear layers needs fp32
+    try:
+        with torch.no_grad():
+            y = conv(g, dev(gl["sagex_feat"]))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    want = gl["sagex_y"]
+    assert y.shape == (n, d)
+    np.testing.assert_allclose(y.cpu().numpy(), want, rtol=0, atol=1e-5 * np.abs(want).max())
+
+
 def test_rectangular_shard_with_global_columns(mk):
     """Row shard of a bigger graph: n_rows < n_src (the 1-D partition of SURVEY.md section 8e)."""
     from oracle import c_oracle, maxk_oracle as mo

@@ -95,6 +95,22 @@ def test_gin_layer_of_the_reference_end_to_end(golden_layers):
         np.testing.assert_allclose(pre, gl["gin_pre_mlp"], rtol=0, atol=2e-6 * np.abs(pre).max())
 
 
+def test_sage_layer_of_the_reference_end_to_end(golden_layers):
+    """utils/maxk_layers.py::MaxKSAGEConv with scaled permutation matrices as weights (exact GEMMs):
+    fc_self(x) + mean over in-neighbours of MaxK(fc_neigh(x)), from the raw features."""
+    gl = golden_layers
+    n, d, k = (int(v) for v in gl["sagex_dims"])
+    feat, ptr, idx = gl["sagex_feat"], gl["sagex_ptr"], gl["sagex_idx"]
+    w_self, w_neigh = gl["sagex_sd_fc_self.weight"], gl["sagex_sd_fc_neigh.weight"]
+    assert (np.count_nonzero(w_self, axis=1) == 1).all() and (np.count_nonzero(w_neigh, axis=1) == 1).all()
+    h_self, h_neigh = feat @ w_self.T, feat @ w_neigh.T          # one product per output: exact
+    val = mo.edge_weights(ptr, idx, "mean")
+    for topk, fwd in ((mo.maxk_cbsr, mo.spgemm_fwd), (c_oracle.maxk_cbsr, c_oracle.spgemm_fwd)):
+        sp_data, sp_index = topk(h_neigh, k)
+        y = h_self.astype(np.float64) + fwd(ptr, idx, val, sp_data, sp_index, d)
+        np.testing.assert_allclose(y, gl["sagex_y"], rtol=0, atol=2e-6 * np.abs(y).max())
+
+
 def test_padding_convention_is_harmless(golden):
     """Rows with fewer than k non-zeros are padded with (0.0, idx 0) by the reference; the
     accumulating dense view ignores them."""
