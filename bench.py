@@ -19,6 +19,17 @@ bounded row sample of the same workload.
 N > 1 (torchrun): the same graph, 1-D row partition, CBSR all-gather forward and CBSR-gradient
 reduce-scatter backward inside the timed step ("scaling": "strong") -- the library's own NVLink
 kernels over peer windows by default, NCCL with MAXK_PEER_EXCHANGE=0.
+
+Next to the headline the line carries (none of it inside the timed region):
+  parity    (N > 1) every rank's sharded forward rows and reduced CBSR gradient against a
+            single-GPU computation of the same rows on the same rank and against the NCCL form of
+            the exchange -- so that a scaling number is never the timing of an unverified result;
+  ksweep    (N = 1) BASELINE.json config 2: k in {8,16,32,64} forward / backward ms next to the dense
+            cuSPARSE SpMM (torch.sparse.mm), the comparator of the reference's README.md:136;
+  products  BASELINE.json config 4 shape (2.45 M nodes): forward / backward ms per layer at this N,
+            where the CBSR table no longer fits L2 and the kernels are HBM-bound;
+  flickr    (N = 1) BASELINE.json config 0 / BASELINE.md section 4: 3-layer MaxK-SAGE forward+backward
+            on the Flickr shape, this GPU path next to the reference's CPU formulation.
 """
 from __future__ import annotations
 
@@ -58,14 +69,17 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel, workload):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+def ncu_traffic(kernel, workload, k=32):
+    """(dram bytes per launch, source) of a kernel from the committed `ncu --set full` capture of
+    this workload (profiles/ncu_traffic.json names the capture), or (None, None).  ncu cannot run
+    inside a timed program, so this is the one figure of the line that is not measured live."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             t = json.load(f)
-        return t.get(workload, {}).get(kernel)
+        rec = t.get(workload if k == 32 else f"{workload}_k{k}", {})
+        return rec.get(kernel), rec.get("_source")
     except Exception:
-        return None
+        return None, None
 
 
 class ClockSampler:
@@ -203,6 +217,271 @@ def cpu_sample_of(g, val, frac_rows):
 
 
 # ---------------------------------------------------------------------------------------
+# records next to the headline (outside the timed region)
+# ---------------------------------------------------------------------------------------
+def _max_over_ranks(x, device, world):
+    if world == 1:
+        return float(x)
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def time_layer(fwd, bwd, steps, warmup, device, world):
+    """(ms per fwd+bwd, fwd ms, bwd ms): CUDA events on the current stream, barrier + synchronize on
+    both sides, max over ranks."""
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+    for _ in range(warmup):
+        bwd(fwd())
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    barrier()
+    for a, b, c in ev:
+        a.record()
+        h = fwd()
+        b.record()
+        bwd(h)
+        c.record()
+    barrier()
+    total = ev[0][0].elapsed_time(ev[-1][2]) / steps
+    f = statistics.mean(a.elapsed_time(b) for a, b, _ in ev)
+    b_ = statistics.mean(b.elapsed_time(c) for _, b, c in ev)
+    return (_max_over_ranks(total, device, world), _max_over_ranks(f, device, world),
+            _max_over_ranks(b_, device, world))
+
+
+def parity_record(mk, mdist, g, rank, world, ptr, idx, val, val_full, x_local, dy, k, d, device):
+    """N > 1: the sharded layer (exchange included) against (1) a single-GPU computation of the same
+    rows on this rank -- dense inputs all-gathered with NCCL, top-k of the whole table, SpGEMM of the
+    local rows, SSpMM of the WHOLE graph sliced to the rank's rows -- and (2) the NCCL form of the
+    two exchanges.  Errors are max|a-b| / max|b|, worst rank."""
+    import torch.distributed as dist
+    from spgemm_gnn_b200 import peer as mpeer
+    n, e = g.num_nodes(), g.num_edges()
+    n_rows = x_local.shape[0]
+    e_local = idx.numel()
+    sd, si = mk.maxk_forward_cbsr(x_local, k)
+    out, fi = mdist.sharded_forward(sd, si, ptr, idx, val, n_rows, d)
+    dxs = mdist.sharded_backward(dy, fi, ptr, idx, val, n_rows, d)
+    out, dxs = out.clone(), dxs.clone()
+
+    x_full = torch.empty((world * n_rows, d), device=device)
+    dy_full = torch.empty((world * n_rows, d), device=device)
+    dist.all_gather_into_tensor(x_full, x_local)
+    dist.all_gather_into_tensor(dy_full, dy)
+    sd_f, si_f = mk.maxk_forward_cbsr(x_full, k)
+    out_1, _ = mk.spgemm_forward(ptr, idx, val, sd_f, si_f, n_rows, e_local, k, d)
+    dxs_1 = mk.spgemm_backward(g.indptr, g.indices, val_full, dy_full[:n].contiguous(), si_f, n, e, k, d)
+    dxs_1 = dxs_1[rank * n_rows:(rank + 1) * n_rows]
+
+    def rel(a, b):
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+    rec = {"fwd_max_rel": rel(out, out_1), "bwd_max_rel": rel(dxs, dxs_1),
+           "index_equal": bool(torch.equal(fi.view(torch.uint8), si_f.view(torch.uint8)))}
+    was = mpeer.enabled()
+    if was:  # same layer with the exchanges as NCCL calls
+        mpeer.set_enabled(False)
+        out_n, fi_n = mdist.sharded_forward(sd, si, ptr, idx, val, n_rows, d)
+        dxs_n = mdist.sharded_backward(dy, fi_n, ptr, idx, val, n_rows, d)
+        mpeer.set_enabled(True)
+        rec["fwd_bit_equal_nccl_form"] = bool(torch.equal(out, out_n))
+        rec["bwd_max_rel_nccl_form"] = rel(dxs, dxs_n)
+    for key in ("fwd_max_rel", "bwd_max_rel", "bwd_max_rel_nccl_form"):
+        if key in rec:
+            rec[key] = _max_over_ranks(rec[key], device, world)
+    flags = torch.tensor([int(rec["index_equal"]), int(rec.get("fwd_bit_equal_nccl_form", True))],
+                         device=device, dtype=torch.int32)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    rec["index_equal"] = bool(flags[0].item())
+    if "fwd_bit_equal_nccl_form" in rec:
+        rec["fwd_bit_equal_nccl_form"] = bool(flags[1].item())
+    rec["ok"] = bool(rec["fwd_max_rel"] <= 1e-6 and rec["bwd_max_rel"] <= 1e-5 and rec["index_equal"]
+                     and rec.get("fwd_bit_equal_nccl_form", True)
+                     and rec.get("bwd_max_rel_nccl_form", 0.0) <= 1e-5)
+    rec["against"] = ("rows of this rank recomputed on one GPU from NCCL-gathered dense inputs (forward: same "
+                      "kernel without the exchange; backward: whole-graph SSpMM, rank's slice)"
+                      + ("; and the NCCL form of both exchanges" if was else ""))
+    rec["exchange"] = "peer windows" if was else "NCCL"
+    return rec
+
+
+def ksweep_record(mk, g, val, x, dy, d, peak, reps=10):
+    """BASELINE.json config 2 on the resident graph: forward / backward ms at k in {8,16,32,64} and the
+    dense cuSPARSE SpMM (torch.sparse.mm forward, transposed backward) the reference reports its
+    speed-ups against (README.md:136; comparator spmm_cusparse in its binary)."""
+    n, e = g.num_nodes(), g.num_edges()
+    w = 1 if d <= 256 else 2
+
+    def t(fn, r):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(r):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / r
+
+    rec = {"graph": "same as config", "reps": reps, "rows": []}
+    for kk in (8, 16, 32, 64):
+        sd, si = mk.maxk_forward_cbsr(x, kk)
+        part = mk.partition(g.indptr, n)
+        f = t(lambda: mk.spgemm_forward(g.indptr, g.indices, val, sd, si, n, e, kk, d), reps)
+        b = t(lambda: mk.spgemm_backward(g.indptr, g.indices, val, dy, si, n, e, kk, d), reps)
+        tk = t(lambda: mk.maxk_forward_cbsr(x, kk), reps)
+        bf, bb = algorithmic_bytes(n, n, e, part.num_parts, kk, d, w)
+        rec["rows"].append({"k": kk, "fwd_ms": f, "bwd_ms": b, "topk_ms": tk,
+                            "fwd_frac_of_peak": bf / (f * 1e-3) / 1e9 / peak,
+                            "bwd_frac_of_peak": bb / (b * 1e-3) / 1e9 / peak,
+                            "fwd_alg_bytes": bf, "bwd_alg_bytes": bb,
+                            "forward_variant": mk.forward_variant(part.num_parts, e, kk, d)})
+        del sd, si
+    try:
+        adj = torch.sparse_csr_tensor(g.indptr.long(), g.indices.long(), val, size=(n, n))
+        cf = t(lambda: torch.sparse.mm(adj, x), 3)
+        adj_t = adj.t().to_sparse_csr()
+        cb = t(lambda: torch.sparse.mm(adj_t, dy), 3)
+        del adj, adj_t
+        rec["cusparse_dense_spmm"] = {"fwd_ms": cf, "bwd_ms": cb, "how": "torch.sparse.mm(CSR, dense [N,D]) fp32"}
+        for r in rec["rows"]:
+            r["speedup_vs_cusparse_fwd"] = cf / r["fwd_ms"]
+            r["speedup_vs_cusparse_bwd"] = cb / r["bwd_ms"]
+    except Exception as exc:
+        rec["cusparse_dense_spmm"] = {"error": str(exc)[:200]}
+    rec["reference_kernels"] = "not runnable on sm_100 (sm_80 SASS only, no PTX, sources absent); README.md:136 quotes 6.93/5.39/2.55/1.46x over cuSPARSE on an A100"
+    torch.cuda.empty_cache()
+    return rec
+
+
+def products_record(mk, mdist, rank, world, k, d, device, peak, steps=10):
+    """BASELINE.json config 4 shape (2,449,029 nodes, ~124 M stored entries, mean degree 51): the CBSR
+    table (392 MB) and gradient (313 MB) exceed L2, so this is where the kernels are HBM-bound.
+    N = 1: forward / backward ms, algorithmic and (committed ncu) DRAM fractions.  N > 1: the same
+    layer row-partitioned, exchanges included -- the north_star's 8-GPU target is the ratio of this
+    record's ms_per_layer at N = 1 and N = 8."""
+    from spgemm_gnn_b200.graph import shaped_graph
+    g = shaped_graph("ogbn-products", device=device)
+    n, e = g.num_nodes(), g.num_edges()
+    w = 1 if d <= 256 else 2
+    val_full = g.edge_weights("mean")
+    if world > 1:
+        local, r0, r1 = mdist.shard_graph(g, rank, world)
+        val = mdist.shard_edge_weights(g, local, r0, r1, "mean")
+    else:
+        local, val = g, val_full
+    n_rows, n_src, e_local = local.num_nodes(), local.num_src, local.num_edges()
+    ptr, idx = local.indptr, local.indices
+    gen = torch.Generator(device=device).manual_seed(197 + rank)
+    x = torch.randn(n_rows, d, device=device, generator=gen)
+    dy = torch.randn(n_rows, d, device=device, generator=gen)
+    sd, si = mk.maxk_forward_cbsr(x, k)
+    part = mk.partition(ptr, n_rows)
+    if world > 1:
+        def fwd():
+            return mdist.sharded_forward(sd, si, ptr, idx, val, n_rows, d)[1]
+
+        def bwd(fi):
+            return mdist.sharded_backward(dy, fi, ptr, idx, val, n_rows, d)
+    else:
+        def fwd():
+            mk.spgemm_forward(ptr, idx, val, sd, si, n_rows, e_local, k, d)
+            return si
+
+        def bwd(fi):
+            return mk.spgemm_backward(ptr, idx, val, dy, fi, n_rows, e_local, k, d)
+    ms, f, b = time_layer(fwd, bwd, steps, 3, device, world)
+    bf, bb = algorithmic_bytes(n_rows, n_src, e_local, part.num_parts, k, d, w)
+    rec = {"graph": f"ogbn-products-shaped synthetic graph, {n} nodes, {e} stored entries, k {k}, dim {d}",
+           "nodes": n, "edges": e, "n_gpus": world, "steps": steps, "ms_per_layer": ms, "fwd_ms": f, "bwd_ms": b,
+           "edges_per_s": 2.0 * e / (ms * 1e-3),
+           "forward_variant": mk.forward_variant(part.num_parts, e_local, k, d)}
+    if world == 1:
+        tf, src = ncu_traffic("spgemm_fwd", "ogbn-products", k)
+        tb, _ = ncu_traffic("sspmm_bwd", "ogbn-products", k)
+        rec.update({"bound": "hbm", "fwd_alg_bytes": bf, "bwd_alg_bytes": bb,
+                    "fwd_frac_of_peak": bf / (f * 1e-3) / 1e9 / peak,
+                    "bwd_frac_of_peak": bb / (b * 1e-3) / 1e9 / peak,
+                    "fwd_dram_bytes_ncu": tf, "bwd_dram_bytes_ncu": tb, "traffic_source": src,
+                    "fwd_dram_frac": (tf / (f * 1e-3) / 1e9 / peak) if tf else None,
+                    "bwd_dram_frac": (tb / (b * 1e-3) / 1e9 / peak) if tb else None})
+    del g, local, sd, si, x, dy
+    mk.clear_partition_cache()
+    torch.cuda.empty_cache()
+    return rec
+
+
+def flickr_record(mk, k, d, device):
+    """BASELINE.json config 0 / BASELINE.md section 4: MaxK-SAGE, Flickr-shaped graph, 3 layers, hidden
+    256, k = 32, forward + backward -- the reference's CPU formulation (torch.topk MaxK + CSR SpMM
+    through autograd; torch.sparse.mm stands in for DGL's CPU SpMM) on the host cores next to this
+    repo's model on the GPU, same weights shape, 3 warm-up + 10 timed iterations, median."""
+    from oracle import ref_torch
+    from spgemm_gnn_b200.graph import FEATS, shaped_graph
+    from spgemm_gnn_b200.models import SAGE
+    import torch.nn.functional as F
+    g = shaped_graph("flickr", device=device)
+    n, e = g.num_nodes(), g.num_edges()
+    in_feats, classes = FEATS["flickr"]
+    gen = torch.Generator(device=device).manual_seed(11)
+    feats = torch.randn(n, in_feats, device=device, generator=gen)
+    labels = torch.randint(0, classes, (n,), device=device, generator=gen)
+    torch.manual_seed(97)
+    model = SAGE(in_feats, d, 3, classes, maxk=k, feat_drop=0.0, norm=True).to(device)
+
+    def gpu_iter():
+        model.zero_grad(set_to_none=True)
+        F.cross_entropy(model(g, feats), labels).backward()
+
+    for _ in range(3):
+        gpu_iter()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        gpu_iter()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    gpu_ms = statistics.median(ts)
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gc = g.to("cpu")
+    adj = ref_torch.csr_matrix(gc.indptr, gc.indices, gc.edge_weights("mean"), n)
+    torch.manual_seed(97)
+    ref = ref_torch.RefSAGE(in_feats, d, 3, classes, maxk=k, feat_drop=0.0, norm=True)
+    fc, lc = feats.cpu(), labels.cpu()
+
+    def cpu_iter():
+        ref.zero_grad(set_to_none=True)
+        F.cross_entropy(ref(adj, fc), lc).backward()
+
+    for _ in range(3):
+        cpu_iter()
+    cs = []
+    for _ in range(10):
+        t0 = time.perf_counter()
+        cpu_iter()
+        cs.append((time.perf_counter() - t0) * 1e3)
+    cpu_ms = statistics.median(cs)
+    layers = 3
+    return {"graph": f"flickr-shaped synthetic graph, {n} nodes, {e} stored entries",
+            "model": f"MaxK-SAGE 3x{d}, k={k}, in {in_feats}, classes {classes}, LayerNorm, no dropout, forward+backward",
+            "gpu_ms_per_iter": gpu_ms, "cpu_ms_per_iter": cpu_ms, "cpu_cores": cores,
+            "gpu_edges_per_s": 2.0 * layers * e / (gpu_ms * 1e-3),
+            "cpu_edges_per_s": 2.0 * layers * e / (cpu_ms * 1e-3),
+            "cpu_kind": "port (oracle/ref_torch.py RefSAGE: torch.topk MaxK + torch.sparse.mm CSR SpMM, autograd)"}
+
+
+# ---------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -216,10 +495,12 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debug only)")
     ap.add_argument("--max-nz", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-rows", type=float, default=1.0 / 32, help="row fraction of the CPU sample")
+    ap.add_argument("--cpu-rows", type=float, default=1.0 / 8, help="row fraction of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-epoch", action="store_true", help="skip the MaxK-SAGE epoch timing")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the parity / ksweep / products / flickr records (debug only)")
     ap.add_argument("--epochs", type=int, default=8)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -234,8 +515,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        dev = "cuda" if torch.cuda.is_available() else "cpu"
-        g = shaped_graph(args.workload, scale=args.scale, device=dev)
+        # CPU only: the reference arm must not touch the GPU (graph generation included)
+        g = shaped_graph(args.workload, scale=args.scale, device="cpu")
         n, e = g.num_nodes(), g.num_edges()
         val = g.edge_weights("mean")
         sample, rows, e_s = cpu_sample_of(g, val, args.cpu_rows)
@@ -396,12 +677,23 @@ def main():
     dom = "spgemm_fwd" if fwd_ms >= bwd_ms else "sspmm_bwd"
     dom_ms, dom_bytes = (fwd_ms, bf) if dom == "spgemm_fwd" else (bwd_ms, bb)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(dom, args.workload),
+    traffic, traffic_src = ncu_traffic(dom, args.workload, k) if world == 1 else (None, None)
+    # which memory level the algorithmic bytes are served from: when the ncu DRAM traffic is a small
+    # part of them (Reddit shape: the 37 MB CBSR table and the 30 MB gradient live in the 126 MB L2)
+    # the kernel is bound by L2 + the SM's load/store pipes, and `frac` compares L2-served bytes with
+    # a DRAM copy peak -- it may exceed 1; `dram_frac` is the honest HBM utilisation
+    table_bytes = n_src * k * (4 + w)
+    in_l2 = (traffic is not None and traffic < 0.5 * dom_bytes) or (traffic is None and table_bytes < (96 << 20))
+    roofline = {"bound": "l2+lsu" if in_l2 else "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "dram_frac": (traffic / (dom_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_bytes": dom_bytes, "launch_ms": dom_ms,
                 "compulsory_bytes": e_local * 8 + n_src * k * (4 + w) + n_rows * d * 4,
-                "note": "algorithmic bytes count every CBSR row gather; the CBSR table itself is "
-                        "L2-resident for this shape, so achieved GB/s is L2+HBM traffic over time"}
+                "note": "algorithmic bytes count every CBSR row gather (SURVEY 8d); on this shape the "
+                        "CBSR table / gradient are L2-resident, so `achieved` is L2+HBM bytes over time "
+                        "and `dram_frac` (ncu DRAM bytes / launch time / peak) is the HBM utilisation; "
+                        "the HBM-bound case of the same kernels is the `products` record"}
     kernels = {
         "spgemm_fwd_ms": fwd_ms, "sspmm_bwd_ms": bwd_ms,
         "spgemm_fwd_alg_GBps": bf / (fwd_ms * 1e-3) / 1e9, "sspmm_bwd_alg_GBps": bb / (bwd_ms * 1e-3) / 1e9,
@@ -413,10 +705,21 @@ def main():
         "edges_per_s_fwd": e / (fwd_ms * 1e-3), "edges_per_s_bwd": e / (bwd_ms * 1e-3),
         "layer_ms_with_maxk_and_scatter": fwd_ms + bwd_ms + topk_ms + scatter_ms,
         "work_records": part.num_parts, "partial_slots": part.num_slots, "max_nz": mk.get_max_nz(),
-        "forward_variant": "banked (mk_cbsr_bank + mk_spgemm_fwd_banked, both inside spgemm_fwd_ms)"
-        if mk.use_banked(part.num_parts, e_local, k, d) else "plain (mk_spgemm_fwd)",
+        "forward_variant": mk.forward_variant(part.num_parts, e_local, k, d),
     }
     kernels.update(cold)
+
+    # ---- records next to the headline: parity of the sharded path, BASELINE configs 2, 4 and 0
+    parity = ksweep = products = flickr = None
+    if not args.no_extra:
+        if world > 1:
+            parity = parity_record(mk, mdist, g, rank, world, ptr, idx, val, val_full, x_local, dy, k, d, device)
+        if args.workload == "reddit" and args.scale == 1.0:
+            if world == 1:
+                ksweep = ksweep_record(mk, g, val_full, x_local, dy, d, peak)
+            products = products_record(mk, mdist, rank, world, k, d, device, peak)
+        if world == 1:
+            flickr = flickr_record(mk, k, d, device)
 
     # ---- end to end through the public entry points with HOST buffers
     e2e = None
@@ -590,7 +893,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world, n, e), "clocks": clk, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
-            "sage_epoch": epoch,
+            "sage_epoch": epoch, "parity": parity, "ksweep": ksweep, "products": products, "flickr": flickr,
         }
         print(json.dumps(line))
     if world > 1:

@@ -81,6 +81,7 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
     __syncwarp();
 
     float* __restrict__ my = acc + 8 * g;
+    const unsigned gmask = 0xffu << (8 * g);  // the lanes that share this group's banks
     const int end = rec.loc + rec.len;
     for (int base = rec.loc; base < end; base += 32) {
         const int n_here = min(32, end - base);
@@ -109,15 +110,13 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (ok[u]) {
+                if (ok[u]) {  // uniform over the 8 lanes of a group
 #pragma unroll
-                    for (int q = 0; q < CAP; ++q) {
+                    for (int q = 0; q < CAP; ++q)
                         if (dv[u][q] != 0.0f) my[sl[u][q]] += vv[u] * dv[u][q];
-#ifdef MK_SYNCWARP_STEPS
-                        __syncwarp();
-#endif
-                    }
+                    accum_fence_group(gmask);
                 }
+                accum_fence_warp();
             }
         }
     }

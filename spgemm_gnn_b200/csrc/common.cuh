@@ -74,6 +74,30 @@ __device__ __forceinline__ void red_add_f1(float* p, float a) {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// ---- ordering of the forward's shared-memory accumulation --------------------------------------
+// The forward kernels add into shared-memory cells with plain LDS / FFMA / STS.  The lanes that work
+// on ONE neighbour hit distinct cells (columns of a CBSR row are distinct), but the same lanes
+// handle another neighbour in the next step and may then hit a cell a DIFFERENT lane of the group
+// updated before.  That read-after-write between lanes needs an ordering the programming model only
+// gives through __syncwarp: `accum_fence(mask)` after every neighbour, over the lanes that share an
+// accumulator (lane groups with private accumulators never touch each other's cells).
+//   MK_SYNC_MODE 1 (default)  group-scoped __syncwarp(mask) per neighbour
+//   MK_SYNC_MODE 2            full-warp __syncwarp() per step (callers place it outside divergent code)
+//   MK_SYNC_MODE 0            no fence (round-1 behaviour; measured for the record only)
+#ifndef MK_SYNC_MODE
+#define MK_SYNC_MODE 1
+#endif
+__device__ __forceinline__ void accum_fence_group(unsigned mask) {
+#if MK_SYNC_MODE == 1
+    __syncwarp(mask);
+#endif
+}
+__device__ __forceinline__ void accum_fence_warp() {
+#if MK_SYNC_MODE == 2
+    __syncwarp();
+#endif
+}
+
 // ---- CBSR index access -------------------------------------------------------------------
 template <typename IdxT>
 struct Idx4;  // four consecutive column ids in one load

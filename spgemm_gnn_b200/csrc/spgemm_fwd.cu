@@ -54,6 +54,7 @@ spgemm_fwd_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx
     __syncwarp();
 
     float* __restrict__ my = acc + g * dpad;
+    const unsigned gmask = (S::LPN >= 32 ? kFull : ((1u << (S::LPN & 31)) - 1u)) << (g * S::LPN);
     const int end = rec.loc + rec.len;
     for (int base = rec.loc; base < end; base += 32) {
         const int n_here = min(32, end - base);
@@ -86,11 +87,13 @@ spgemm_fwd_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (ok[u]) {
+                if (ok[u]) {  // uniform over the lanes of a group
 #pragma unroll
                     for (int q = 0; q < S::EPL; ++q)
                         if (dv[u][q] != 0.0f) my[cv[u][q]] += vv[u] * dv[u][q];
+                    accum_fence_group(gmask);
                 }
+                accum_fence_warp();
             }
         }
     }
@@ -202,6 +205,7 @@ spgemm_fwd_vec_kernel(const mk_part* __restrict__ parts, const int* __restrict__
     __syncwarp();
 
     float* __restrict__ my = acc + g * dpad;
+    const unsigned gmask = (LPN >= 32 ? kFull : ((1u << (LPN & 31)) - 1u)) << (g * LPN);
     const int end = rec.loc + rec.len;
     for (int base = rec.loc; base < end; base += 32) {
         const int n_here = min(32, end - base);
@@ -229,11 +233,13 @@ spgemm_fwd_vec_kernel(const mk_part* __restrict__ parts, const int* __restrict__
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (ok[u]) {
+                if (ok[u]) {  // uniform over the lanes of a group
 #pragma unroll
                     for (int q = 0; q < EPL; ++q)
                         if (dv[u][q] != 0.0f) my[cv[u][q]] += vv[u] * dv[u][q];
+                    accum_fence_group(gmask);
                 }
+                accum_fence_warp();
             }
         }
     }

@@ -33,7 +33,7 @@ __all__ = [
     "maxk_forward_cbsr", "cbsr_scatter", "cbsr_gather", "partition",
     "clear_partition_cache", "install_partition", "set_max_nz", "get_max_nz", "launch_count",
     "banked_supported", "cbsr_bank", "maxk_forward_banked", "spgemm_forward_banked",
-    "spgemm_backward_banked", "set_banked", "set_backward_tma", "use_banked", "partition_blocked", "backward_blocks",
+    "spgemm_backward_banked", "set_banked", "set_backward_tma", "use_banked", "forward_variant", "partition_blocked", "backward_blocks",
     "set_backward_block_mb", "add_layernorm_supported", "add_layernorm_forward", "layernorm_backward",
 ]
 
@@ -82,6 +82,13 @@ def use_banked(num_parts: int, num_edges: int, dim_sparse: int, dim_origin: int)
     # ties at 16, loses at 8 (too few entries per row to balance 8 banks)
     return (_BANKED and dim_sparse >= 32 and banked_supported(dim_sparse, dim_origin)
             and num_edges >= _BANKED_MIN_RECORD * max(num_parts, 1))
+
+
+def forward_variant(num_parts: int, num_edges: int, dim_sparse: int, dim_origin: int) -> str:
+    """Which forward `spgemm_forward` runs for this shape (reported by bench.py)."""
+    if use_banked(num_parts, num_edges, dim_sparse, dim_origin):
+        return "banked (mk_cbsr_bank + mk_spgemm_fwd_banked, both inside the forward time)"
+    return "plain (mk_spgemm_fwd)"
 
 
 def _stream() -> int:
@@ -220,6 +227,17 @@ class _Partition:
 _part_cache = {}
 
 
+def _evict(cache: dict, limit: int) -> None:
+    """Keep a record cache bounded: entries whose row pointer is gone go first, then the oldest
+    (dicts keep insertion order) -- never the whole cache at once."""
+    if len(cache) < limit:
+        return
+    for key in [k for k, v in cache.items() if v.ptr_ref() is None]:
+        del cache[key]
+    while len(cache) >= limit:
+        del cache[next(iter(cache))]
+
+
 def clear_partition_cache() -> None:
     _part_cache.clear()
     _block_cache.clear()
@@ -251,8 +269,7 @@ def partition(ptr: torch.Tensor, num_nodes: int, max_nz: Optional[int] = None) -
     _launches += 5
     p.ptr_ref = weakref.ref(ptr)
     p.version = ptr._version
-    if len(_part_cache) > 64:
-        _part_cache.clear()
+    _evict(_part_cache, 64)
     _part_cache[key] = p
     return p
 
@@ -325,8 +342,7 @@ def partition_blocked(ptr: torch.Tensor, idx: torch.Tensor, num_nodes: int, n_sr
     _launches += 6
     p.ptr_ref = weakref.ref(ptr)
     p.version = ptr._version
-    if len(_block_cache) > 32:
-        _block_cache.clear()
+    _evict(_block_cache, 32)
     _block_cache[key] = p
     return p
 

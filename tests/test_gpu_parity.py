@@ -8,6 +8,8 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import oracle_sample_check
+
 pytestmark = pytest.mark.gpu
 
 REL_TOL = 1e-5
@@ -432,8 +434,9 @@ def test_autograd_layer_matches_torch_reference(mk, kind):
     assert torch.equal(xc.grad.cpu() == 0, dx_ref == 0)
 
 
+
 # ---------------------------------------------------------------------------------------
-# full BASELINE size: properties that need no CPU oracle
+# full BASELINE size: properties that need no CPU oracle, plus an oracle check on a row sample
 # ---------------------------------------------------------------------------------------
 def test_reddit_shape_properties(mk):
     """Reddit-shaped synthetic graph (232,965 nodes, ~114M edges), D=256, k=32: adjointness
@@ -466,6 +469,7 @@ def test_reddit_shape_properties(mk):
     # both sides are sums of ~6e7 signed terms: compare against the sum of their magnitudes
     scale = float((out.double().abs() * dy.double().abs()).sum())
     assert abs(lhs - rhs) <= 1e-8 * scale
+    oracle_sample_check(g, val, sp_data, sp_index, out, dy, dxs, 256, 32)
 
     # mean aggregation of a constant CBSR table reproduces the constant (rows of A sum to 1)
     ones = torch.ones_like(sp_data)
@@ -623,6 +627,7 @@ def test_other_baseline_shapes_full_size(mk, shape, d, k):
     rhs = float((sp_data.double() * dxs.double()).sum())
     scale = float((out.double().abs() * dy.double().abs()).sum())
     assert abs(lhs - rhs) <= 1e-8 * scale
+    oracle_sample_check(g, val, sp_data, sp_index, out, dy, dxs, d, k)
 
 
 def test_empty_and_extreme_inputs(mk):

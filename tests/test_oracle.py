@@ -244,3 +244,33 @@ def test_scatter_gather_round_trip():
     assert np.array_equal(c_oracle.cbsr_gather(dense, idx), data)
     out, _ = mo.maxk_dense_forward(x, 12)
     assert np.array_equal(dense, out)
+
+
+def test_row_sample_checker_agrees_with_the_whole_problem_oracle():
+    """The sampler the full-size GPU tests use (conftest.oracle_sample_check) cuts sub-problems out
+    of the graph; fed with the whole-problem oracle's own results it must pass, and it must notice a
+    single wrong element."""
+    import pytest
+    import torch
+    from conftest import oracle_sample_check, small_graph
+    from oracle import c_oracle
+    g = small_graph(600, 20)
+    n, d, k = g.num_nodes(), 64, 8
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    dy = rng.standard_normal((n, d)).astype(np.float32)
+    val = g.edge_weights("both")
+    wd, wi = c_oracle.maxk_cbsr(x, k)
+    ptr, idx = g.indptr.numpy(), g.indices.numpy()
+    out = torch.from_numpy(c_oracle.spgemm_fwd(ptr, idx, val.numpy(), wd, wi, d).astype(np.float32))
+    dxs = torch.from_numpy(c_oracle.sspmm_bwd(ptr, idx, val.numpy(), dy, wi).astype(np.float32))
+    args = (g, val, torch.from_numpy(wd), torch.from_numpy(wi))
+    oracle_sample_check(*args, out, torch.from_numpy(dy), dxs, d, k, n_sample=600)
+    bad = out.clone()
+    bad[17, int(wi[g.indices[g.indptr[17]]][0])] += 1e-2
+    with pytest.raises(AssertionError):
+        oracle_sample_check(*args, bad, torch.from_numpy(dy), dxs, d, k, n_sample=600)
+    badb = dxs.clone()
+    badb[5, 3] += 1e-2
+    with pytest.raises(AssertionError):
+        oracle_sample_check(*args, out, torch.from_numpy(dy), badb, d, k, n_sample=600)
