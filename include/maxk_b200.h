@@ -33,7 +33,8 @@ extern "C" {
 #define MK_API __attribute__((visibility("default")))
 #endif
 
-#define MK_VERSION 101 /* major*100 + minor; 1.01 added the mk_peer_* exchange and mk_sspmm_bwd_tma */
+#define MK_VERSION 200 /* major*100 + minor; 2.00: overlapped copy-engine all-gather (mk_peer_push & co. replace
+                          * mk_peer_allgather / mk_peer_bank_push), mk_spgemm_fwd_banked_ex, soft peer time-outs */
 
 enum {
     MK_OK = 0,
@@ -161,6 +162,22 @@ MK_API int mk_spgemm_fwd_banked(const mk_part* parts, int64_t num_parts, int64_t
                                 const int32_t* idx, const float* val, const float* bk_data,
                                 const uint16_t* bk_slot, float* out, float* partial, int64_t n_rows,
                                 int k, int d, void* stream);
+/* mk_spgemm_fwd_banked with the knobs of the row-partitioned and the load-balanced forms:
+ *   exec_parts  (nullable) the same records in the order the CTAs should take them (peer.py /
+ *               maxk_kernels.py sort them longest first, so that the grid drains on short records);
+ *               `parts` stays in row order for the fold of the multi-record rows;
+ *   split       (nullable) int32 [n_rows]: position in idx of the first stored entry of the row whose
+ *               column is >= rank * rows_per_rank; a record walks [split, end) first, [begin, split)
+ *               second -- the order in which mk_peer_push lets the source blocks arrive;
+ *   wait_window (nullable) this rank's window of the table that is still arriving: the kernel checks
+ *               done[q] (peer.cuh) before it reads rows [q*rows_per_rank, (q+1)*rows_per_rank), and
+ *               when it has finished the whole table has arrived.                                  */
+MK_API int mk_spgemm_fwd_banked_ex(const mk_part* parts, int64_t num_parts, int64_t num_slots,
+                                   const mk_part* exec_parts, const int32_t* idx, const float* val,
+                                   const float* bk_data, const uint16_t* bk_slot, float* out,
+                                   float* partial, int64_t n_rows, int k, int d, const int32_t* split,
+                                   const void* wait_window, int world, int rank, int64_t rows_per_rank,
+                                   int timeout_ms, void* stream);
 MK_API int mk_sspmm_bwd_banked(const mk_part* parts, int64_t num_parts, const int32_t* idx,
                                const float* val, const float* dy, const uint16_t* bk_slot,
                                float* dxs, int64_t n_rows, int64_t n_src, int k, int d, void* stream);
@@ -184,17 +201,31 @@ MK_API int mk_layernorm_bwd(const float* gy, const float* z, const float* gamma,
  * Not in the reference (single GPU; README_INTEGRATED.md:382 lists "Multi-GPU support with NCCL" as
  * future work).  SURVEY.md section 8e: 1-D row partition, all-gather of the CBSR table in front of
  * the forward SpGEMM, reduce-scatter of the CBSR gradient behind the backward SSpMM.  These entry
- * points are that pair as this library's own kernels over peer-mapped memory (NVLink loads/stores),
- * next to the torch.distributed/NCCL form in spgemm_gnn_b200/dist.py.
+ * points are that pair over peer-mapped memory (NVLink), next to the torch.distributed/NCCL form in
+ * spgemm_gnn_b200/dist.py.
  *
  * A WINDOW is one device buffer per rank (same size on every rank) that every peer process maps
  * with CUDA IPC.  Its first MK_PEER_HEADER_BYTES are flags owned by the library (zeroed by
  * mk_peer_alloc, never to be written by the caller); payload offsets below count from the window
  * base and must be >= MK_PEER_HEADER_BYTES and 16-byte aligned.  `h_windows[q]` is rank q's window
  * in the caller's address space (own window: the mk_peer_alloc pointer; others: mk_peer_open).
- * All ranks must issue the same collectives on a window in the same order.  Kernels that wait for
- * a peer longer than `timeout_ms` (<= 0: 30 s) set the header's error word and trap.  `grid` is the
- * number of thread blocks (0: the library's choice for the device).                               */
+ * All ranks must issue the same collectives on a window in the same order.  A kernel that waits for
+ * a peer longer than `timeout_ms` (<= 0: 30 s) writes the collective's number into the header's
+ * error word and stops waiting (its results are then undefined; mk_peer_epoch reports the word).
+ *
+ * Overlapped all-gather (the forward).  Per collective, on the rank's main stream unless noted:
+ *   mk_peer_begin_push   one-block kernel: returns when every peer has released the table buffer
+ *                        (0 or 1) that is about to be overwritten;
+ *   <producer>           the rank's rows are written into its OWN window (mk_cbsr_bank outputs, ...);
+ *   mk_peer_publish      opens collective e = epoch + 1: the own rows are complete;
+ *   mk_peer_push         on a SIDE stream, after an event recorded behind mk_peer_publish: one
+ *                        cudaMemcpyAsync per peer and segment (copy engines, no SM), peers visited
+ *                        rank-1, rank-2, ...; each peer's copies are followed by a 4-byte copy of e
+ *                        into done[rank] of that peer's header.  Segment g of this rank is the
+ *                        h_bytes[g] bytes at h_offsets[g] + rank * h_bytes[g] of every window;
+ *   <consumer>           mk_spgemm_fwd_banked_ex(wait_window = own window) starts at once and waits
+ *                        per source block; any other consumer calls mk_peer_wait_all first;
+ *   mk_peer_release      after the last reader of the table: tells the peers this rank is done with it. */
 #define MK_PEER_MAX_RANKS 16
 #define MK_PEER_HEADER_BYTES 1024
 #define MK_PEER_HANDLE_BYTES 64
@@ -205,28 +236,24 @@ MK_API int mk_peer_open(const unsigned char* h_handle, void** window);
 MK_API int mk_peer_close(void* window);
 /* collectives completed through the window and its error word (synchronises the stream)          */
 MK_API int mk_peer_epoch(const void* window, uint32_t* h_epoch, uint32_t* h_error, void* stream);
-/* All-gather by stores: segment g of this rank (h_src[g], h_bytes[g] bytes, a multiple of 16) lands
- * at h_offsets[g] + rank * h_bytes[g] in EVERY rank's window.  Up to 4 segments per launch.  When
- * the call's kernel has finished, this rank's window holds every rank's segments.               */
-MK_API int mk_peer_allgather(void* const* h_windows, int world, int rank, int n_seg,
-                             const void* const* h_src, const int64_t* h_bytes,
-                             const int64_t* h_offsets, int grid, int timeout_ms, void* stream);
-/* mk_cbsr_bank fused with the all-gather: the banked values (fp32), cell offsets (uint16) and the
- * SORTED column ids of this rank's n rows are written into rows [rank*n, rank*n + n) of the three
- * [world*n, k] tables at off_data / off_slot / off_index of every rank's window.  mode 1: every row
- * is stored straight into all tables (measured, the default); mode 2: rows go to the own table,
- * then each block copies its contiguous range to the peers with 16-byte stores (experimental;
- * needs n*k*index_bytes % 16 == 0).                                                             */
-MK_API int mk_peer_bank_push(const float* sp_data, const void* sp_index, int index_bytes,
-                             void* const* h_windows, int world, int rank, int64_t off_data,
-                             int64_t off_slot, int64_t off_index, int64_t n, int k, int d,
-                             int mode, int timeout_ms, void* stream);
-/* Reduce-scatter by loads: out[0 .. block_bytes/4) = sum over q (rank order, fixed) of the floats at
- * offset + rank * block_bytes of rank q's window.  When the call's kernel has finished, no peer
- * reads this rank's window any more (it may be overwritten).                                     */
+MK_API int mk_peer_begin_push(void* window, int world, int rank, int buffer, int timeout_ms, void* stream);
+MK_API int mk_peer_publish(void* window, int rank, int buffer, void* stream);
+MK_API int mk_peer_push(void* const* h_windows, int world, int rank, int n_seg,
+                        const int64_t* h_offsets, const int64_t* h_bytes, void* stream);
+MK_API int mk_peer_wait_all(void* window, int world, int timeout_ms, void* stream);
+MK_API int mk_peer_release(void* const* h_windows, int world, int rank, void* stream);
+/* Reduce-scatter by loads (the backward): out[0 .. block_bytes/4) = sum over q (rank order, fixed) of
+ * the floats at offset + rank * block_bytes of rank q's window.  When the call's kernel has
+ * finished, no peer reads this rank's window any more (it may be overwritten).  `grid` is the number
+ * of thread blocks (0: the library's choice); it is capped so that the grid is resident at once.
+ * The _virtual form runs ALL ranks of a single-process emulation (every window on one device) in
+ * one launch -- separate launches that wait on one another must not share a device; tests only.   */
 MK_API int mk_peer_reduce_scatter(void* const* h_windows, int world, int rank, int64_t offset,
                                   int64_t block_bytes, float* out, int grid, int timeout_ms,
                                   void* stream);
+MK_API int mk_peer_reduce_scatter_virtual(void* const* h_windows, int world, int64_t offset,
+                                          int64_t block_bytes, float* const* h_outs, int grid,
+                                          int timeout_ms, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,8 @@ SIGNATURES = {
     "mk_banked_rows": (_i32, [_i32]),
     "mk_cbsr_bank": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "mk_spgemm_fwd_banked": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "mk_spgemm_fwd_banked_ex": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
+                                       _vp, _vp, _i32, _i32, _i64, _i32, _vp]),
     "mk_sspmm_bwd_banked": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     "mk_peer_alloc": (_i32, [_i64, ctypes.POINTER(_vp)]),
     "mk_peer_free": (_i32, [_vp]),
@@ -45,11 +47,13 @@ SIGNATURES = {
     "mk_peer_open": (_i32, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "mk_peer_close": (_i32, [_vp]),
     "mk_peer_epoch": (_i32, [_vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), _vp]),
-    "mk_peer_allgather": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _i32, ctypes.POINTER(_vp),
-                                 ctypes.POINTER(_i64), ctypes.POINTER(_i64), _i32, _i32, _vp]),
-    "mk_peer_bank_push": (_i32, [_vp, _vp, _i32, ctypes.POINTER(_vp), _i32, _i32, _i64, _i64, _i64,
-                                 _i64, _i32, _i32, _i32, _i32, _vp]),
+    "mk_peer_begin_push": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp]),
+    "mk_peer_publish": (_i32, [_vp, _i32, _i32, _vp]),
+    "mk_peer_push": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp]),
+    "mk_peer_wait_all": (_i32, [_vp, _i32, _i32, _vp]),
+    "mk_peer_release": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _vp]),
     "mk_peer_reduce_scatter": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _i64, _i64, _vp, _i32, _i32, _vp]),
+    "mk_peer_reduce_scatter_virtual": (_i32, [ctypes.POINTER(_vp), _i32, _i64, _i64, ctypes.POINTER(_vp), _i32, _i32, _vp]),
 }
 
 _lib = None

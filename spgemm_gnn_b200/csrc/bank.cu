@@ -18,7 +18,6 @@
 // 32*row + bank of every entry.  The assignment is sequential in nature, so it runs one thread
 // per row (32 rows per warp side by side); the data movement runs one warp per row.
 #include "common.cuh"
-#include "peer.cuh"
 
 namespace mk {
 
@@ -44,42 +43,14 @@ __device__ __forceinline__ int bank_slot_b(int c, int ra) {
 // Phase 1 (one thread per row): choose copy and position of every entry, leave one descriptor
 // byte per entry (position | copy << 7) in shared memory.  Phase 2 (one warp per row): move the
 // row with coalesced loads and stores.  bk_index may be null (the forward kernel does not need it).
-//
-// PUSH != 0 is the fused "bank -> all-gather" form of the row-partitioned forward (section 8e):
-// every row -- banked values, cell offsets and the SORTED column ids the backward needs -- ends up
-// in the table of EVERY rank (rows [row_base, row_base + n) of the windows in `pa`), under the flag
-// protocol of peer.cuh.  The sequential phase 1 runs before the first remote store, so waiting for
-// the peers' ready flags costs nothing.  bk_data / bk_index / bk_slot are not used in that form.
-//   PUSH == 1  phase 2 stores each row straight into all P tables: 128 / 64 / 32-byte lines per
-//              row and destination over NVLink (measured, the default);
-//   PUSH == 2  phase 2 stores the rows into the OWN table only; the block then copies its 128 rows
-//              (one contiguous range per table) to the P-1 peers with 16-byte vector stores, 512
-//              bytes per warp instruction on the wire (experimental, MAXK_PEER_PUSH_MODE=2).
-struct BankPushArgs {
-    PeerSet ps;
-    int world, rank;
-    int64_t off_data, off_slot, off_index;  // byte offsets of the three tables inside a window
-    int64_t row_base;                       // first table row of this rank
-    uint64_t timeout_ns;
-};
-
-__device__ __forceinline__ uint4 ld_cg_16(const uint4* p) {
-    uint4 r;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p)
-                 : "memory");
-    return r;
-}
-
-template <int K, typename IdxT, int PUSH>
+// In the row-partitioned forward the outputs point into the rank's peer window (peer.py), from
+// where the copy engines push the finished rows to the other ranks (mk_peer_push).
+template <int K, typename IdxT>
 __global__ void __launch_bounds__(128)
 cbsr_bank_kernel(const float* __restrict__ sp_data, const IdxT* __restrict__ sp_index,
                  float* __restrict__ bk_data, IdxT* __restrict__ bk_index,
-                 uint16_t* __restrict__ bk_slot, int64_t n, int d, const BankPushArgs pa) {
+                 uint16_t* __restrict__ bk_slot, int64_t n, int d) {
     using Mask = typename BankMask<K>::type;
-    uint32_t epoch = 0;
-    if (PUSH) epoch = peer_begin(pa.ps, pa.world, pa.rank);
     constexpr int CAP = K / 8;  // entries per bank when perfectly balanced == steps per neighbour
     constexpr int DSTRIDE = K + 4;
     __shared__ uint8_t desc[128 * DSTRIDE];
@@ -167,7 +138,6 @@ cbsr_bank_kernel(const float* __restrict__ sp_data, const IdxT* __restrict__ sp_
         }
     }
     __syncthreads();
-    if (PUSH) peer_wait_all_ready(pa.ps, pa.world, pa.rank, epoch, pa.timeout_ns);
 
     // ---- phase 2: warp w moves rows [32w, 32w+32) of the block, lane = entry; four rows are
     //      loaded before any is stored so that the row-to-row latency chain is a quarter as long
@@ -202,66 +172,28 @@ cbsr_bank_kernel(const float* __restrict__ sp_data, const IdxT* __restrict__ sp_
                     const int p = dsc & 0x7f;
                     const uint16_t cell =
                         static_cast<uint16_t>((dsc & 0x80) ? bank_slot_b(c, ra) : bank_slot_a(c));
-                    if (PUSH == 0) {
-                        bk_data[grow * K + p] = vv[q][j];
-                        bk_slot[grow * K + p] = cell;
-                        if (bk_index) bk_index[grow * K + p] = static_cast<IdxT>(c);
-                    } else if (PUSH == 2) {
-                        const int64_t trow = (pa.row_base + grow) * K;
-                        unsigned char* wq = pa.ps.win[pa.rank];
-                        reinterpret_cast<float*>(wq + pa.off_data)[trow + p] = vv[q][j];
-                        reinterpret_cast<uint16_t*>(wq + pa.off_slot)[trow + p] = cell;
-                        reinterpret_cast<IdxT*>(wq + pa.off_index)[trow + e] = static_cast<IdxT>(c);
-                    } else {
-                        const int64_t trow = (pa.row_base + grow) * K;
-                        for (int s = 0; s < pa.world; ++s) {  // own copy first, then rank+1, ...
-                            unsigned char* wq = pa.ps.win[(pa.rank + s) % pa.world];
-                            reinterpret_cast<float*>(wq + pa.off_data)[trow + p] = vv[q][j];
-                            reinterpret_cast<uint16_t*>(wq + pa.off_slot)[trow + p] = cell;
-                            reinterpret_cast<IdxT*>(wq + pa.off_index)[trow + e] = static_cast<IdxT>(c);
-                        }
-                    }
+                    bk_data[grow * K + p] = vv[q][j];
+                    bk_slot[grow * K + p] = cell;
+                    if (bk_index) bk_index[grow * K + p] = static_cast<IdxT>(c);
                 }
             }
         }
     }
-    if (PUSH == 2) {
-        // the block's rows now sit in the own table: one contiguous byte range per table (every
-        // range a multiple of 16 bytes, checked by the host), copied to the peers rank+1, rank+2, ...
-        __syncthreads();
-        const int64_t nrows = min(static_cast<int64_t>(128), n - row0);
-        const int64_t first = pa.row_base + row0;
-        const int64_t tab_off[3] = {pa.off_data, pa.off_slot, pa.off_index};
-        const int64_t row_bytes[3] = {K * 4, K * 2, K * static_cast<int64_t>(sizeof(IdxT))};
-        for (int s = 1; s < pa.world && nrows > 0; ++s) {
-            unsigned char* wq = pa.ps.win[(pa.rank + s) % pa.world];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const int64_t b0 = tab_off[a] + first * row_bytes[a];
-                const int64_t n16 = nrows * row_bytes[a] / 16;
-                const uint4* src = reinterpret_cast<const uint4*>(pa.ps.win[pa.rank] + b0);
-                uint4* dst = reinterpret_cast<uint4*>(wq + b0);
-                for (int64_t i = threadIdx.x; i < n16; i += 128) st_peer_16(dst + i, ld_cg_16(src + i));
-            }
-        }
-    }
-    if (PUSH) peer_end(pa.ps, pa.world, pa.rank, epoch, pa.timeout_ns);
 }
 
-template <typename IdxT, int PUSH>
+template <typename IdxT>
 static int launch_bank(const float* sp_data, const void* sp_index, float* bk_data, void* bk_index,
-                       uint16_t* bk_slot, int64_t n, int k, int d, const BankPushArgs& pa,
-                       cudaStream_t st) {
-    const int64_t blocks = PUSH && n == 0 ? 1 : (n + 127) / 128;  // the flag protocol is collective
+                       uint16_t* bk_slot, int64_t n, int k, int d, cudaStream_t st) {
+    const int64_t blocks = (n + 127) / 128;
     if (blocks > 0x7fffffffLL) return MK_EUNSUPPORTED;
     const IdxT* si = static_cast<const IdxT*>(sp_index);
     IdxT* bi = static_cast<IdxT*>(bk_index);
     const unsigned nb = static_cast<unsigned>(blocks);
     switch (k) {
-        case 8: cbsr_bank_kernel<8, IdxT, PUSH><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d, pa); break;
-        case 16: cbsr_bank_kernel<16, IdxT, PUSH><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d, pa); break;
-        case 32: cbsr_bank_kernel<32, IdxT, PUSH><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d, pa); break;
-        case 64: cbsr_bank_kernel<64, IdxT, PUSH><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d, pa); break;
+        case 8: cbsr_bank_kernel<8, IdxT><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d); break;
+        case 16: cbsr_bank_kernel<16, IdxT><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d); break;
+        case 32: cbsr_bank_kernel<32, IdxT><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d); break;
+        case 64: cbsr_bank_kernel<64, IdxT><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d); break;
         default: return MK_EUNSUPPORTED;
     }
     MK_LAUNCH_CHECK("cbsr_bank_kernel");
@@ -286,44 +218,7 @@ extern "C" int mk_cbsr_bank(const float* sp_data, const void* sp_index, int inde
     if (n == 0) return MK_OK;
     if (!sp_data || !sp_index || !bk_data || !bk_slot) return MK_EINVAL;
     cudaStream_t st = mk::as_stream(stream);
-    const mk::BankPushArgs none{};
     return index_bytes == 1
-               ? mk::launch_bank<uint8_t, 0>(sp_data, sp_index, bk_data, bk_index, bk_slot, n, k, d, none, st)
-               : mk::launch_bank<uint16_t, 0>(sp_data, sp_index, bk_data, bk_index, bk_slot, n, k, d, none, st);
-}
-
-extern "C" int mk_peer_bank_push(const float* sp_data, const void* sp_index, int index_bytes,
-                                 void* const* h_windows, int world, int rank, int64_t off_data,
-                                 int64_t off_slot, int64_t off_index, int64_t n, int k, int d,
-                                 int mode, int timeout_ms, void* stream) {
-    if (mode != 1 && mode != 2) return MK_EINVAL;
-    if (mode == 2 && (n * k * index_bytes) % 16 != 0) return MK_EINVAL;
-    if (n < 0 || d < 1 || k < 1 || k > d) return MK_EINVAL;
-    if (index_bytes != 1 && index_bytes != 2) return MK_EINVAL;
-    if ((index_bytes == 1 && d > 256)) return MK_EINVAL;
-    if (!mk_banked_supported(k, d)) return MK_EUNSUPPORTED;
-    if (world < 1 || world > mk::kMaxPeers || rank < 0 || rank >= world || !h_windows) return MK_EINVAL;
-    if (off_data < mk::kHdrBytes || off_slot < mk::kHdrBytes || off_index < mk::kHdrBytes) return MK_EINVAL;
-    if ((off_data & 15) || (off_slot & 15) || (off_index & 15)) return MK_EINVAL;
-    if (n > 0 && (!sp_data || !sp_index)) return MK_EINVAL;
-    mk::BankPushArgs pa{};
-    for (int q = 0; q < world; ++q) {
-        if (!h_windows[q]) return MK_EINVAL;
-        pa.ps.win[q] = static_cast<unsigned char*>(h_windows[q]);
-    }
-    pa.world = world;
-    pa.rank = rank;
-    pa.off_data = off_data;
-    pa.off_slot = off_slot;
-    pa.off_index = off_index;
-    pa.row_base = static_cast<int64_t>(rank) * n;
-    pa.timeout_ns = static_cast<uint64_t>(timeout_ms > 0 ? timeout_ms : 30000) * 1000000ull;
-    cudaStream_t st = mk::as_stream(stream);
-    if (mode == 2)
-        return index_bytes == 1
-                   ? mk::launch_bank<uint8_t, 2>(sp_data, sp_index, nullptr, nullptr, nullptr, n, k, d, pa, st)
-                   : mk::launch_bank<uint16_t, 2>(sp_data, sp_index, nullptr, nullptr, nullptr, n, k, d, pa, st);
-    return index_bytes == 1
-               ? mk::launch_bank<uint8_t, 1>(sp_data, sp_index, nullptr, nullptr, nullptr, n, k, d, pa, st)
-               : mk::launch_bank<uint16_t, 1>(sp_data, sp_index, nullptr, nullptr, nullptr, n, k, d, pa, st);
+               ? mk::launch_bank<uint8_t>(sp_data, sp_index, bk_data, bk_index, bk_slot, n, k, d, st)
+               : mk::launch_bank<uint16_t>(sp_data, sp_index, bk_data, bk_index, bk_slot, n, k, d, st);
 }

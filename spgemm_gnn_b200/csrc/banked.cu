@@ -13,48 +13,103 @@
 // over the 4 groups and the 2 copies when the row is written.  Backward: the cells are replicas
 // of dY[r, :], built once per record.
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace mk {
 
-template <int CAP>
+// Loads of a lane's CAP consecutive entries.  CG = false: read-only path (ld.global.nc), the
+// table is complete before the kernel starts.  CG = true: L2-coherent loads (ld.global.cg) for the
+// forward that runs while peers are still storing other rows of the table over NVLink (the L1 hit
+// rate of these gathers is 0.15 % -- profiles/r1_final_* -- so nothing is lost).
+template <bool CG>
+__device__ __forceinline__ float4 ld_tab_f4(const float* p) {
+    if (!CG) return __ldg(reinterpret_cast<const float4*>(p));
+    float4 r;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+template <bool CG>
+__device__ __forceinline__ float2 ld_tab_f2(const float* p) {
+    if (!CG) return __ldg(reinterpret_cast<const float2*>(p));
+    float2 r;
+    asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+template <bool CG>
+__device__ __forceinline__ float ld_tab_f1(const float* p) {
+    if (!CG) return __ldg(p);
+    float r;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+template <bool CG>
+__device__ __forceinline__ uint4 ld_tab_u4(const void* p) {
+    if (!CG) return __ldg(reinterpret_cast<const uint4*>(p));
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+template <bool CG>
+__device__ __forceinline__ uint2 ld_tab_u2(const void* p) {
+    if (!CG) return __ldg(reinterpret_cast<const uint2*>(p));
+    uint2 r;
+    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+template <bool CG>
+__device__ __forceinline__ uint32_t ld_tab_u1(const void* p) {
+    if (!CG) return __ldg(reinterpret_cast<const uint32_t*>(p));
+    uint32_t r;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+template <bool CG>
+__device__ __forceinline__ uint32_t ld_tab_h1(const uint16_t* p) {
+    if (!CG) return __ldg(p);
+    uint16_t r;
+    asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p));
+    return r;
+}
+
+template <int CAP, bool CG = false>
 struct BankedLoad;
-template <>
-struct BankedLoad<1> {
-    static __device__ __forceinline__ void data(const float* p, float (&v)[1]) { v[0] = __ldg(p); }
-    static __device__ __forceinline__ void slots(const uint16_t* p, int (&s)[1]) { s[0] = __ldg(p); }
+template <bool CG>
+struct BankedLoad<1, CG> {
+    static __device__ __forceinline__ void data(const float* p, float (&v)[1]) { v[0] = ld_tab_f1<CG>(p); }
+    static __device__ __forceinline__ void slots(const uint16_t* p, int (&s)[1]) { s[0] = ld_tab_h1<CG>(p); }
 };
-template <>
-struct BankedLoad<2> {
+template <bool CG>
+struct BankedLoad<2, CG> {
     static __device__ __forceinline__ void data(const float* p, float (&v)[2]) {
-        const float2 f = __ldg(reinterpret_cast<const float2*>(p));
+        const float2 f = ld_tab_f2<CG>(p);
         v[0] = f.x; v[1] = f.y;
     }
     static __device__ __forceinline__ void slots(const uint16_t* p, int (&s)[2]) {
-        const ushort2 q = __ldg(reinterpret_cast<const ushort2*>(p));
-        s[0] = q.x; s[1] = q.y;
+        const uint32_t q = ld_tab_u1<CG>(p);
+        s[0] = q & 0xffff; s[1] = q >> 16;
     }
 };
-template <>
-struct BankedLoad<4> {
+template <bool CG>
+struct BankedLoad<4, CG> {
     static __device__ __forceinline__ void data(const float* p, float (&v)[4]) {
-        const float4 f = __ldg(reinterpret_cast<const float4*>(p));
+        const float4 f = ld_tab_f4<CG>(p);
         v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
     }
     static __device__ __forceinline__ void slots(const uint16_t* p, int (&s)[4]) {
-        const ushort4 q = __ldg(reinterpret_cast<const ushort4*>(p));
-        s[0] = q.x; s[1] = q.y; s[2] = q.z; s[3] = q.w;
+        const uint2 q = ld_tab_u2<CG>(p);
+        s[0] = q.x & 0xffff; s[1] = q.x >> 16; s[2] = q.y & 0xffff; s[3] = q.y >> 16;
     }
 };
-template <>
-struct BankedLoad<8> {
+template <bool CG>
+struct BankedLoad<8, CG> {
     static __device__ __forceinline__ void data(const float* p, float (&v)[8]) {
-        const float4 f = __ldg(reinterpret_cast<const float4*>(p));
-        const float4 h = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        const float4 f = ld_tab_f4<CG>(p);
+        const float4 h = ld_tab_f4<CG>(p + 4);
         v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
         v[4] = h.x; v[5] = h.y; v[6] = h.z; v[7] = h.w;
     }
     static __device__ __forceinline__ void slots(const uint16_t* p, int (&s)[8]) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint4 q = ld_tab_u4<CG>(p);
         s[0] = q.x & 0xffff; s[1] = q.x >> 16; s[2] = q.y & 0xffff; s[3] = q.y >> 16;
         s[4] = q.z & 0xffff; s[5] = q.z >> 16; s[6] = q.w & 0xffff; s[7] = q.w >> 16;
     }
@@ -63,12 +118,26 @@ struct BankedLoad<8> {
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <int K, int U>
+// Forward over a table that may still be ARRIVING (multi-GPU, peer.cuh): rank q's rows of the table
+// are complete once done[q] >= the window's epoch.  `hdr` is the OWN window's header.
+struct FwdWait {
+    const uint32_t* hdr;  // null: the table is complete (single GPU, NCCL form)
+    int world, rank;
+    int rows_per_rank;    // table rows [q*rows_per_rank, (q+1)*rows_per_rank) come from rank q
+    uint64_t timeout_ns;
+};
+
+// `split` (nullable): per CSR row, the position in idx of the first stored entry whose column is
+// >= rank*rows_per_rank.  A record then walks [split, end) first and [begin, split) second, i.e.
+// the source blocks in the order rank, rank+1, ..., world-1, 0, ..., rank-1 -- the order in which
+// mk_peer_bank_push makes them arrive.  The summation order of a row is fixed either way.
+template <int K, int U, bool WAIT>
 __global__ void __launch_bounds__(32)
 spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
                          const float* __restrict__ val, const float* __restrict__ bk_data,
                          const uint16_t* __restrict__ bk_slot, float* __restrict__ out,
-                         float* __restrict__ partial, int d, int rows) {
+                         float* __restrict__ partial, int d, int rows, const int* __restrict__ split,
+                         const FwdWait fw) {
     constexpr int CAP = K / 8;
     extern __shared__ __align__(16) float acc[];  // 32 * rows
     const int lane = lane_id();
@@ -76,51 +145,86 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
     const int t = lane & 7;
     const mk_part rec = parts[blockIdx.x];
 
+    // which source blocks have arrived (bit q); refreshed only while something is missing
+    unsigned have = 0xffffffffu;
+    uint32_t epoch = 0;
+    if (WAIT) {
+        epoch = fw.hdr[kHdrEpoch];
+        const bool there = lane >= fw.world ||
+                           static_cast<int32_t>(ld_acquire_sys(fw.hdr + kHdrDone + lane) - epoch) >= 0;
+        have = __ballot_sync(kFull, there);
+    }
+
     for (int c = lane * 4; c < 32 * rows; c += 128)
         *reinterpret_cast<float4*>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
 
     float* __restrict__ my = acc + 8 * g;
-    const unsigned gmask = 0xffu << (8 * g);  // the lanes that share this group's banks
-    const int end = rec.loc + rec.len;
-    for (int base = rec.loc; base < end; base += 32) {
-        const int n_here = min(32, end - base);
-        int my_nz = 0;
-        float my_v = 0.f;
-        if (lane < n_here) {
-            my_nz = ld_stream_i1(idx + base + lane);
-            my_v = ld_stream_f1(val + base + lane);
-        }
-        for (int i = 0; i < n_here; i += 4 * U) {
-            float dv[U][CAP];
-            int sl[U][CAP];
-            float vv[U];
-            bool ok[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int e = i + u * 4 + g;
-                const int nz = __shfl_sync(kFull, my_nz, e & 31);
-                vv[u] = __shfl_sync(kFull, my_v, e & 31);
-                ok[u] = e < n_here;
-                if (ok[u]) {
-                    const int64_t off = static_cast<int64_t>(nz) * K + CAP * t;
-                    BankedLoad<CAP>::data(bk_data + off, dv[u]);
-                    BankedLoad<CAP>::slots(bk_slot + off, sl[u]);
+    [[maybe_unused]] const unsigned gmask = 0xffu << (8 * g);  // the lanes that share this group's banks
+    const int lo = rec.loc, hi = rec.loc + rec.len;
+    int sp = lo;
+    if (split != nullptr) sp = min(max(__ldg(split + rec.row), lo), hi);
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const int b0 = pass == 0 ? sp : lo;
+        const int end = pass == 0 ? hi : sp;
+        for (int base = b0; base < end; base += 32) {
+            const int n_here = min(32, end - base);
+            int my_nz = 0;
+            float my_v = 0.f;
+            if (lane < n_here) {
+                my_nz = ld_stream_i1(idx + base + lane);
+                my_v = ld_stream_f1(val + base + lane);
+            }
+            if (WAIT && have != 0xffffffffu) {  // uniform; false for every CTA once all rows are in
+                int blk = __float2int_rd(__fdividef(static_cast<float>(my_nz), static_cast<float>(fw.rows_per_rank)));
+                blk += (my_nz >= (blk + 1) * fw.rows_per_rank) ? 1 : 0;
+                blk -= (my_nz < blk * fw.rows_per_rank) ? 1 : 0;
+                const unsigned need = __reduce_or_sync(kFull, lane < n_here ? (1u << blk) : 0u);
+                const unsigned missing = need & ~have;
+                if (missing) {
+                    if ((missing >> lane) & 1u)
+                        wait_flag(fw.hdr + kHdrDone + lane, epoch,
+                                  const_cast<uint32_t*>(fw.hdr) + kHdrError, fw.timeout_ns);
+                    __syncwarp();
+                    have |= missing;
                 }
             }
+            for (int i = 0; i < n_here; i += 4 * U) {
+                float dv[U][CAP];
+                int sl[U][CAP];
+                float vv[U];
+                bool ok[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (ok[u]) {  // uniform over the 8 lanes of a group
-#pragma unroll
-                    for (int q = 0; q < CAP; ++q)
-                        if (dv[u][q] != 0.0f) my[sl[u][q]] += vv[u] * dv[u][q];
-                    accum_fence_group(gmask);
+                for (int u = 0; u < U; ++u) {
+                    const int e = i + u * 4 + g;
+                    const int nz = __shfl_sync(kFull, my_nz, e & 31);
+                    vv[u] = __shfl_sync(kFull, my_v, e & 31);
+                    ok[u] = e < n_here;
+                    if (ok[u]) {
+                        const int64_t off = static_cast<int64_t>(nz) * K + CAP * t;
+                        BankedLoad<CAP, WAIT>::data(bk_data + off, dv[u]);
+                        BankedLoad<CAP, WAIT>::slots(bk_slot + off, sl[u]);
+                    }
                 }
-                accum_fence_warp();
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (ok[u]) {  // uniform over the 8 lanes of a group
+#pragma unroll
+                        for (int q = 0; q < CAP; ++q)
+                            if (dv[u][q] != 0.0f) my[sl[u][q]] += vv[u] * dv[u][q];
+                        accum_fence_group(gmask);
+                    }
+                    accum_fence_warp();
+                }
             }
         }
     }
     __syncwarp();
+    // the kernel's completion must mean "the whole table has arrived" (the backward reads the
+    // gathered column ids after it): one CTA waits for every sender
+    if (WAIT && blockIdx.x == 0 && lane < fw.world)
+        wait_flag(fw.hdr + kHdrDone + lane, epoch, const_cast<uint32_t*>(fw.hdr) + kHdrError, fw.timeout_ns);
 
     // ---- fold the 4 groups and the 2 copies.  Lane (s, b) sums, for row 4i+s, the cells of bank
     //      b of every group, visiting the groups in the order (j+s)&3 so that the four rows read
@@ -247,19 +351,29 @@ sspmm_bwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restrict
 template <int K>
 static int launch_fwd_banked(const mk_part* parts, int64_t num_parts, const int* idx,
                              const float* val, const float* bk_data, const uint16_t* bk_slot,
-                             float* out, float* partial, int d, int rows, cudaStream_t st) {
+                             float* out, float* partial, int d, int rows, const int* split,
+                             const FwdWait& fw, cudaStream_t st) {
 #ifdef MK_FWD_U
     constexpr int U = MK_FWD_U;
 #else
     constexpr int U = K >= 64 ? 2 : (K == 32 ? 4 : 8);
 #endif
     const size_t smem = static_cast<size_t>(32) * rows * 4;
-    auto kern = spgemm_fwd_banked_kernel<K, U>;
-    if (smem > 48 * 1024)
-        MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-    kern<<<static_cast<unsigned>(num_parts), 32, smem, st>>>(parts, idx, val, bk_data, bk_slot, out,
-                                                             partial, d, rows);
+    if (fw.hdr != nullptr) {
+        auto kern = spgemm_fwd_banked_kernel<K, U, true>;
+        if (smem > 48 * 1024)
+            MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem)));
+        kern<<<static_cast<unsigned>(num_parts), 32, smem, st>>>(parts, idx, val, bk_data, bk_slot, out,
+                                                                 partial, d, rows, split, fw);
+    } else {
+        auto kern = spgemm_fwd_banked_kernel<K, U, false>;
+        if (smem > 48 * 1024)
+            MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem)));
+        kern<<<static_cast<unsigned>(num_parts), 32, smem, st>>>(parts, idx, val, bk_data, bk_slot, out,
+                                                                 partial, d, rows, split, fw);
+    }
     MK_LAUNCH_CHECK("spgemm_fwd_banked_kernel");
     return MK_OK;
 }
@@ -287,14 +401,25 @@ int launch_fold(const mk_part* parts, int64_t num_parts, const float* partial, f
 
 extern "C" int mk_banked_supported(int k, int d);
 extern "C" int mk_banked_rows(int d);
+extern "C" int mk_peer_wait_all(void* window, int world, int timeout_ms, void* stream);
 
-extern "C" int mk_spgemm_fwd_banked(const mk_part* parts, int64_t num_parts, int64_t num_slots,
-                                    const int32_t* idx, const float* val, const float* bk_data,
-                                    const uint16_t* bk_slot, float* out, float* partial,
-                                    int64_t n_rows, int k, int d, void* stream) {
+extern "C" int mk_spgemm_fwd_banked_ex(const mk_part* parts, int64_t num_parts, int64_t num_slots,
+                                       const mk_part* exec_parts, const int32_t* idx, const float* val,
+                                       const float* bk_data, const uint16_t* bk_slot, float* out,
+                                       float* partial, int64_t n_rows, int k, int d,
+                                       const int32_t* split, const void* wait_window, int world,
+                                       int rank, int64_t rows_per_rank, int timeout_ms, void* stream) {
     if (n_rows < 0 || num_parts < 0 || num_slots < 0 || d < 1 || k < 1 || k > d) return MK_EINVAL;
     if (!mk_banked_supported(k, d)) return MK_EUNSUPPORTED;
-    if (n_rows == 0 || num_parts == 0) return MK_OK;
+    if (wait_window != nullptr &&
+        (world < 1 || world > mk::kMaxPeers || rank < 0 || rank >= world || rows_per_rank < 1 ||
+         rows_per_rank > 0x7fffffffLL))
+        return MK_EINVAL;
+    if (n_rows == 0 || num_parts == 0) {
+        // nothing to compute, but the collective's contract stands: return once the table is complete
+        if (wait_window != nullptr) return mk_peer_wait_all(const_cast<void*>(wait_window), world, timeout_ms, stream);
+        return MK_OK;
+    }
     if (!parts || !out || !bk_data || !bk_slot) return MK_EINVAL;
     if (num_slots > 0 && !partial) return MK_EINVAL;
     if (num_parts > 0x7fffffffLL) return MK_EUNSUPPORTED;
@@ -302,17 +427,32 @@ extern "C" int mk_spgemm_fwd_banked(const mk_part* parts, int64_t num_parts, int
         reinterpret_cast<uintptr_t>(bk_slot) % 16 || (partial && reinterpret_cast<uintptr_t>(partial) % 16))
         return MK_EINVAL;
     cudaStream_t st = mk::as_stream(stream);
+    mk::FwdWait fw{};
+    fw.hdr = static_cast<const uint32_t*>(wait_window);
+    fw.world = world;
+    fw.rank = rank;
+    fw.rows_per_rank = static_cast<int>(rows_per_rank);
+    fw.timeout_ns = static_cast<uint64_t>(timeout_ms > 0 ? timeout_ms : 30000) * 1000000ull;
+    const mk_part* ex = exec_parts ? exec_parts : parts;
     const int rows = mk_banked_rows(d);
     int rc;
     switch (k) {
-        case 8: rc = mk::launch_fwd_banked<8>(parts, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, st); break;
-        case 16: rc = mk::launch_fwd_banked<16>(parts, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, st); break;
-        case 32: rc = mk::launch_fwd_banked<32>(parts, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, st); break;
-        default: rc = mk::launch_fwd_banked<64>(parts, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, st); break;
+        case 8: rc = mk::launch_fwd_banked<8>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, st); break;
+        case 16: rc = mk::launch_fwd_banked<16>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, st); break;
+        case 32: rc = mk::launch_fwd_banked<32>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, st); break;
+        default: rc = mk::launch_fwd_banked<64>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, st); break;
     }
     if (rc != MK_OK) return rc;
     if (num_slots > 0) return mk::launch_fold(parts, num_parts, partial, out, d, st);
     return MK_OK;
+}
+
+extern "C" int mk_spgemm_fwd_banked(const mk_part* parts, int64_t num_parts, int64_t num_slots,
+                                    const int32_t* idx, const float* val, const float* bk_data,
+                                    const uint16_t* bk_slot, float* out, float* partial,
+                                    int64_t n_rows, int k, int d, void* stream) {
+    return mk_spgemm_fwd_banked_ex(parts, num_parts, num_slots, nullptr, idx, val, bk_data, bk_slot, out,
+                                   partial, n_rows, k, d, nullptr, nullptr, 1, 0, 1, 0, stream);
 }
 
 extern "C" int mk_sspmm_bwd_banked(const mk_part* parts, int64_t num_parts, const int32_t* idx,

@@ -77,15 +77,19 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 // ---- ordering of the forward's shared-memory accumulation --------------------------------------
 // The forward kernels add into shared-memory cells with plain LDS / FFMA / STS.  The lanes that work
 // on ONE neighbour hit distinct cells (columns of a CBSR row are distinct), but the same lanes
-// handle another neighbour in the next step and may then hit a cell a DIFFERENT lane of the group
-// updated before.  That read-after-write between lanes needs an ordering the programming model only
-// gives through __syncwarp: `accum_fence(mask)` after every neighbour, over the lanes that share an
-// accumulator (lane groups with private accumulators never touch each other's cells).
-//   MK_SYNC_MODE 1 (default)  group-scoped __syncwarp(mask) per neighbour
-//   MK_SYNC_MODE 2            full-warp __syncwarp() per step (callers place it outside divergent code)
-//   MK_SYNC_MODE 0            no fence (round-1 behaviour; measured for the record only)
+// handle another neighbour in the next step and may then hit a cell a DIFFERENT lane updated
+// before.  That read-after-write between lanes needs an ordering the programming model only gives
+// through __syncwarp, so every neighbour step ends with one.  Measured on a B200 (Reddit shape,
+// profiles/r2/sync_modes.log; k = 8 / 16 / 32 / 64 forward ms):
+//   MK_SYNC_MODE 0  no fence (round 1)                          1.600 / 2.455 / 2.896 / 6.321
+//   MK_SYNC_MODE 1  __syncwarp(group mask) inside the branch    1.995 / 3.212 / 3.482 / 6.053
+//   MK_SYNC_MODE 2  __syncwarp() by all 32 lanes, placed after  1.604 / 2.456 / 2.916 / 6.328
+//                   the group-uniform `if (ok)` has reconverged  (the default)
+// Mode 2 compiles to no WARPSYNC at all: ptxas proves the warp converged at that point (BSYNC),
+// where in-order issue already gives the ordering -- the fence is free and the guarantee is in the
+// source instead of in an assumption.  Mode 1 needs WARPSYNC + the collective machinery per group.
 #ifndef MK_SYNC_MODE
-#define MK_SYNC_MODE 1
+#define MK_SYNC_MODE 2
 #endif
 __device__ __forceinline__ void accum_fence_group(unsigned mask) {
 #if MK_SYNC_MODE == 1

@@ -6,75 +6,92 @@
 //   forward   every rank needs the whole CBSR table:  all-gather of N*k*(4+w) bytes;
 //   backward  every rank holds a full-height partial CBSR gradient:  reduce-scatter of N*k*4.
 //
-// torch.distributed / NCCL do both (dist.py) and stay the default.  This file is the same pair as
-// this library's own kernels over peer-mapped memory (protocol: peer.cuh):
+// torch.distributed / NCCL do both (dist.py, the fallback).  This file is the same pair over
+// peer-mapped memory (protocol: peer.cuh):
 //
-//   mk_peer_allgather       each rank STORES its rows into every rank's table (16-byte vector
-//                           stores over NVLink, destinations visited in rotated order so that at
-//                           any moment every rank receives from one sender);
-//   mk_peer_bank_push       (bank.cu) the banking kernel writes its output rows straight into
-//                           every rank's table -- compute and all-gather in one kernel;
-//   mk_peer_reduce_scatter  each rank LOADS its block of rows from every rank's partial buffer
-//                           and folds them in rank order 0..P-1 (fixed order: bit-reproducible,
-//                           which NCCL's ring/tree order is not obliged to be).
+//   mk_peer_publish + mk_peer_push   the all-gather, OVERLAPPED with the kernel that consumes it:
+//       the rank's rows are produced straight into its own window (mk_cbsr_bank / mk_topk_cbsr write
+//       there), mk_peer_publish opens collective e, and mk_peer_push enqueues -- on a side stream --
+//       one copy-engine transfer per peer and table (rank-1, rank-2, ... so that every rank receives
+//       from one sender at a time), each peer's transfers followed by a 4-byte copy of e into
+//       done[rank] of that peer's header.  No SM is involved and nothing waits: the forward SpGEMM
+//       (banked.cu, WAIT form) starts at once on the local rows and checks done[q] before it touches
+//       rank q's rows, walking every CSR row in arrival order.  Overwriting a table buffer needs the
+//       peers to be done with its previous contents: mk_peer_release (after the consumer) and
+//       mk_peer_begin_push (before the producer) are that handshake, two one-block kernels on the
+//       main stream; with the two table buffers peer.py alternates, the wait is for a collective two
+//       steps back and never blocks in practice.
+//   mk_peer_wait_all                 for consumers that cannot wait per block (un-banked kernels).
+//   mk_peer_reduce_scatter           each rank LOADS its block of rows from every rank's partial
+//       buffer and folds them in rank order 0..P-1 (fixed order: bit-reproducible, which NCCL's
+//       ring/tree order is not obliged to be).  Grid sized to be co-resident.
 //
 // Why the SpGEMM / SSpMM themselves do not reach into peer memory: a CBSR row is re-read ~deg/P
 // times by a rank, so gathering rows over NVLink inside the kernel would move E/P*k*5 bytes per
 // rank against N*k*5 once for the all-gather (6-60x more on the BASELINE shapes); the same holds
-// for pushing reductions to the owner.  The exchange sits in front of / behind the kernels.
+// for pushing reductions to the owner.  The exchange sits next to the kernels, not inside them.
 #include <string.h>
 
 #include "peer.cuh"
 
 namespace mk {
 
-constexpr int kMaxSegs = 4;
+constexpr int kHdrSig = 3;      // the value mk_peer_push copies into the peers' done[] words
+constexpr int kHdrLastUse = 4;  // [2]: collective that last filled table buffer 0 / 1 of this window
 
-struct GatherSegs {
-    const uint4* src[kMaxSegs];  // this rank's rows
-    int64_t n16[kMaxSegs];       // 16-byte units per rank
-    int64_t off[kMaxSegs];       // byte offset of rank 0's block inside a window
-    int nseg;
-};
-
-__global__ void __launch_bounds__(256)
-peer_allgather_kernel(const PeerSet ps, const int world, const int rank, const GatherSegs segs,
-                      const uint64_t timeout_ns) {
-    const uint32_t e = peer_begin(ps, world, rank);
-    const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int s = 0; s < world; ++s) {
-        const int q = (rank + s) % world;
-        peer_wait_ready(ps, rank, q, e, timeout_ns);
-        for (int g = 0; g < segs.nseg; ++g) {
-            const uint4* __restrict__ src = segs.src[g];
-            const int64_t n16 = segs.n16[g];
-            uint4* dst = reinterpret_cast<uint4*>(ps.win[q] + segs.off[g]) + rank * n16;
-            if (q == rank && dst == src) continue;  // produced in place
-            int64_t i = tid;
-            for (; i + 3 * nthr < n16; i += 4 * nthr) {  // four loads in flight per thread
-                const uint4 a = src[i], b = src[i + nthr], c = src[i + 2 * nthr], d = src[i + 3 * nthr];
-                st_peer_16(dst + i, a);
-                st_peer_16(dst + i + nthr, b);
-                st_peer_16(dst + i + 2 * nthr, c);
-                st_peer_16(dst + i + 3 * nthr, d);
-            }
-            for (; i < n16; i += nthr) st_peer_16(dst + i, src[i]);
-        }
-    }
-    peer_end(ps, world, rank, e, timeout_ns);
+// Before a rank overwrites its rows of table buffer `buf` (and lets the copy engines overwrite the
+// peers'): every peer must be done READING the collective that filled that buffer last.  Peers say
+// so with mk_peer_release (ready[q] = number of the last collective whose table q has finished
+// with).  One block, on the rank's main stream, where no consumer of this window is running any
+// more -- it never competes with spinning CTAs for an SM.  With two buffers the wait is for a
+// collective two steps back and is over before it starts.
+__global__ void peer_wait_ready_kernel(uint32_t* hdr, int world, int rank, int buf, uint64_t timeout_ns) {
+    const uint32_t need = hdr[kHdrLastUse + buf];
+    if (need != 0u && threadIdx.x < world && static_cast<int>(threadIdx.x) != rank)
+        wait_flag(hdr + kHdrReady + threadIdx.x, need, hdr + kHdrError, timeout_ns);
 }
+
+// Opens collective e = epoch + 1 on the calling rank's window: the rank's own rows are complete
+// (stream order), so done[rank] = e; `sig` = e is what the copy engines hand to the peers.
+__global__ void peer_publish_kernel(uint32_t* hdr, int rank, int buf) {
+    const uint32_t e = hdr[kHdrEpoch] + 1u;
+    hdr[kHdrSig] = e;
+    hdr[kHdrLastUse + buf] = e;
+    st_release_sys(hdr + kHdrDone + rank, e);
+    hdr[kHdrEpoch] = e;
+}
+
+// "I have finished with the table of my current collective": ready[rank] = epoch in every peer's header.
+__global__ void peer_release_kernel(const PeerSet ps, int world, int rank) {
+    const uint32_t e = peer_hdr(ps, rank)[kHdrEpoch];
+    if (threadIdx.x < world && static_cast<int>(threadIdx.x) != rank)
+        st_release_sys(peer_hdr(ps, threadIdx.x) + kHdrReady + rank, e);
+}
+
+// One block: returns when every sender's rows of the current collective have arrived.
+__global__ void peer_wait_all_kernel(uint32_t* hdr, int world, uint64_t timeout_ns) {
+    const uint32_t e = hdr[kHdrEpoch];
+    if (threadIdx.x < world) wait_flag(hdr + kHdrDone + threadIdx.x, e, hdr + kHdrError, timeout_ns);
+}
+
+struct OutSet {
+    float4* out[kMaxPeers];
+};
 
 // out[i] = sum over q = 0..world-1 of window_q[off + rank*n4 + i]   (float4 units)
 template <int WORLD>
 __global__ void __launch_bounds__(256)
-peer_reduce_scatter_kernel(const PeerSet ps, const int world_rt, const int rank, const int64_t off,
-                           const int64_t n4, float4* __restrict__ out, const uint64_t timeout_ns) {
+peer_reduce_scatter_kernel(const PeerSet ps, const int world_rt, const int rank_arg, const int virt,
+                           const int64_t off, const int64_t n4, const OutSet outs,
+                           const uint64_t timeout_ns) {
     const int world = WORLD > 0 ? WORLD : world_rt;
-    const uint32_t e = peer_begin(ps, world, rank);
-    peer_wait_all_ready(ps, world, rank, e, timeout_ns);
-    const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const PeerCtx c = peer_ctx(rank_arg, virt != 0);
+    const int rank = c.rank;
+    float4* __restrict__ out = outs.out[virt ? rank : 0];
+    const uint32_t e = peer_begin(ps, world, c);
+    peer_wait_all_ready(ps, world, c, e, timeout_ns);
+    const int64_t tid = static_cast<int64_t>(c.bid) * blockDim.x + threadIdx.x;
+    const int64_t nthr = static_cast<int64_t>(c.nblk) * blockDim.x;
     for (int64_t i = tid; i < n4; i += nthr) {
         float4 v[WORLD > 0 ? WORLD : 1];
         if (WORLD > 0) {
@@ -96,7 +113,7 @@ peer_reduce_scatter_kernel(const PeerSet ps, const int world_rt, const int rank,
             out[i] = acc;
         }
     }
-    peer_end(ps, world, rank, e, timeout_ns);
+    peer_end(ps, world, c, e, timeout_ns);
 }
 
 static int fill_peers(PeerSet& ps, void* const* h_windows, int world, int rank) {
@@ -109,16 +126,46 @@ static int fill_peers(PeerSet& ps, void* const* h_windows, int world, int rank) 
     return MK_OK;
 }
 
-static unsigned pick_grid(int grid, int64_t units, int per_sm) {
-    if (grid > 0) return static_cast<unsigned>(grid);
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess)
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int64_t want = (units + 255) / 256;
-    const int64_t cap = static_cast<int64_t>(sms) * per_sm;
+template <int WORLD>
+static int launch_rs(const PeerSet& ps, int world, int rank, int virt, int64_t off, int64_t n4,
+                     const OutSet& outs, int grid, uint64_t tmo, cudaStream_t st) {
+    auto kern = peer_reduce_scatter_kernel<WORLD>;
+    // every block may wait for a flag that block 0 of a peer's grid writes: the grid must be resident
+    // at once (all virtual ranks together in the single-launch emulation)
+    int cap = coresident_blocks(kern, 256, 0);
+    if (virt) cap /= world;
+    if (cap < 1) return MK_EUNSUPPORTED;
+    int64_t want = grid > 0 ? grid : (n4 + 255) / 256;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
-    return static_cast<unsigned>(want);
+    const dim3 g(static_cast<unsigned>(want), virt ? static_cast<unsigned>(world) : 1u);
+    kern<<<g, 256, 0, st>>>(ps, world, rank, virt, off, n4, outs, tmo);
+    MK_LAUNCH_CHECK("peer_reduce_scatter_kernel");
+    return MK_OK;
+}
+
+static int reduce_scatter_any(void* const* h_windows, int world, int rank, int virt, int64_t offset,
+                              int64_t block_bytes, float* const* h_outs, int grid, int timeout_ms,
+                              void* stream) {
+    PeerSet ps;
+    const int rc = fill_peers(ps, h_windows, world, rank);
+    if (rc != MK_OK) return rc;
+    if (offset < MK_PEER_HEADER_BYTES || (offset & 15) || block_bytes < 0 || (block_bytes & 15)) return MK_EINVAL;
+    OutSet outs;
+    memset(&outs, 0, sizeof(outs));
+    for (int q = 0; q < (virt ? world : 1); ++q) {
+        if (block_bytes > 0 && (!h_outs || !h_outs[q] || (reinterpret_cast<uintptr_t>(h_outs[q]) & 15))) return MK_EINVAL;
+        outs.out[q] = reinterpret_cast<float4*>(h_outs ? h_outs[q] : nullptr);
+    }
+    const int64_t n4 = block_bytes / 16;
+    const uint64_t tmo = static_cast<uint64_t>(timeout_ms > 0 ? timeout_ms : 30000) * 1000000ull;
+    cudaStream_t st = as_stream(stream);
+    switch (world) {
+        case 2: return launch_rs<2>(ps, world, rank, virt, offset, n4, outs, grid, tmo, st);
+        case 4: return launch_rs<4>(ps, world, rank, virt, offset, n4, outs, grid, tmo, st);
+        case 8: return launch_rs<8>(ps, world, rank, virt, offset, n4, outs, grid, tmo, st);
+        default: return launch_rs<0>(ps, world, rank, virt, offset, n4, outs, grid, tmo, st);
+    }
 }
 
 }  // namespace mk
@@ -182,52 +229,75 @@ extern "C" int mk_peer_epoch(const void* window, uint32_t* h_epoch, uint32_t* h_
 }
 
 // ---- collectives ------------------------------------------------------------------------------
-extern "C" int mk_peer_allgather(void* const* h_windows, int world, int rank, int n_seg,
-                                 const void* const* h_src, const int64_t* h_bytes,
-                                 const int64_t* h_offsets, int grid, int timeout_ms, void* stream) {
+extern "C" int mk_peer_begin_push(void* window, int world, int rank, int buffer, int timeout_ms,
+                                  void* stream) {
+    if (!window || world < 1 || world > mk::kMaxPeers || rank < 0 || rank >= world) return MK_EINVAL;
+    if (buffer < 0 || buffer > 1) return MK_EINVAL;
+    const uint64_t tmo = static_cast<uint64_t>(timeout_ms > 0 ? timeout_ms : 30000) * 1000000ull;
+    mk::peer_wait_ready_kernel<<<1, 32, 0, mk::as_stream(stream)>>>(static_cast<uint32_t*>(window), world,
+                                                                    rank, buffer, tmo);
+    MK_LAUNCH_CHECK("peer_wait_ready_kernel");
+    return MK_OK;
+}
+
+extern "C" int mk_peer_publish(void* window, int rank, int buffer, void* stream) {
+    if (!window || rank < 0 || rank >= mk::kMaxPeers || buffer < 0 || buffer > 1) return MK_EINVAL;
+    mk::peer_publish_kernel<<<1, 1, 0, mk::as_stream(stream)>>>(static_cast<uint32_t*>(window), rank, buffer);
+    MK_LAUNCH_CHECK("peer_publish_kernel");
+    return MK_OK;
+}
+
+extern "C" int mk_peer_release(void* const* h_windows, int world, int rank, void* stream) {
     mk::PeerSet ps;
     const int rc = mk::fill_peers(ps, h_windows, world, rank);
     if (rc != MK_OK) return rc;
-    if (n_seg < 1 || n_seg > mk::kMaxSegs || !h_src || !h_bytes || !h_offsets) return MK_EINVAL;
-    mk::GatherSegs segs;
-    memset(&segs, 0, sizeof(segs));
-    segs.nseg = n_seg;
-    int64_t most = 0;
-    for (int g = 0; g < n_seg; ++g) {
-        if (h_bytes[g] < 0 || (h_bytes[g] & 15) || h_offsets[g] < MK_PEER_HEADER_BYTES || (h_offsets[g] & 15))
-            return MK_EINVAL;
-        if (h_bytes[g] > 0 && (!h_src[g] || (reinterpret_cast<uintptr_t>(h_src[g]) & 15))) return MK_EINVAL;
-        segs.src[g] = static_cast<const uint4*>(h_src[g]);
-        segs.n16[g] = h_bytes[g] / 16;
-        segs.off[g] = h_offsets[g];
-        if (segs.n16[g] > most) most = segs.n16[g];
+    mk::peer_release_kernel<<<1, 32, 0, mk::as_stream(stream)>>>(ps, world, rank);
+    MK_LAUNCH_CHECK("peer_release_kernel");
+    return MK_OK;
+}
+
+extern "C" int mk_peer_push(void* const* h_windows, int world, int rank, int n_seg,
+                            const int64_t* h_offsets, const int64_t* h_bytes, void* stream) {
+    if (world < 1 || world > mk::kMaxPeers || rank < 0 || rank >= world || !h_windows) return MK_EINVAL;
+    if (n_seg < 1 || n_seg > 8 || !h_offsets || !h_bytes) return MK_EINVAL;
+    for (int q = 0; q < world; ++q)
+        if (!h_windows[q]) return MK_EINVAL;
+    for (int g = 0; g < n_seg; ++g)
+        if (h_bytes[g] < 0 || h_offsets[g] < MK_PEER_HEADER_BYTES) return MK_EINVAL;
+    cudaStream_t st = mk::as_stream(stream);
+    unsigned char* mine = static_cast<unsigned char*>(h_windows[rank]);
+    for (int s = 1; s < world; ++s) {
+        unsigned char* dst = static_cast<unsigned char*>(h_windows[(rank - s + world) % world]);
+        for (int g = 0; g < n_seg; ++g) {
+            if (h_bytes[g] == 0) continue;
+            const int64_t o = h_offsets[g] + rank * h_bytes[g];
+            MK_CUDA_TRY(cudaMemcpyAsync(dst + o, mine + o, static_cast<size_t>(h_bytes[g]),
+                                        cudaMemcpyDeviceToDevice, st));
+        }
+        // same stream, same destination: lands behind the rows it announces
+        MK_CUDA_TRY(cudaMemcpyAsync(dst + 4 * (mk::kHdrDone + rank), mine + 4 * mk::kHdrSig, 4,
+                                    cudaMemcpyDeviceToDevice, st));
     }
+    return MK_OK;
+}
+
+extern "C" int mk_peer_wait_all(void* window, int world, int timeout_ms, void* stream) {
+    if (!window || world < 1 || world > mk::kMaxPeers) return MK_EINVAL;
     const uint64_t tmo = static_cast<uint64_t>(timeout_ms > 0 ? timeout_ms : 30000) * 1000000ull;
-    const unsigned nb = mk::pick_grid(grid, (most + 3) / 4, 4);
-    mk::peer_allgather_kernel<<<nb, 256, 0, mk::as_stream(stream)>>>(ps, world, rank, segs, tmo);
-    MK_LAUNCH_CHECK("peer_allgather_kernel");
+    mk::peer_wait_all_kernel<<<1, 32, 0, mk::as_stream(stream)>>>(static_cast<uint32_t*>(window), world, tmo);
+    MK_LAUNCH_CHECK("peer_wait_all_kernel");
     return MK_OK;
 }
 
 extern "C" int mk_peer_reduce_scatter(void* const* h_windows, int world, int rank, int64_t offset,
                                       int64_t block_bytes, float* out, int grid, int timeout_ms,
                                       void* stream) {
-    mk::PeerSet ps;
-    const int rc = mk::fill_peers(ps, h_windows, world, rank);
-    if (rc != MK_OK) return rc;
-    if (offset < MK_PEER_HEADER_BYTES || (offset & 15) || block_bytes < 0 || (block_bytes & 15)) return MK_EINVAL;
-    if (block_bytes > 0 && (!out || (reinterpret_cast<uintptr_t>(out) & 15))) return MK_EINVAL;
-    const int64_t n4 = block_bytes / 16;
-    const uint64_t tmo = static_cast<uint64_t>(timeout_ms > 0 ? timeout_ms : 30000) * 1000000ull;
-    const unsigned nb = mk::pick_grid(grid, n4, 8);
-    cudaStream_t st = mk::as_stream(stream);
-    float4* o = reinterpret_cast<float4*>(out);
-    switch (world) {
-        case 2: mk::peer_reduce_scatter_kernel<2><<<nb, 256, 0, st>>>(ps, world, rank, offset, n4, o, tmo); break;
-        case 4: mk::peer_reduce_scatter_kernel<4><<<nb, 256, 0, st>>>(ps, world, rank, offset, n4, o, tmo); break;
-        case 8: mk::peer_reduce_scatter_kernel<8><<<nb, 256, 0, st>>>(ps, world, rank, offset, n4, o, tmo); break;
-        default: mk::peer_reduce_scatter_kernel<0><<<nb, 256, 0, st>>>(ps, world, rank, offset, n4, o, tmo); break;
-    }
-    MK_LAUNCH_CHECK("peer_reduce_scatter_kernel");
-    return MK_OK;
+    float* outs[1] = {out};
+    return mk::reduce_scatter_any(h_windows, world, rank, 0, offset, block_bytes, outs, grid, timeout_ms, stream);
+}
+
+extern "C" int mk_peer_reduce_scatter_virtual(void* const* h_windows, int world, int64_t offset,
+                                              int64_t block_bytes, float* const* h_outs, int grid,
+                                              int timeout_ms, void* stream) {
+    return mk::reduce_scatter_any(h_windows, world, 0, 1, offset, block_bytes, h_outs, grid, timeout_ms, stream);
 }

@@ -150,9 +150,9 @@ def allreduce_grads(params: Iterable[torch.nn.Parameter], group=None) -> None:
 # the sharded hot path as an autograd Function
 # ---------------------------------------------------------------------------------------
 def _peer_path(group, *row_bytes) -> bool:
-    """Peer-memory kernels (peer.py) instead of NCCL calls: not switched off (MAXK_PEER_EXCHANGE=0),
-    NCCL group on one box, and every per-rank segment a multiple of 16 bytes (same answer on every
-    rank: same shapes)."""
+    """Peer-memory exchange (peer.py) instead of NCCL calls: not switched off (MAXK_PEER_EXCHANGE=0),
+    NCCL group on one box, and every listed per-rank segment a multiple of 16 bytes (same answer on
+    every rank: same shapes)."""
     from . import peer
     return peer.enabled() and peer.available(group) and all(b % 16 == 0 for b in row_bytes)
 
@@ -161,39 +161,62 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
                     keep_index: bool = True):
     """Exchange + local forward SpGEMM of one rank.  Returns (out [num_rows, D], gathered sorted
     column ids [P*R, k] for the backward).  Where the banked kernels apply, the LOCAL rows are
-    banked first and the banked values + cell offsets are gathered next to the sorted column ids
+    banked first and the banked values + cell offsets travel next to the sorted column ids
     (7 bytes per entry instead of 5), so that no rank re-banks rows it does not own.
 
-    On an NCCL group the exchange runs as this library's own kernels over peer-mapped windows
-    (default; `MAXK_PEER_EXCHANGE=0` keeps the NCCL calls below): the banking kernel stores its rows
-    into every rank's table (`peer.bank_push`), the un-banked table goes through `peer.allgather`.  The table window is shared by all layers of a
-    shape, so the column ids are copied out of it when the backward will need them."""
+    On an NCCL group the exchange runs over peer-mapped windows (default; `MAXK_PEER_EXCHANGE=0`
+    keeps the NCCL calls below) and OVERLAPS the SpGEMM: the rank's rows are produced straight
+    into its own window, the copy engines carry them to the peers on a side stream
+    (`peer.publish_and_push`), and the SpGEMM starts at once -- it walks every CSR row in the order
+    the source blocks arrive (own rows, rank+1, rank+2, ...) and checks the sender's flag before it
+    touches a block.  The window holds two table buffers (alternating) and is shared by all layers
+    of a shape, so the column ids are copied out of it when a backward will need them."""
     from . import maxk_kernels, peer
     r, k = sp_data.shape
     ib = sp_index.element_size()
     world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
     part = maxk_kernels.partition(ptr, num_rows)
     banked = maxk_kernels.use_banked(part.num_parts, idx.numel(), k, dim_origin)
-    if _peer_path(group, r * k * 4, r * k * 2, r * k * ib):
+    # every record walks the source blocks own, rank+1, ..., rank-1: one fixed summation order for the
+    # peer form and the NCCL form (their forwards are bit-equal)
+    split = maxk_kernels.block_split(ptr, idx, num_rows, world, rank, r) if (banked and sp_data.is_cuda) else None
+    if _peer_path(group, r * k * 4):
         rows = world * r
-        sizes = [rows * k * 4, rows * k * 2, rows * k * ib] if banked else [rows * k * 4, rows * k * ib]
-        offs, total = peer.layout(sizes)
+        per_rank = [r * k * 4, r * k * 2, r * k * ib] if banked else [r * k * 4, r * k * ib]
+        offs, total = peer.layout([world * b for b in per_rank] * 2)        # two table buffers
         win = peer.window("table_banked" if banked else "table_plain", total, group)
         if win is not None:
+            buf = win.next_buffer()
+            o = offs[len(per_rank) * buf: len(per_rank) * (buf + 1)]
+            mine = slice(rank * r, (rank + 1) * r)
+            peer.begin_push(win, buf)
+            full_data = win.view(o[0], (rows, k), torch.float32)
+            full_index = win.view(o[-1], (rows, k), sp_index.dtype)
+            full_index[mine].copy_(sp_index)
             if banked:
-                full_data, full_slot, full_index = peer.bank_push(win, sp_data, sp_index, dim_origin, offs)
-                out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, full_data, full_slot, num_rows,
-                                                         idx.numel(), k, dim_origin)
+                full_slot = win.view(o[1], (rows, k), torch.int16)
+                maxk_kernels.cbsr_bank(sp_data, sp_index, dim_origin, with_index=False,
+                                       out=(full_data[mine], full_slot[mine]))
+                peer.publish_and_push(win, buf, o, per_rank)
+                out = maxk_kernels.spgemm_forward_banked(
+                    ptr, idx, val, full_data, full_slot, num_rows, idx.numel(), k, dim_origin, split=split,
+                    wait=(win.local, world, rank, r, peer.timeout_ms()))
             else:
-                full_data, full_index = peer.allgather(win, [sp_data, sp_index], offs)
+                full_data[mine].copy_(sp_data)
+                peer.publish_and_push(win, buf, o, per_rank)
+                peer.wait_all(win)
                 out, _ = maxk_kernels.spgemm_forward(ptr, idx, val, full_data, full_index, num_rows,
                                                      idx.numel(), k, dim_origin, allow_banked=False)
-            return out, (full_index.clone() if keep_index else full_index)
+            peer.join_push(win)
+            kept = full_index.clone() if keep_index else full_index
+            peer.release(win)
+            return out, kept
     if banked:
         bk_data, _, bk_slot = maxk_kernels.cbsr_bank(sp_data, sp_index, dim_origin, with_index=False)
         full_data, full_slot, full_index = allgather_many([bk_data, bk_slot, sp_index], group)
         out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, full_data, full_slot, num_rows,
-                                                 idx.numel(), k, dim_origin)
+                                                 idx.numel(), k, dim_origin, split=split)
     else:
         full_data, full_index = allgather_many([sp_data, sp_index], group)
         out, _ = maxk_kernels.spgemm_forward(ptr, idx, val, full_data, full_index, num_rows,
@@ -264,6 +287,18 @@ class ShardedGraph(CSRGraph):
     def edge_weights(self, kind: str) -> torch.Tensor:
         kind = {"right": "mean", "none": "sum"}.get(kind, kind)
         return self._weights[kind]
+
+    def to(self, device) -> "ShardedGraph":
+        """A shard is bound to its rank's device and process group: moving it would silently drop the
+        sharding (CSRGraph.to returns a plain graph whose global column ids no longer match a local
+        table).  Same device: no-op; anything else is an error."""
+        if torch.device(device) == self.device or (torch.device(device).type == self.device.type
+                                                   and torch.device(device).index is None):
+            return self
+        raise RuntimeError("a ShardedGraph cannot be moved: build it from the full graph on the target device")
+
+    def row_slice(self, r0: int, r1: int):
+        raise RuntimeError("row_slice of a ShardedGraph is not defined: slice the full graph, then shard it")
 
     def local_rows(self, t: torch.Tensor) -> torch.Tensor:
         """Rows [row_begin, row_end) of a full-height tensor, zero-padded to rows_per_rank."""

@@ -32,12 +32,18 @@ __all__ = [
     "maxk_forward", "maxk_backward", "spgemm_forward", "spgemm_backward",
     "maxk_forward_cbsr", "cbsr_scatter", "cbsr_gather", "partition",
     "clear_partition_cache", "install_partition", "set_max_nz", "get_max_nz", "launch_count",
-    "banked_supported", "cbsr_bank", "maxk_forward_banked", "spgemm_forward_banked",
+    "banked_supported", "cbsr_bank", "block_split", "maxk_forward_banked", "spgemm_forward_banked",
     "spgemm_backward_banked", "set_banked", "set_backward_tma", "use_banked", "forward_variant", "partition_blocked", "backward_blocks",
     "set_backward_block_mb", "add_layernorm_supported", "add_layernorm_forward", "layernorm_backward",
 ]
 
 _MAX_NZ = int(os.environ.get("MAXK_MAX_NZ", "1024"))
+# The backward has no partial rows to fold, so shorter records cost nothing and shorten the tail of
+# the grid (measured on an 8-way shard of the Reddit shape: 0.370 ms at 1024, 0.346 ms at 256).
+_BWD_MAX_NZ = int(os.environ.get("MAXK_BWD_MAX_NZ", "0"))      # 0: same as the forward
+# Records handed to the CTAs longest first (LPT): the grid then drains on the shortest records instead
+# of on a straggling 1024-entry one.  The row-ordered list stays what the fold of multi-record rows uses.
+_EXEC_SORTED = os.environ.get("MAXK_EXEC_ORDER", "1") != "0"
 _BANKED = os.environ.get("MAXK_BANKED", "1") != "0"
 _BANKED_MIN_RECORD = 96   # mean stored entries per work record below which banking does not pay
 # experimental backward: this many of the 4 neighbours of a warp step (k = 32) reduce through the TMA
@@ -214,7 +220,20 @@ def maxk_backward(grad_output: torch.Tensor, indices: torch.Tensor,
 # work partition cache (per graph)
 # ---------------------------------------------------------------------------------------
 class _Partition:
-    __slots__ = ("parts", "num_parts", "num_slots", "max_nz", "partial", "ptr_ref", "version")
+    __slots__ = ("parts", "num_parts", "num_slots", "max_nz", "partial", "ptr_ref", "version", "_exec")
+
+    def exec_parts(self) -> torch.Tensor:
+        """The records in the order the CTAs take them: longest first (stable, so equal lengths keep
+        their row order), or the row order itself with MAXK_EXEC_ORDER=0."""
+        ex = getattr(self, "_exec", None)
+        if ex is None:
+            if _EXEC_SORTED and self.num_parts > 1:
+                order = torch.argsort(self.parts[: self.num_parts, 2], descending=True, stable=True)
+                ex = self.parts[order].contiguous()
+            else:
+                ex = self.parts
+            self._exec = ex
+        return ex
 
     def partial_for(self, d: int, device) -> Optional[torch.Tensor]:
         """Scratch rows for the records of multi-record rows.  A fresh tensor per call (the caching
@@ -241,6 +260,7 @@ def _evict(cache: dict, limit: int) -> None:
 def clear_partition_cache() -> None:
     _part_cache.clear()
     _block_cache.clear()
+    _split_cache.clear()
 
 
 def partition(ptr: torch.Tensor, num_nodes: int, max_nz: Optional[int] = None) -> _Partition:
@@ -263,6 +283,7 @@ def partition(ptr: torch.Tensor, num_nodes: int, max_nz: Optional[int] = None) -
         p.num_parts, p.num_slots, p.max_nz = int(np_.value), int(ns_.value), max_nz
         p.parts = torch.empty((max(p.num_parts, 1), 4), dtype=torch.int32, device=ptr.device)
         p.partial = None
+        p._exec = None
         rc = L.mk_partition(ptr.data_ptr(), num_nodes, max_nz, p.parts.data_ptr(), None, None,
                             _stream())
         _lib.check(rc, "mk_partition")
@@ -337,6 +358,7 @@ def partition_blocked(ptr: torch.Tensor, idx: torch.Tensor, num_nodes: int, n_sr
         p.num_parts, p.num_slots, p.max_nz = int(np_.value), int(ns_.value), max_nz
         p.parts = torch.empty((max(p.num_parts, 1), 4), dtype=torch.int32, device=ptr.device)
         p.partial = None
+        p._exec = p.parts      # block-major order IS the point of this list: never re-sorted
         _lib.check(L.mk_partition_ranges(rs, re, vrows, num_nodes, max_nz, 1, p.parts.data_ptr(), None,
                                          None, _stream()), "mk_partition_ranges")
     _launches += 6
@@ -356,6 +378,7 @@ def install_partition(ptr: torch.Tensor, num_nodes: int, max_nz: int, parts: tor
     p.num_parts, p.num_slots, p.max_nz = int(parts.shape[0]), int(num_slots), int(max_nz)
     p.parts = parts.contiguous()
     p.partial = None
+    p._exec = None
     p.ptr_ref = weakref.ref(ptr)
     p.version = ptr._version
     _part_cache[(ptr.device.index, ptr.data_ptr(), int(num_nodes), int(max_nz))] = p
@@ -427,7 +450,9 @@ def spgemm_backward(ptr, idx, val, grad_output, sp_index, num_nodes, num_edges, 
     ib = _index_bytes(sp_index, dim_origin)
     n_src = sp_index.shape[0]
     nb = backward_blocks(n_src, dim_sparse, num_nodes, num_edges)
-    part = partition(ptr, num_nodes) if nb <= 1 else partition_blocked(ptr, idx, num_nodes, n_src, nb)
+    part = (partition(ptr, num_nodes, _BWD_MAX_NZ or None) if nb <= 1
+            else partition_blocked(ptr, idx, num_nodes, n_src, nb))
+    parts = part.exec_parts()
     if out is None:
         dxs = torch.empty((n_src, dim_sparse), dtype=torch.float32, device=grad_output.device)
     else:
@@ -439,12 +464,12 @@ def spgemm_backward(ptr, idx, val, grad_output, sp_index, num_nodes, num_edges, 
     with torch.cuda.device(grad_output.device):
         if tma:
             rc = _lib.lib().mk_sspmm_bwd_tma(
-                part.parts.data_ptr(), part.num_parts, idx.data_ptr(), val.data_ptr(),
+                parts.data_ptr(), part.num_parts, idx.data_ptr(), val.data_ptr(),
                 grad_output.data_ptr(), sp_index.data_ptr(), ib, dxs.data_ptr(), num_nodes, n_src,
                 dim_sparse, dim_origin, tma, _stream())
         else:
             rc = _lib.lib().mk_sspmm_bwd(
-                part.parts.data_ptr(), part.num_parts, idx.data_ptr(), val.data_ptr(),
+                parts.data_ptr(), part.num_parts, idx.data_ptr(), val.data_ptr(),
                 grad_output.data_ptr(), sp_index.data_ptr(), ib, dxs.data_ptr(), num_nodes, n_src,
                 dim_sparse, dim_origin, _stream())
     _lib.check(rc, "mk_sspmm_bwd")
@@ -459,11 +484,13 @@ def banked_supported(k: int, dim_origin: int) -> bool:
     return bool(_lib.lib().mk_banked_supported(int(k), int(dim_origin)))
 
 
-def cbsr_bank(sp_data: torch.Tensor, sp_index: torch.Tensor, dim_origin: int, with_index: bool = True):
+def cbsr_bank(sp_data: torch.Tensor, sp_index: torch.Tensor, dim_origin: int, with_index: bool = True,
+              *, out=None):
     """(sp_data, sp_index) -> (bk_data, bk_index, bk_slot): every row re-ordered and every entry
     given one of two shared-memory cells so that the aggregation kernels run without bank
     conflicts.  `(bk_data, bk_index)` is the same CBSR row in another entry order; with
-    `with_index=False` bk_index is not produced (the forward kernel does not read it)."""
+    `with_index=False` bk_index is not produced (the forward kernel does not read it).
+    `out = (bk_data, bk_slot)`: write into these [n, k] fp32 / int16 buffers (rows of a peer window)."""
     global _launches
     _cuda_contig(sp_data, "sp_data")
     _cuda_contig(sp_index, "sp_index")
@@ -472,9 +499,17 @@ def cbsr_bank(sp_data: torch.Tensor, sp_index: torch.Tensor, dim_origin: int, wi
     n, k = sp_data.shape
     _chk(banked_supported(k, dim_origin), "banked CBSR needs k in {8,16,32,64}, dim % 8 == 0, dim <= 512")
     ib = _index_bytes(sp_index, dim_origin)
-    bk_data = torch.empty_like(sp_data)
+    if out is None:
+        bk_data = torch.empty_like(sp_data)
+        bk_slot = torch.empty((n, k), dtype=torch.int16, device=sp_data.device)
+    else:
+        bk_data, bk_slot = out
+        _cuda_contig(bk_data, "out")
+        _cuda_contig(bk_slot, "out")
+        _chk(bk_data.dtype == torch.float32 and bk_slot.dtype in (torch.int16, torch.uint16)
+             and tuple(bk_data.shape) == (n, k) and tuple(bk_slot.shape) == (n, k),
+             "out must be (float32 [n,k], int16 [n,k])")
     bk_index = torch.empty_like(sp_index) if with_index else None
-    bk_slot = torch.empty((n, k), dtype=torch.int16, device=sp_data.device)
     with torch.cuda.device(sp_data.device):
         rc = _lib.lib().mk_cbsr_bank(sp_data.data_ptr(), sp_index.data_ptr(), ib, bk_data.data_ptr(),
                                      bk_index.data_ptr() if with_index else None, bk_slot.data_ptr(),
@@ -484,14 +519,44 @@ def cbsr_bank(sp_data: torch.Tensor, sp_index: torch.Tensor, dim_origin: int, wi
     return bk_data, bk_index, bk_slot
 
 
+_split_cache = {}
+
+
+def block_split(ptr: torch.Tensor, idx: torch.Tensor, num_nodes: int, world: int, rank: int,
+                rows_per_rank: int) -> torch.Tensor:
+    """int32 [num_nodes]: for every CSR row (ascending global column ids) the position in `idx` of
+    its first stored entry whose column belongs to rank `rank` or a later rank.  The row-partitioned
+    forward walks [split, end) first and [begin, split) second: own block, rank+1, ..., rank-1 --
+    the order in which the peers' rows arrive (peer.py).  Built once per graph on the GPU."""
+    global _launches
+    key = (ptr.device.index, ptr.data_ptr(), idx.data_ptr(), int(num_nodes), int(world), int(rank), int(rows_per_rank))
+    hit = _split_cache.get(key)
+    if hit is not None and hit[0]() is ptr and hit[1] == ptr._version:
+        return hit[2]
+    blk = torch.empty(((world + 1) * num_nodes,), dtype=torch.int32, device=ptr.device)
+    with torch.cuda.device(ptr.device):
+        _lib.check(_lib.lib().mk_block_ptr(ptr.data_ptr(), idx.data_ptr(), num_nodes, world, rows_per_rank,
+                                           blk.data_ptr(), _stream()), "mk_block_ptr")
+    _launches += 1
+    split = blk[rank * num_nodes:(rank + 1) * num_nodes].clone()
+    if len(_split_cache) >= 32:
+        del _split_cache[next(iter(_split_cache))]
+    _split_cache[key] = (weakref.ref(ptr), ptr._version, split)
+    return split
+
+
 def maxk_forward_banked(input: torch.Tensor, k: int):
     """top-k -> CBSR -> banked form in one call: (bk_data, bk_index, bk_slot)."""
     sp_data, sp_index = maxk_forward_cbsr(input, k)
     return cbsr_bank(sp_data, sp_index, input.shape[1])
 
 
-def spgemm_forward_banked(ptr, idx, val, bk_data, bk_slot, num_nodes, num_edges, dim_sparse, dim_origin):
-    """`spgemm_forward` on a banked table: same result, no shared-memory bank conflicts."""
+def spgemm_forward_banked(ptr, idx, val, bk_data, bk_slot, num_nodes, num_edges, dim_sparse, dim_origin,
+                          *, split: Optional[torch.Tensor] = None, wait=None):
+    """`spgemm_forward` on a banked table: same result, no shared-memory bank conflicts.
+    Row-partitioned form (dist.py): `split` int32 [num_nodes] makes every record walk the source
+    blocks in arrival order, `wait = (window base pointer, world, rank, rows_per_rank, timeout_ms)`
+    lets the kernel run while the peers' rows are still arriving (peer.py)."""
     global _launches
     _check_graph(ptr, idx, val)
     _cuda_contig(bk_data, "sp_data")
@@ -500,16 +565,23 @@ def spgemm_forward_banked(ptr, idx, val, bk_data, bk_slot, num_nodes, num_edges,
     _chk(bk_slot.dtype in (torch.int16, torch.uint16) and bk_slot.shape == bk_data.shape,
          "bk_slot must be 16-bit with the shape of bk_data")
     _chk(bk_data.shape[1] == dim_sparse, "dim_sparse must equal sp_data.size(1)")
+    if split is not None:
+        _cuda_contig(split, "split")
+        _chk(split.dtype == torch.int32 and split.numel() >= num_nodes, "split must be int32 [num_nodes]")
     part = partition(ptr, num_nodes)
     out = torch.empty((num_nodes, dim_origin), dtype=torch.float32, device=bk_data.device)
     partial = part.partial_for(dim_origin, bk_data.device)
+    ex = part.exec_parts()
+    w_ptr, w_world, w_rank, w_rows, w_tmo = wait if wait is not None else (None, 1, 0, 1, 0)
     with torch.cuda.device(bk_data.device):
-        rc = _lib.lib().mk_spgemm_fwd_banked(
-            part.parts.data_ptr(), part.num_parts, part.num_slots, idx.data_ptr(), val.data_ptr(),
+        rc = _lib.lib().mk_spgemm_fwd_banked_ex(
+            part.parts.data_ptr(), part.num_parts, part.num_slots,
+            ex.data_ptr() if ex is not part.parts else None, idx.data_ptr(), val.data_ptr(),
             bk_data.data_ptr(), bk_slot.data_ptr(), out.data_ptr(),
             partial.data_ptr() if partial is not None else None, num_nodes, dim_sparse, dim_origin,
-            _stream())
-    _lib.check(rc, "mk_spgemm_fwd_banked")
+            split.data_ptr() if split is not None else None, w_ptr, int(w_world), int(w_rank),
+            int(w_rows), int(w_tmo), _stream())
+    _lib.check(rc, "mk_spgemm_fwd_banked_ex")
     _launches += 1 + (1 if part.num_slots else 0)
     return out
 
@@ -531,7 +603,7 @@ def spgemm_backward_banked(ptr, idx, val, grad_output, bk_slot, num_nodes, num_e
     dxs = torch.empty((n_src, dim_sparse), dtype=torch.float32, device=grad_output.device)
     with torch.cuda.device(grad_output.device):
         rc = _lib.lib().mk_sspmm_bwd_banked(
-            part.parts.data_ptr(), part.num_parts, idx.data_ptr(), val.data_ptr(),
+            part.exec_parts().data_ptr(), part.num_parts, idx.data_ptr(), val.data_ptr(),
             grad_output.data_ptr(), bk_slot.data_ptr(), dxs.data_ptr(), num_nodes, n_src,
             dim_sparse, dim_origin, _stream())
     _lib.check(rc, "mk_sspmm_bwd_banked")

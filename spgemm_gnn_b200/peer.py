@@ -1,14 +1,16 @@
 """Peer-memory exchange of the row-partitioned hot path (csrc/peer.cu).
 
 The two exchanges of a sharded layer -- all-gather of the CBSR table in front of the forward
-SpGEMM, reduce-scatter of the CBSR gradient behind the backward SSpMM -- as this library's own
-kernels over NVLink instead of NCCL calls:
+SpGEMM, reduce-scatter of the CBSR gradient behind the backward SSpMM -- over NVLink peer memory
+instead of NCCL calls:
 
-  * `bank_push`       csrc/bank.cu writes the banked rows it produces straight into every rank's
-                      table (compute + all-gather in one kernel);
-  * `allgather`       the plain form for the un-banked table (stores into every rank's table);
-  * `reduce_scatter`  every rank loads its block from every rank's partial buffer and folds it in
-                      rank order (bit-reproducible).
+  * forward  `begin_push` -> the producer writes the rank's rows into its OWN window ->
+             `publish_and_push` (copy engines, side stream: one transfer per peer and table, each
+             peer's transfers followed by its `done` flag) -> the forward SpGEMM starts at once and
+             waits per source block (`spgemm_forward_banked(wait=...)`) -> `join_push`, `release`.
+             The transfer overlaps the kernel that consumes it; no SM copies anything.
+  * backward `reduce_scatter`: every rank loads its block from every rank's partial buffer and
+             folds it in rank order (bit-reproducible); the SSpMM wrote straight into the window.
 
 Rules of use: every rank issues the same collectives through a window in the same order, and a
 rank issues them from one stream at a time (stream order is what tells the peers that the rank is
@@ -18,10 +20,12 @@ A `PeerWindow` is one device buffer per rank, mapped into every process of the g
 (`mk_peer_export` / `mk_peer_open`, handles exchanged with `all_gather_object`).  The kernels keep
 their flags and epoch counters in the window's header, so captured CUDA graphs replay correctly.
 
-On by default for NCCL groups of 2..16 ranks (checked against the NCCL path at 2 and 8 GPUs:
-forward bit-equal, profiles/r1_peer_exchange.md); `MAXK_PEER_EXCHANGE=0` (or `set_enabled(False)`)
+On by default for NCCL groups of 2..16 ranks; `MAXK_PEER_EXCHANGE=0` (or `set_enabled(False)`)
 keeps dist.py on NCCL, and so does any failure to map the windows (agreed on by all ranks).  There
 is no CPU form: on a gloo group `available()` is False and dist.py stays on its collectives.
+
+A kernel that waits for a peer longer than `MAXK_PEER_TIMEOUT_MS` writes the window's error word and
+gives up; `check_errors()` (one device synchronisation) turns that into a `PeerTimeoutError`.
 """
 from __future__ import annotations
 
@@ -41,10 +45,11 @@ _ALIGN = 256
 
 _ENABLED = os.environ.get("MAXK_PEER_EXCHANGE", "1") != "0"   # "0": stay on NCCL collectives
 _TIMEOUT_MS = int(os.environ.get("MAXK_PEER_TIMEOUT_MS", "120000"))
-# how bank_push reaches the peers: 1 = every row stored straight into all tables (measured),
-# 2 = own table first, then each block copies its rows with 16-byte stores (experimental)
-_PUSH_MODE = int(os.environ.get("MAXK_PEER_PUSH_MODE", "1"))
 _launches = 0
+
+
+class PeerTimeoutError(RuntimeError):
+    pass
 
 
 def set_enabled(on: bool) -> None:
@@ -58,6 +63,10 @@ def enabled() -> bool:
 
 def launch_count() -> int:
     return _launches
+
+
+def timeout_ms() -> int:
+    return _TIMEOUT_MS
 
 
 def available(group=None) -> bool:
@@ -97,6 +106,9 @@ class PeerWindow:
         self.opened: List[int] = []  # peers' buffers mapped with mk_peer_open
         self.ptrs = (ctypes.c_void_p * MAX_RANKS)()
         self._bytes = None
+        self._side = None          # stream of the copy-engine pushes
+        self._pushed = None        # event behind the last push
+        self._buf = 1              # table buffer of the last forward (alternates 0, 1, 0, ...)
 
     # ---- construction -------------------------------------------------------------------
     @classmethod
@@ -184,6 +196,18 @@ class PeerWindow:
             raise ValueError("view outside the window payload")
         return self._bytes[offset:offset + nb].view(dtype).view(*shape)
 
+    def side_stream(self) -> torch.cuda.Stream:
+        if self._side is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("the push stream must exist before CUDA graph capture (run one eager step first)")
+            with torch.cuda.device(self.device):
+                self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
+    def next_buffer(self) -> int:
+        self._buf ^= 1
+        return self._buf
+
     def epoch(self) -> Tuple[int, int]:
         """(collectives completed, error word) -- synchronises the current stream."""
         e, err = ctypes.c_uint32(0), ctypes.c_uint32(0)
@@ -241,50 +265,70 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def allgather(win: PeerWindow, locals_: Sequence[torch.Tensor], offsets: Sequence[int],
-              grid: int = 0) -> List[torch.Tensor]:
-    """Every rank's `locals_[g]` ([R, ...], same shape on all ranks) -> [world*R, ...] at
-    `offsets[g]` of every rank's window.  Returns the gathered tensors (views of the window)."""
+def begin_push(win: PeerWindow, buf: int) -> None:
+    """Before the producer overwrites table buffer `buf`: wait until every peer has released it."""
     global _launches
-    n = len(locals_)
-    src = (ctypes.c_void_p * n)()
-    nbytes = (ctypes.c_int64 * n)()
-    offs = (ctypes.c_int64 * n)()
-    outs = []
-    for g, t in enumerate(locals_):
-        if not (t.is_cuda and t.is_contiguous()):
-            raise RuntimeError("peer all-gather wants contiguous CUDA tensors")
-        b = t.numel() * t.element_size()
-        if b % 16:
-            raise RuntimeError("peer all-gather segments must be multiples of 16 bytes")
-        src[g], nbytes[g], offs[g] = t.data_ptr(), b, int(offsets[g])
-        outs.append(win.view(int(offsets[g]), (win.world * t.shape[0],) + tuple(t.shape[1:]), t.dtype))
     with torch.cuda.device(win.device):
-        rc = _lib.lib().mk_peer_allgather(win.ptrs, win.world, win.rank, n, src, nbytes, offs, grid,
-                                          _TIMEOUT_MS, _stream())
-    _lib.check(rc, "mk_peer_allgather")
+        rc = _lib.lib().mk_peer_begin_push(win.local, win.world, win.rank, int(buf), _TIMEOUT_MS, _stream())
+    _lib.check(rc, "mk_peer_begin_push")
     _launches += 1
-    return outs
 
 
-def bank_push(win: PeerWindow, sp_data: torch.Tensor, sp_index: torch.Tensor, dim_origin: int,
-              offsets: Sequence[int]):
-    """Fused banking + all-gather: (full bk_data fp32, full bk_slot int16, full sorted sp_index),
-    each [world*R, k], views of this rank's window at `offsets` = (data, slot, index)."""
+def publish_and_push(win: PeerWindow, buf: int, offsets: Sequence[int], bytes_per_rank: Sequence[int]) -> None:
+    """The rank's rows of the segments at `offsets` (segment g: `bytes_per_rank[g]` bytes per rank) are
+    complete in its own window (current stream): open the collective and let the copy engines carry
+    the rows to every peer on the window's side stream, each peer's rows followed by its flag."""
     global _launches
-    r, k = sp_data.shape
-    if not (sp_data.is_cuda and sp_data.is_contiguous() and sp_index.is_contiguous()):
-        raise RuntimeError("peer bank_push wants contiguous CUDA tensors")
-    od, os_, oi = (int(o) for o in offsets)
+    n = len(offsets)
+    offs = (ctypes.c_int64 * n)(*[int(o) for o in offsets])
+    nbytes = (ctypes.c_int64 * n)(*[int(b) for b in bytes_per_rank])
+    L = _lib.lib()
+    main = torch.cuda.current_stream()
+    side = win.side_stream()
     with torch.cuda.device(win.device):
-        rc = _lib.lib().mk_peer_bank_push(sp_data.data_ptr(), sp_index.data_ptr(), sp_index.element_size(),
-                                          win.ptrs, win.world, win.rank, od, os_, oi, r, k, dim_origin,
-                                          2 if _PUSH_MODE == 2 else 1, _TIMEOUT_MS, _stream())
-    _lib.check(rc, "mk_peer_bank_push")
+        _lib.check(L.mk_peer_publish(win.local, win.rank, int(buf), main.cuda_stream), "mk_peer_publish")
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        _lib.check(L.mk_peer_push(win.ptrs, win.world, win.rank, n, offs, nbytes, side.cuda_stream), "mk_peer_push")
+        win._pushed = torch.cuda.Event()
+        win._pushed.record(side)
     _launches += 1
-    rows = win.world * r
-    return (win.view(od, (rows, k), torch.float32), win.view(os_, (rows, k), torch.int16),
-            win.view(oi, (rows, k), sp_index.dtype))
+
+
+def join_push(win: PeerWindow) -> None:
+    """The current stream continues only after the window's pushes have left (joins the side stream;
+    needed before the next producer touches the window, and before a CUDA graph capture ends)."""
+    if win._pushed is not None:
+        torch.cuda.current_stream().wait_event(win._pushed)
+        win._pushed = None
+
+
+def wait_all(win: PeerWindow) -> None:
+    """For consumers that cannot wait per block: returns (on the stream) when the whole table is in."""
+    global _launches
+    with torch.cuda.device(win.device):
+        rc = _lib.lib().mk_peer_wait_all(win.local, win.world, _TIMEOUT_MS, _stream())
+    _lib.check(rc, "mk_peer_wait_all")
+    _launches += 1
+
+
+def release(win: PeerWindow) -> None:
+    """The rank has finished reading the table of its current collective (tells the peers)."""
+    global _launches
+    with torch.cuda.device(win.device):
+        rc = _lib.lib().mk_peer_release(win.ptrs, win.world, win.rank, _stream())
+    _lib.check(rc, "mk_peer_release")
+    _launches += 1
+
+
+def check_errors() -> None:
+    """Raise if a kernel gave up waiting for a peer on any window (synchronises the device)."""
+    for key, w in _windows.items():
+        ep, err = w.epoch()
+        if err:
+            raise PeerTimeoutError(f"peer window {key[0]}: a kernel of rank {w.rank} gave up waiting for a peer "
+                                   f"in collective {err} (epoch {ep}); results since then are invalid")
 
 
 def reduce_scatter(win: PeerWindow, offset: int, rows: int, k: int, grid: int = 0) -> torch.Tensor:
@@ -301,3 +345,19 @@ def reduce_scatter(win: PeerWindow, offset: int, rows: int, k: int, grid: int = 
     _lib.check(rc, "mk_peer_reduce_scatter")
     _launches += 1
     return out
+
+
+def reduce_scatter_virtual(wins: Sequence[PeerWindow], offset: int, rows: int, k: int, grid: int = 0):
+    """Single-process emulation (PeerWindow.create_virtual): the reduce-scatter of ALL virtual ranks
+    in one launch -- launches that wait on one another must not share a device.  Tests only."""
+    global _launches
+    world = len(wins)
+    block = rows * k * 4
+    outs = [torch.empty((rows, k), dtype=torch.float32, device=wins[0].device) for _ in range(world)]
+    optr = (ctypes.c_void_p * world)(*[o.data_ptr() for o in outs])
+    with torch.cuda.device(wins[0].device):
+        rc = _lib.lib().mk_peer_reduce_scatter_virtual(wins[0].ptrs, world, int(offset), block, optr, grid,
+                                                       _TIMEOUT_MS, _stream())
+    _lib.check(rc, "mk_peer_reduce_scatter_virtual")
+    _launches += 1
+    return outs

@@ -217,6 +217,9 @@ def main(argv=None):
         sg = ShardedGraph(g, rank, world)
         feats, labels, train_mask = sg.local_rows(feats), sg.local_rows(labels), sg.local_rows(train_mask)
         g = sg
+        # weights were initialised from the common seed above; from here on every rank draws its own
+        # random numbers, so that the dropout masks of the shards are independent
+        torch.manual_seed(a.seed + 1000003 * (rank + 1))
     say = print if rank == 0 else (lambda *_: None)
     say(f"{a.dataset}: {n_nodes} nodes, {n_edges} edges; model {a.model} "
         f"{sum(p.numel() for p in model.parameters())} params; {world} GPU(s)")

@@ -36,7 +36,8 @@ int main(void) {
     CHECK(mk_banked_supported(32, 256) == 1 && mk_banked_supported(7, 256) == 0);
     CHECK(mk_peer_alloc(8, &p) == MK_EINVAL);
     CHECK(mk_peer_export(0, handle) == MK_EINVAL);
-    CHECK(mk_peer_allgather(windows, 2, 0, 1, 0, 0, 0, 0, 0, 0) == MK_EINVAL);
+    CHECK(mk_peer_push(windows, 2, 0, 1, 0, 0, 0) == MK_EINVAL);
+    CHECK(mk_peer_publish(0, 0, 0, 0) == MK_EINVAL);
     CHECK(mk_peer_reduce_scatter(windows, 2, 5, 1024, 64, 0, 0, 0, 0) == MK_EINVAL);
     printf("c abi ok: version %d\n", mk_version());
     return 0;

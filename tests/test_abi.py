@@ -38,7 +38,7 @@ def test_header_is_plain_c_and_links(built_lib, tmp_path):
                            os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe,
                            "-L", libdir, "-lmaxk_b200", "-Wl,-rpath," + libdir])
     out = subprocess.check_output([exe]).decode()
-    assert "c abi ok: version 101" in out
+    assert "c abi ok: version 200" in out
 
 
 def test_library_is_sm100a_and_has_no_torch_dependency(built_lib):
@@ -51,7 +51,7 @@ def test_library_is_sm100a_and_has_no_torch_dependency(built_lib):
 
 def test_version_and_error_strings(built_lib):
     L = _lib.lib()
-    assert L.mk_version() == 101
+    assert L.mk_version() == 200
     assert L.mk_error_string(0) == b"ok"
     assert L.mk_error_string(-1) == b"invalid argument"
     assert b"CUDA" in L.mk_error_string(-3)
@@ -77,25 +77,31 @@ def test_peer_argument_validation_without_a_device(built_lib):
     VP = ctypes.c_void_p
     wins = (VP * 16)()
     wins[0], wins[1] = 0x1000, 0x2000
-    src, nb, off = (VP * 1)(), (ctypes.c_int64 * 1)(64), (ctypes.c_int64 * 1)(1024)
-    src[0] = 0x3000
+    nb, off = (ctypes.c_int64 * 1)(64), (ctypes.c_int64 * 1)(1024)
     E = _lib.MK_EINVAL
-    assert L.mk_peer_allgather(wins, 0, 0, 1, src, nb, off, 0, 0, None) == E        # world < 1
-    assert L.mk_peer_allgather(wins, 17, 0, 1, src, nb, off, 0, 0, None) == E       # world > 16
-    assert L.mk_peer_allgather(wins, 2, 2, 1, src, nb, off, 0, 0, None) == E        # rank >= world
-    assert L.mk_peer_allgather(wins, 3, 0, 1, src, nb, off, 0, 0, None) == E        # window 2 missing
-    assert L.mk_peer_allgather(wins, 2, 0, 5, src, nb, off, 0, 0, None) == E        # > 4 segments
+    assert L.mk_peer_push(wins, 0, 0, 1, off, nb, None) == E          # world < 1
+    assert L.mk_peer_push(wins, 17, 0, 1, off, nb, None) == E         # world > 16
+    assert L.mk_peer_push(wins, 2, 2, 1, off, nb, None) == E          # rank >= world
+    assert L.mk_peer_push(wins, 3, 0, 1, off, nb, None) == E          # window 2 missing
+    assert L.mk_peer_push(wins, 2, 0, 9, off, nb, None) == E          # > 8 segments
     off[0] = 512
-    assert L.mk_peer_allgather(wins, 2, 0, 1, src, nb, off, 0, 0, None) == E        # inside the header
-    off[0], nb[0] = 1024, 24
-    assert L.mk_peer_allgather(wins, 2, 0, 1, src, nb, off, 0, 0, None) == E        # not 16-byte units
+    assert L.mk_peer_push(wins, 2, 0, 1, off, nb, None) == E          # inside the header
+    off[0] = 1024
+    assert L.mk_peer_push(wins, 1, 0, 1, off, nb, None) == _lib.MK_OK  # one rank: nothing to send
+    assert L.mk_peer_begin_push(None, 2, 0, 0, 0, None) == E           # no window
+    assert L.mk_peer_begin_push(0x1000, 2, 0, 2, 0, None) == E         # only two table buffers
+    assert L.mk_peer_publish(None, 0, 0, None) == E
+    assert L.mk_peer_publish(0x1000, 0, 3, None) == E
+    assert L.mk_peer_wait_all(None, 2, 0, None) == E
+    assert L.mk_peer_release(wins, 2, 5, None) == E                    # rank >= world
     assert L.mk_peer_reduce_scatter(wins, 2, 0, 1000, 64, None, 0, 0, None) == E     # offset in header
     assert L.mk_peer_reduce_scatter(wins, 2, 0, 1024, 64, None, 0, 0, None) == E     # no output
-    assert L.mk_peer_bank_push(None, None, 1, wins, 2, 0, 1024, 2048, 4096, 4, 7, 256, 1, 0, None) == _lib.MK_EUNSUPPORTED
-    assert L.mk_peer_bank_push(None, None, 1, wins, 2, 0, 1024, 2048, 4096, 4, 32, 256, 1, 0, None) == E  # null rows
-    assert L.mk_peer_bank_push(None, None, 1, wins, 2, 0, 8, 2048, 4096, 0, 32, 256, 1, 0, None) == E     # header
-    assert L.mk_peer_bank_push(None, None, 1, wins, 2, 0, 1024, 2048, 4096, 4, 32, 256, 3, 0, None) == E  # mode
-    assert L.mk_peer_bank_push(None, None, 1, wins, 2, 0, 1024, 2048, 4096, 3, 8, 256, 2, 0, None) == E   # 24-byte block
+    assert L.mk_peer_reduce_scatter(wins, 2, 0, 1024, 24, None, 0, 0, None) == E     # not 16-byte units
+    # waiting forward: bad rank layout is rejected before any CUDA call
+    assert L.mk_spgemm_fwd_banked_ex(None, 5, 0, None, None, None, None, None, None, None, 5, 32, 256,
+                                     None, 0x1000, 2, 2, 100, 0, None) == E
+    assert L.mk_spgemm_fwd_banked_ex(None, 5, 0, None, None, None, None, None, None, None, 5, 32, 256,
+                                     None, 0x1000, 2, 0, 0, 0, None) == E
     p = VP(0)
     assert L.mk_peer_alloc(16, ctypes.byref(p)) == E                                # smaller than the header
     assert L.mk_peer_free(None) == _lib.MK_OK and L.mk_peer_close(None) == _lib.MK_OK

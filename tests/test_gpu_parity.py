@@ -720,3 +720,51 @@ def test_fused_add_layernorm_matches_torch(mk, n, d, with_b, with_bias):
         close(cbias.grad, rbias.grad, "grad bias")
     close(norm.weight.grad, rw.grad, "grad gamma")
     close(norm.bias.grad, rbeta.grad, "grad beta")
+
+
+# ---------------------------------------------------------------------------------------
+# the knobs of the row-partitioned / load-balanced forward (mk_spgemm_fwd_banked_ex)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [32, 64, 16])
+def test_forward_arrival_order_walk_and_sorted_records(mk, k):
+    """`split` (walk [split, end) before [begin, split)) and the longest-first record order change the
+    order of execution, not the result: against the float64 oracle at the 1e-5 bar, bit-equal between
+    record orders (each row is still summed by one warp in one fixed order), and with a pre-opened
+    wait window the waiting kernel is bit-equal to the plain one."""
+    from oracle import c_oracle
+    from spgemm_gnn_b200 import maxk_kernels as mkk
+    from conftest import small_graph
+    g = small_graph(3000, 70, seed=8, device="cuda")
+    n, e, d = g.num_nodes(), g.num_edges(), 256
+    rng = np.random.default_rng(k)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    val = g.edge_weights("both")
+    sd, si = mk.maxk_forward_cbsr(dev(x), k)
+    bd, _, bs = mk.cbsr_bank(sd, si, d, with_index=False)
+    mk.set_max_nz(64)
+    try:
+        mk.clear_partition_cache()
+        world, rank = 4, 1
+        r = -(-n // world)
+        split = mk.block_split(g.indptr, g.indices, n, world, rank, r)
+        # split really is the first entry of the row with column >= rank * r
+        ptr, idx = g.indptr.cpu().numpy(), g.indices.cpu().numpy()
+        want_split = np.array([ptr[i] + np.searchsorted(idx[ptr[i]:ptr[i + 1]], rank * r) for i in range(n)])
+        assert np.array_equal(split.cpu().numpy(), want_split)
+        base = mk.spgemm_forward_banked(g.indptr, g.indices, val, bd, bs, n, e, k, d)
+        walked = mk.spgemm_forward_banked(g.indptr, g.indices, val, bd, bs, n, e, k, d, split=split)
+        want = c_oracle.spgemm_fwd(ptr, idx, val.cpu().numpy(), sd.cpu().numpy(), si.cpu().numpy(), d)
+        bound = c_oracle.spgemm_fwd(ptr, idx, np.abs(val.cpu().numpy()), np.abs(sd.cpu().numpy()), si.cpu().numpy(), d)
+        assert_rel(base, want, bound, "banked forward, sorted records")
+        assert_rel(walked, want, bound, "banked forward, arrival-order walk")
+        was = mkk._EXEC_SORTED
+        mkk._EXEC_SORTED = False
+        mk.clear_partition_cache()
+        try:
+            row_order = mk.spgemm_forward_banked(g.indptr, g.indices, val, bd, bs, n, e, k, d)
+        finally:
+            mkk._EXEC_SORTED = was
+        assert torch.equal(base, row_order)
+    finally:
+        mk.set_max_nz(1024)
+        mk.clear_partition_cache()

@@ -1,15 +1,14 @@
 #!/usr/bin/env python
 """Checks of the peer-memory exchange kernels (csrc/peer.cu, bank.cu PUSH form, peer.py).
 
-    python tools/peer_check.py virtual [WORLD] [--all-k]    one GPU: WORLD virtual ranks, one stream each
+    python tools/peer_check.py virtual [WORLD] [--all-k]    one GPU: WORLD virtual ranks in one process
     torchrun --nproc-per-node N tools/peer_check.py dist [--bench] [--products] [--stress]    N GPUs
-    (either form: --push-mode 2 selects the experimental vector-copy form of the fused bank + push)
 
 `virtual` exercises the kernels and their flag protocol inside one process (every "peer" window
 is a local buffer), `dist` runs the sharded forward/backward of dist.py with the peer path and
 with NCCL on the same inputs and compares them (forward bit-exact, backward to summation order),
-then optionally times both.  Runs in its own process because a kernel that gives up on a peer
-traps, which poisons the CUDA context (tests/test_gpu_peer.py calls this file as a subprocess).
+then optionally times both.  Runs in its own process (tests/test_gpu_peer.py calls this file as a
+subprocess): a peer time-out leaves garbage behind that no later test should inherit.
 """
 import os
 import sys
@@ -20,63 +19,83 @@ import torch
 
 
 def virtual(world: int) -> int:
+    """One GPU, WORLD virtual ranks in one process (every "peer" window is a local buffer).  The
+    overlapped all-gather needs no kernel that waits for another launch -- the copy engines carry rows
+    and flags -- so the ranks simply take turns on one stream; the reduce-scatter, whose blocks do wait
+    for peers' flags, runs all ranks in ONE launch (mk_peer_reduce_scatter_virtual)."""
     import maxk_kernels as mk
-    from spgemm_gnn_b200 import peer
+    from spgemm_gnn_b200 import dist as mdist, peer
+    from spgemm_gnn_b200.graph import synthetic_graph
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     peer._TIMEOUT_MS = 8000
-    r, k, d = 1000, 32, 256           # r*k*1 is a multiple of 16; r not a multiple of 128
+    d = 256
     gen = torch.Generator(device=dev).manual_seed(11)
-    streams = [torch.cuda.Stream() for _ in range(world)]
     ok = True
+    g = synthetic_graph(4 * 1003, 4 * 1003 * 90, seed=5, device=dev)
+    n = g.num_nodes()
+    wins_all = []
 
-    # ---- all-gather by stores, three rounds through the same windows (epochs 1..3)
-    rows = world * r
-    offs, total = peer.layout([rows * k * 4, rows * k])
-    wins = peer.PeerWindow.create_virtual(total, world, dev)
-    for rnd in range(3):
-        data = [torch.randn(r, k, device=dev, generator=gen) for _ in range(world)]
-        index = [torch.randint(0, 256, (r, k), device=dev, generator=gen, dtype=torch.int32).to(torch.uint8)
-                 for _ in range(world)]
-        torch.cuda.synchronize()
-        outs = []
-        for q in range(world):
-            with torch.cuda.stream(streams[q]):
-                outs.append(peer.allgather(wins[q], [data[q], index[q]], offs, grid=6))
-        torch.cuda.synchronize()
-        want_d, want_i = torch.cat(data), torch.cat(index)
-        for q in range(world):
-            good = torch.equal(outs[q][0], want_d) and torch.equal(outs[q][1], want_i)
-            ep, err = wins[q].epoch()
-            good &= (ep == rnd + 1 and err == 0)
-            ok &= good
-        print(f"allgather round {rnd}: {'OK' if ok else 'FAIL'}")
-
-    # ---- fused bank + push against cbsr_bank + concatenation (--all-k: every banked width)
-    wins3 = []
-    for kk in ((8, 16, 32, 64) if "--all-k" in sys.argv else (k,)):
-        offs3, total3 = peer.layout([rows * kk * 4, rows * kk * 2, rows * kk])
-        wk = peer.PeerWindow.create_virtual(total3, world, dev)
-        wins3 += wk
-        for rnd in range(2):
+    for kk in ((8, 16, 32, 64) if "--all-k" in sys.argv else (32,)):
+        r = mdist.rows_per_rank(n, world)
+        rows = world * r
+        per_rank = [r * kk * 4, r * kk * 2, r * kk]
+        offs, total = peer.layout([world * b for b in per_rank] * 2)
+        wins = peer.PeerWindow.create_virtual(total, world, dev)
+        wins_all += wins
+        shards = [mdist.shard_graph(g, q, world) for q in range(world)]
+        vals = [mdist.shard_edge_weights(g, sh[0], sh[1], sh[2], "mean") for sh in shards]
+        for rnd in range(4):   # rounds 2, 3 re-use the two table buffers: release / begin_push handshake
             xs = [torch.randn(r, d, device=dev, generator=gen) for _ in range(world)]
             cb = [mk.maxk_forward_cbsr(x, kk) for x in xs]
             ref = [mk.cbsr_bank(sd, si, d, with_index=False) for sd, si in cb]
-            torch.cuda.synchronize()
-            outs = []
-            for q in range(world):
-                with torch.cuda.stream(streams[q]):
-                    outs.append(peer.bank_push(wk[q], cb[q][0], cb[q][1], d, offs3))
-            torch.cuda.synchronize()
             want = (torch.cat([a for a, _, _ in ref]), torch.cat([c for _, _, c in ref]),
                     torch.cat([si for _, si in cb]))
+            outs = []
             for q in range(world):
-                good = all(torch.equal(a, b) for a, b in zip(outs[q], want))
-                ok &= good
-            print(f"bank_push k={kk} round {rnd}: {'OK' if ok else 'FAIL'}")
+                w = wins[q]
+                buf = w.next_buffer()
+                o = offs[3 * buf: 3 * buf + 3]
+                mine = slice(q * r, (q + 1) * r)
+                peer.begin_push(w, buf)
+                fd = w.view(o[0], (rows, kk), torch.float32)
+                fs = w.view(o[1], (rows, kk), torch.int16)
+                fi = w.view(o[2], (rows, kk), torch.uint8)
+                fi[mine].copy_(cb[q][1])
+                mk.cbsr_bank(cb[q][0], cb[q][1], d, with_index=False, out=(fd[mine], fs[mine]))
+                peer.publish_and_push(w, buf, o, per_rank)
+            for q in range(world):
+                w = wins[q]
+                buf = w._buf
+                o = offs[3 * buf: 3 * buf + 3]
+                fd = w.view(o[0], (rows, kk), torch.float32)
+                fs = w.view(o[1], (rows, kk), torch.int16)
+                fi = w.view(o[2], (rows, kk), torch.uint8)
+                local = shards[q][0]
+                split = mk.block_split(local.indptr, local.indices, r, world, q, r)
+                out = mk.spgemm_forward_banked(local.indptr, local.indices, vals[q], fd, fs, r, local.num_edges(),
+                                               kk, d, split=split, wait=(w.local, world, q, r, 8000))
+                peer.join_push(w)
+                outs.append((out, fd.clone(), fs.clone(), fi.clone()))
+                peer.release(w)
+            torch.cuda.synchronize()
+            for q in range(world):
+                out, fd, fs, fi = outs[q]
+                local = shards[q][0]
+                split = mk.block_split(local.indptr, local.indices, r, world, q, r)
+                out_ref = mk.spgemm_forward_banked(local.indptr, local.indices, vals[q], want[0], want[1], r,
+                                                   local.num_edges(), kk, d, split=split)
+                good = (torch.equal(fd, want[0]) and torch.equal(fs, want[1]) and torch.equal(fi, want[2])
+                        and torch.equal(out, out_ref))
+                ep, err = wins[q].epoch()
+                good &= (ep == rnd + 1 and err == 0)
+                ok &= bool(good)
+            print(f"push + waiting forward k={kk} round {rnd}: {'OK' if ok else 'FAIL'}")
 
     # ---- reduce-scatter by loads: fixed rank order, so bit-equal to the same fold in torch
+    k, r = 32, 1000
+    rows = world * r
     offs1, total1 = peer.layout([rows * k * 4])
     wins1 = peer.PeerWindow.create_virtual(total1, world, dev)
     for rnd in range(3):
@@ -86,18 +105,17 @@ def virtual(world: int) -> int:
             v.copy_(torch.randn(rows, k, device=dev, generator=gen))
             parts.append(v.clone())
         torch.cuda.synchronize()
-        outs = []
-        for q in range(world):
-            with torch.cuda.stream(streams[q]):
-                outs.append(peer.reduce_scatter(wins1[q], offs1[0], r, k, grid=5))
+        outs = peer.reduce_scatter_virtual(wins1, offs1[0], r, k, grid=5)
         torch.cuda.synchronize()
         for q in range(world):
             acc = parts[0][q * r:(q + 1) * r].clone()
             for p in parts[1:]:
                 acc += p[q * r:(q + 1) * r]
             ok &= torch.equal(outs[q], acc)
+            ep, err = wins1[q].epoch()
+            ok &= (ep == rnd + 1 and err == 0)
         print(f"reduce_scatter round {rnd}: {'OK' if ok else 'FAIL'}")
-    for w in wins + wins3 + wins1:
+    for w in wins_all + wins1:
         w.close()
     print("virtual peer check:", "OK" if ok else "FAIL")
     return 0 if ok else 1
@@ -176,6 +194,11 @@ def distributed(bench: bool) -> int:
         torch.cuda.empty_cache()
     peer.set_enabled(False)
     torch.cuda.synchronize()
+    try:
+        peer.check_errors()
+    except peer.PeerTimeoutError as exc:
+        ok = False
+        print(f"rank {rank}: {exc}", flush=True)
     dist.barrier()
     peer.close_all()
     dist.destroy_process_group()
@@ -185,9 +208,6 @@ def distributed(bench: bool) -> int:
 
 
 if __name__ == "__main__":
-    if "--push-mode" in sys.argv:   # 2 = experimental "own table first, then block copies" bank_push
-        from spgemm_gnn_b200 import peer as _peer
-        _peer._PUSH_MODE = int(sys.argv[sys.argv.index("--push-mode") + 1])
     mode = sys.argv[1] if len(sys.argv) > 1 else "virtual"
     if mode == "virtual":
         sys.exit(virtual(int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 4))
