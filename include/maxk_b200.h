@@ -178,6 +178,19 @@ MK_API int mk_spgemm_fwd_banked_ex(const mk_part* parts, int64_t num_parts, int6
                                    float* partial, int64_t n_rows, int k, int d, const int32_t* split,
                                    const void* wait_window, int world, int rank, int64_t rows_per_rank,
                                    int timeout_ms, void* stream);
+/* Packed banked CBSR for k = 8, 16 (mk_packed_supported): one entry = {float value, uint16 cell,
+ * uint16 column} in 8 bytes, bk_pack [n, k] of them, so that a lane fetches value and cell offset with
+ * ONE load -- at these widths the forward is bound by L1 wavefronts per gathered row, and the separate
+ * value / offset arrays cost two.  Same result as mk_spgemm_fwd; arguments as mk_spgemm_fwd_banked_ex. */
+MK_API int mk_packed_supported(int k, int d);
+MK_API int mk_cbsr_bank_packed(const float* sp_data, const void* sp_index, int index_bytes,
+                               void* bk_pack, int64_t n, int k, int d, void* stream);
+MK_API int mk_spgemm_fwd_packed_ex(const mk_part* parts, int64_t num_parts, int64_t num_slots,
+                                   const mk_part* exec_parts, const int32_t* idx, const float* val,
+                                   const void* bk_pack, float* out, float* partial, int64_t n_rows,
+                                   int k, int d, const int32_t* split, const void* wait_window,
+                                   int world, int rank, int64_t rows_per_rank, int timeout_ms,
+                                   void* stream);
 MK_API int mk_sspmm_bwd_banked(const mk_part* parts, int64_t num_parts, const int32_t* idx,
                                const float* val, const float* dy, const uint16_t* bk_slot,
                                float* dxs, int64_t n_rows, int64_t n_src, int k, int d, void* stream);

@@ -40,6 +40,10 @@ SIGNATURES = {
     "mk_spgemm_fwd_banked": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "mk_spgemm_fwd_banked_ex": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
                                        _vp, _vp, _i32, _i32, _i64, _i32, _vp]),
+    "mk_packed_supported": (_i32, [_i32, _i32]),
+    "mk_cbsr_bank_packed": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, _i32, _vp]),
+    "mk_spgemm_fwd_packed_ex": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
+                                       _vp, _vp, _i32, _i32, _i64, _i32, _vp]),
     "mk_sspmm_bwd_banked": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     "mk_peer_alloc": (_i32, [_i64, ctypes.POINTER(_vp)]),
     "mk_peer_free": (_i32, [_vp]),

@@ -49,7 +49,7 @@ template <int K, typename IdxT>
 __global__ void __launch_bounds__(128)
 cbsr_bank_kernel(const float* __restrict__ sp_data, const IdxT* __restrict__ sp_index,
                  float* __restrict__ bk_data, IdxT* __restrict__ bk_index,
-                 uint16_t* __restrict__ bk_slot, int64_t n, int d) {
+                 uint16_t* __restrict__ bk_slot, uint2* __restrict__ bk_pack, int64_t n, int d) {
     using Mask = typename BankMask<K>::type;
     constexpr int CAP = K / 8;  // entries per bank when perfectly balanced == steps per neighbour
     constexpr int DSTRIDE = K + 4;
@@ -172,9 +172,14 @@ cbsr_bank_kernel(const float* __restrict__ sp_data, const IdxT* __restrict__ sp_
                     const int p = dsc & 0x7f;
                     const uint16_t cell =
                         static_cast<uint16_t>((dsc & 0x80) ? bank_slot_b(c, ra) : bank_slot_a(c));
-                    bk_data[grow * K + p] = vv[q][j];
-                    bk_slot[grow * K + p] = cell;
-                    if (bk_index) bk_index[grow * K + p] = static_cast<IdxT>(c);
+                    if (bk_pack != nullptr) {  // packed form: value, cell and column of an entry in 8 bytes
+                        bk_pack[grow * K + p] = make_uint2(__float_as_uint(vv[q][j]),
+                                                           static_cast<uint32_t>(cell) | (static_cast<uint32_t>(c) << 16));
+                    } else {
+                        bk_data[grow * K + p] = vv[q][j];
+                        bk_slot[grow * K + p] = cell;
+                        if (bk_index) bk_index[grow * K + p] = static_cast<IdxT>(c);
+                    }
                 }
             }
         }
@@ -183,17 +188,17 @@ cbsr_bank_kernel(const float* __restrict__ sp_data, const IdxT* __restrict__ sp_
 
 template <typename IdxT>
 static int launch_bank(const float* sp_data, const void* sp_index, float* bk_data, void* bk_index,
-                       uint16_t* bk_slot, int64_t n, int k, int d, cudaStream_t st) {
+                       uint16_t* bk_slot, uint2* bk_pack, int64_t n, int k, int d, cudaStream_t st) {
     const int64_t blocks = (n + 127) / 128;
     if (blocks > 0x7fffffffLL) return MK_EUNSUPPORTED;
     const IdxT* si = static_cast<const IdxT*>(sp_index);
     IdxT* bi = static_cast<IdxT*>(bk_index);
     const unsigned nb = static_cast<unsigned>(blocks);
     switch (k) {
-        case 8: cbsr_bank_kernel<8, IdxT><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d); break;
-        case 16: cbsr_bank_kernel<16, IdxT><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d); break;
-        case 32: cbsr_bank_kernel<32, IdxT><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d); break;
-        case 64: cbsr_bank_kernel<64, IdxT><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, n, d); break;
+        case 8: cbsr_bank_kernel<8, IdxT><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, bk_pack, n, d); break;
+        case 16: cbsr_bank_kernel<16, IdxT><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, bk_pack, n, d); break;
+        case 32: cbsr_bank_kernel<32, IdxT><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, bk_pack, n, d); break;
+        case 64: cbsr_bank_kernel<64, IdxT><<<nb, 128, 0, st>>>(sp_data, si, bk_data, bi, bk_slot, bk_pack, n, d); break;
         default: return MK_EUNSUPPORTED;
     }
     MK_LAUNCH_CHECK("cbsr_bank_kernel");
@@ -219,6 +224,23 @@ extern "C" int mk_cbsr_bank(const float* sp_data, const void* sp_index, int inde
     if (!sp_data || !sp_index || !bk_data || !bk_slot) return MK_EINVAL;
     cudaStream_t st = mk::as_stream(stream);
     return index_bytes == 1
-               ? mk::launch_bank<uint8_t>(sp_data, sp_index, bk_data, bk_index, bk_slot, n, k, d, st)
-               : mk::launch_bank<uint16_t>(sp_data, sp_index, bk_data, bk_index, bk_slot, n, k, d, st);
+               ? mk::launch_bank<uint8_t>(sp_data, sp_index, bk_data, bk_index, bk_slot, nullptr, n, k, d, st)
+               : mk::launch_bank<uint16_t>(sp_data, sp_index, bk_data, bk_index, bk_slot, nullptr, n, k, d, st);
+}
+
+extern "C" int mk_packed_supported(int k, int d) { return (k == 8 || k == 16) && mk_banked_supported(k, d) ? 1 : 0; }
+
+extern "C" int mk_cbsr_bank_packed(const float* sp_data, const void* sp_index, int index_bytes,
+                                   void* bk_pack, int64_t n, int k, int d, void* stream) {
+    if (n < 0 || d < 1 || k < 1 || k > d) return MK_EINVAL;
+    if (index_bytes != 1 && index_bytes != 2) return MK_EINVAL;
+    if ((index_bytes == 1 && d > 256)) return MK_EINVAL;
+    if (!mk_packed_supported(k, d)) return MK_EUNSUPPORTED;
+    if (n == 0) return MK_OK;
+    if (!sp_data || !sp_index || !bk_pack || (reinterpret_cast<uintptr_t>(bk_pack) & 15)) return MK_EINVAL;
+    cudaStream_t st = mk::as_stream(stream);
+    uint2* bp = static_cast<uint2*>(bk_pack);
+    return index_bytes == 1
+               ? mk::launch_bank<uint8_t>(sp_data, sp_index, nullptr, nullptr, nullptr, bp, n, k, d, st)
+               : mk::launch_bank<uint16_t>(sp_data, sp_index, nullptr, nullptr, nullptr, bp, n, k, d, st);
 }

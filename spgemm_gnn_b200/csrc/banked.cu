@@ -115,6 +115,36 @@ struct BankedLoad<8, CG> {
     }
 };
 
+// Packed form (k = 8, 16): one entry = {value bits, cell | column << 16} in 8 bytes, a lane's CAP
+// entries in ONE load.  At these widths the two-array form pays a full L1 wavefront for a 32-byte
+// row of values and another for 8-16 bytes of offsets (the sectors are fetched whole anyway), and the
+// forward is bound by exactly those wavefronts; packing halves them without moving more bytes.
+template <int CAP, bool CG>
+struct PackedLoad;
+template <bool CG>
+struct PackedLoad<1, CG> {
+    static __device__ __forceinline__ void both(const uint2* p, float (&v)[1], int (&s)[1]) {
+        const uint2 q = ld_tab_u2<CG>(p);
+        v[0] = __uint_as_float(q.x); s[0] = q.y & 0xffff;
+    }
+};
+template <bool CG>
+struct PackedLoad<2, CG> {
+    static __device__ __forceinline__ void both(const uint2* p, float (&v)[2], int (&s)[2]) {
+        const uint4 q = ld_tab_u4<CG>(p);
+        v[0] = __uint_as_float(q.x); s[0] = q.y & 0xffff;
+        v[1] = __uint_as_float(q.z); s[1] = q.w & 0xffff;
+    }
+};
+template <int CAP, bool CG>
+struct PackedLoadAny {  // CAP > 2 is never packed; keeps the template instantiable
+    static __device__ __forceinline__ void both(const uint2*, float (&)[CAP], int (&)[CAP]) {}
+};
+template <bool CG>
+struct PackedLoadAny<1, CG> : PackedLoad<1, CG> {};
+template <bool CG>
+struct PackedLoadAny<2, CG> : PackedLoad<2, CG> {};
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -131,7 +161,7 @@ struct FwdWait {
 // >= rank*rows_per_rank.  A record then walks [split, end) first and [begin, split) second, i.e.
 // the source blocks in the order rank, rank+1, ..., world-1, 0, ..., rank-1 -- the order in which
 // mk_peer_bank_push makes them arrive.  The summation order of a row is fixed either way.
-template <int K, int U, bool WAIT>
+template <int K, int U, bool WAIT, bool PACKED = false>
 __global__ void __launch_bounds__(32)
 spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
                          const float* __restrict__ val, const float* __restrict__ bk_data,
@@ -203,8 +233,12 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
                     ok[u] = e < n_here;
                     if (ok[u]) {
                         const int64_t off = static_cast<int64_t>(nz) * K + CAP * t;
-                        BankedLoad<CAP, WAIT>::data(bk_data + off, dv[u]);
-                        BankedLoad<CAP, WAIT>::slots(bk_slot + off, sl[u]);
+                        if (PACKED) {  // bk_data is the packed table
+                            PackedLoadAny<CAP, WAIT>::both(reinterpret_cast<const uint2*>(bk_data) + off, dv[u], sl[u]);
+                        } else {
+                            BankedLoad<CAP, WAIT>::data(bk_data + off, dv[u]);
+                            BankedLoad<CAP, WAIT>::slots(bk_slot + off, sl[u]);
+                        }
                     }
                 }
 #pragma unroll
@@ -348,7 +382,7 @@ sspmm_bwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restrict
     }
 }
 
-template <int K>
+template <int K, bool PACKED>
 static int launch_fwd_banked(const mk_part* parts, int64_t num_parts, const int* idx,
                              const float* val, const float* bk_data, const uint16_t* bk_slot,
                              float* out, float* partial, int d, int rows, const int* split,
@@ -360,14 +394,14 @@ static int launch_fwd_banked(const mk_part* parts, int64_t num_parts, const int*
 #endif
     const size_t smem = static_cast<size_t>(32) * rows * 4;
     if (fw.hdr != nullptr) {
-        auto kern = spgemm_fwd_banked_kernel<K, U, true>;
+        auto kern = spgemm_fwd_banked_kernel<K, U, true, PACKED>;
         if (smem > 48 * 1024)
             MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem)));
         kern<<<static_cast<unsigned>(num_parts), 32, smem, st>>>(parts, idx, val, bk_data, bk_slot, out,
                                                                  partial, d, rows, split, fw);
     } else {
-        auto kern = spgemm_fwd_banked_kernel<K, U, false>;
+        auto kern = spgemm_fwd_banked_kernel<K, U, false, PACKED>;
         if (smem > 48 * 1024)
             MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem)));
@@ -403,14 +437,13 @@ extern "C" int mk_banked_supported(int k, int d);
 extern "C" int mk_banked_rows(int d);
 extern "C" int mk_peer_wait_all(void* window, int world, int timeout_ms, void* stream);
 
-extern "C" int mk_spgemm_fwd_banked_ex(const mk_part* parts, int64_t num_parts, int64_t num_slots,
-                                       const mk_part* exec_parts, const int32_t* idx, const float* val,
-                                       const float* bk_data, const uint16_t* bk_slot, float* out,
-                                       float* partial, int64_t n_rows, int k, int d,
-                                       const int32_t* split, const void* wait_window, int world,
-                                       int rank, int64_t rows_per_rank, int timeout_ms, void* stream) {
+static int fwd_banked_any(bool packed, const mk_part* parts, int64_t num_parts, int64_t num_slots,
+                         const mk_part* exec_parts, const int32_t* idx, const float* val,
+                         const float* bk_data, const uint16_t* bk_slot, float* out, float* partial,
+                         int64_t n_rows, int k, int d, const int32_t* split, const void* wait_window,
+                         int world, int rank, int64_t rows_per_rank, int timeout_ms, void* stream) {
     if (n_rows < 0 || num_parts < 0 || num_slots < 0 || d < 1 || k < 1 || k > d) return MK_EINVAL;
-    if (!mk_banked_supported(k, d)) return MK_EUNSUPPORTED;
+    if (!mk_banked_supported(k, d) || (packed && k > 16)) return MK_EUNSUPPORTED;
     if (wait_window != nullptr &&
         (world < 1 || world > mk::kMaxPeers || rank < 0 || rank >= world || rows_per_rank < 1 ||
          rows_per_rank > 0x7fffffffLL))
@@ -420,7 +453,7 @@ extern "C" int mk_spgemm_fwd_banked_ex(const mk_part* parts, int64_t num_parts, 
         if (wait_window != nullptr) return mk_peer_wait_all(const_cast<void*>(wait_window), world, timeout_ms, stream);
         return MK_OK;
     }
-    if (!parts || !out || !bk_data || !bk_slot) return MK_EINVAL;
+    if (!parts || !out || !bk_data || (!packed && !bk_slot)) return MK_EINVAL;
     if (num_slots > 0 && !partial) return MK_EINVAL;
     if (num_parts > 0x7fffffffLL) return MK_EUNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(out) % 16 || reinterpret_cast<uintptr_t>(bk_data) % 16 ||
@@ -436,15 +469,41 @@ extern "C" int mk_spgemm_fwd_banked_ex(const mk_part* parts, int64_t num_parts, 
     const mk_part* ex = exec_parts ? exec_parts : parts;
     const int rows = mk_banked_rows(d);
     int rc;
-    switch (k) {
-        case 8: rc = mk::launch_fwd_banked<8>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, st); break;
-        case 16: rc = mk::launch_fwd_banked<16>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, st); break;
-        case 32: rc = mk::launch_fwd_banked<32>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, st); break;
-        default: rc = mk::launch_fwd_banked<64>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, st); break;
+    if (packed) {
+        rc = k == 8 ? mk::launch_fwd_banked<8, true>(ex, num_parts, idx, val, bk_data, nullptr, out, partial, d, rows, split, fw, st)
+                    : mk::launch_fwd_banked<16, true>(ex, num_parts, idx, val, bk_data, nullptr, out, partial, d, rows, split, fw, st);
+    } else {
+        switch (k) {
+            case 8: rc = mk::launch_fwd_banked<8, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, st); break;
+            case 16: rc = mk::launch_fwd_banked<16, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, st); break;
+            case 32: rc = mk::launch_fwd_banked<32, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, st); break;
+            default: rc = mk::launch_fwd_banked<64, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, st); break;
+        }
     }
     if (rc != MK_OK) return rc;
     if (num_slots > 0) return mk::launch_fold(parts, num_parts, partial, out, d, st);
     return MK_OK;
+}
+
+extern "C" int mk_spgemm_fwd_banked_ex(const mk_part* parts, int64_t num_parts, int64_t num_slots,
+                                       const mk_part* exec_parts, const int32_t* idx, const float* val,
+                                       const float* bk_data, const uint16_t* bk_slot, float* out,
+                                       float* partial, int64_t n_rows, int k, int d,
+                                       const int32_t* split, const void* wait_window, int world,
+                                       int rank, int64_t rows_per_rank, int timeout_ms, void* stream) {
+    return fwd_banked_any(false, parts, num_parts, num_slots, exec_parts, idx, val, bk_data, bk_slot, out,
+                          partial, n_rows, k, d, split, wait_window, world, rank, rows_per_rank, timeout_ms, stream);
+}
+
+extern "C" int mk_spgemm_fwd_packed_ex(const mk_part* parts, int64_t num_parts, int64_t num_slots,
+                                       const mk_part* exec_parts, const int32_t* idx, const float* val,
+                                       const void* bk_pack, float* out, float* partial, int64_t n_rows,
+                                       int k, int d, const int32_t* split, const void* wait_window,
+                                       int world, int rank, int64_t rows_per_rank, int timeout_ms,
+                                       void* stream) {
+    return fwd_banked_any(true, parts, num_parts, num_slots, exec_parts, idx, val,
+                          static_cast<const float*>(bk_pack), nullptr, out, partial, n_rows, k, d, split,
+                          wait_window, world, rank, rows_per_rank, timeout_ms, stream);
 }
 
 extern "C" int mk_spgemm_fwd_banked(const mk_part* parts, int64_t num_parts, int64_t num_slots,

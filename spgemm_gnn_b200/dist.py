@@ -177,50 +177,65 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     part = maxk_kernels.partition(ptr, num_rows)
-    banked = maxk_kernels.use_banked(part.num_parts, idx.numel(), k, dim_origin)
+    e = idx.numel()
+    form = ("banked" if maxk_kernels.use_banked(part.num_parts, e, k, dim_origin) else
+            "packed" if maxk_kernels.use_packed(part.num_parts, e, k, dim_origin) else "plain")
     # every record walks the source blocks own, rank+1, ..., rank-1: one fixed summation order for the
     # peer form and the NCCL form (their forwards are bit-equal)
-    split = maxk_kernels.block_split(ptr, idx, num_rows, world, rank, r) if (banked and sp_data.is_cuda) else None
+    split = (maxk_kernels.block_split(ptr, idx, num_rows, world, rank, r)
+             if (form != "plain" and sp_data.is_cuda) else None)
     if _peer_path(group, r * k * 4):
         rows = world * r
-        per_rank = [r * k * 4, r * k * 2, r * k * ib] if banked else [r * k * 4, r * k * ib]
+        per_rank = {"banked": [r * k * 4, r * k * 2, r * k * ib], "packed": [r * k * 8, r * k * ib],
+                    "plain": [r * k * 4, r * k * ib]}[form]
         offs, total = peer.layout([world * b for b in per_rank] * 2)        # two table buffers
-        win = peer.window("table_banked" if banked else "table_plain", total, group)
+        win = peer.window("table_" + form, total, group)
         if win is not None:
             buf = win.next_buffer()
             o = offs[len(per_rank) * buf: len(per_rank) * (buf + 1)]
             mine = slice(rank * r, (rank + 1) * r)
+            wait = (win.local, world, rank, r, peer.timeout_ms())
             peer.begin_push(win, buf)
-            full_data = win.view(o[0], (rows, k), torch.float32)
             full_index = win.view(o[-1], (rows, k), sp_index.dtype)
             full_index[mine].copy_(sp_index)
-            if banked:
+            if form == "banked":
+                full_data = win.view(o[0], (rows, k), torch.float32)
                 full_slot = win.view(o[1], (rows, k), torch.int16)
                 maxk_kernels.cbsr_bank(sp_data, sp_index, dim_origin, with_index=False,
                                        out=(full_data[mine], full_slot[mine]))
                 peer.publish_and_push(win, buf, o, per_rank)
-                out = maxk_kernels.spgemm_forward_banked(
-                    ptr, idx, val, full_data, full_slot, num_rows, idx.numel(), k, dim_origin, split=split,
-                    wait=(win.local, world, rank, r, peer.timeout_ms()))
+                out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, full_data, full_slot, num_rows, e, k,
+                                                         dim_origin, split=split, wait=wait)
+            elif form == "packed":
+                full_pack = win.view(o[0], (rows, k, 2), torch.int32)
+                maxk_kernels.cbsr_bank_packed(sp_data, sp_index, dim_origin, out=full_pack[mine])
+                peer.publish_and_push(win, buf, o, per_rank)
+                out = maxk_kernels.spgemm_forward_packed(ptr, idx, val, full_pack, num_rows, e, k, dim_origin,
+                                                         split=split, wait=wait)
             else:
+                full_data = win.view(o[0], (rows, k), torch.float32)
                 full_data[mine].copy_(sp_data)
                 peer.publish_and_push(win, buf, o, per_rank)
                 peer.wait_all(win)
-                out, _ = maxk_kernels.spgemm_forward(ptr, idx, val, full_data, full_index, num_rows,
-                                                     idx.numel(), k, dim_origin, allow_banked=False)
+                out, _ = maxk_kernels.spgemm_forward(ptr, idx, val, full_data, full_index, num_rows, e, k,
+                                                     dim_origin, allow_banked=False)
             peer.join_push(win)
             kept = full_index.clone() if keep_index else full_index
             peer.release(win)
             return out, kept
-    if banked:
+    if form == "banked":
         bk_data, _, bk_slot = maxk_kernels.cbsr_bank(sp_data, sp_index, dim_origin, with_index=False)
         full_data, full_slot, full_index = allgather_many([bk_data, bk_slot, sp_index], group)
-        out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, full_data, full_slot, num_rows,
-                                                 idx.numel(), k, dim_origin, split=split)
+        out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, full_data, full_slot, num_rows, e, k,
+                                                 dim_origin, split=split)
+    elif form == "packed":
+        bk_pack = maxk_kernels.cbsr_bank_packed(sp_data, sp_index, dim_origin)
+        full_pack, full_index = allgather_many([bk_pack, sp_index], group)
+        out = maxk_kernels.spgemm_forward_packed(ptr, idx, val, full_pack, num_rows, e, k, dim_origin, split=split)
     else:
         full_data, full_index = allgather_many([sp_data, sp_index], group)
-        out, _ = maxk_kernels.spgemm_forward(ptr, idx, val, full_data, full_index, num_rows,
-                                             idx.numel(), k, dim_origin, allow_banked=False)
+        out, _ = maxk_kernels.spgemm_forward(ptr, idx, val, full_data, full_index, num_rows, e, k,
+                                             dim_origin, allow_banked=False)
     return out, full_index
 
 

@@ -32,7 +32,8 @@ __all__ = [
     "maxk_forward", "maxk_backward", "spgemm_forward", "spgemm_backward",
     "maxk_forward_cbsr", "cbsr_scatter", "cbsr_gather", "partition",
     "clear_partition_cache", "install_partition", "set_max_nz", "get_max_nz", "launch_count",
-    "banked_supported", "cbsr_bank", "block_split", "maxk_forward_banked", "spgemm_forward_banked",
+    "banked_supported", "cbsr_bank", "block_split", "packed_supported", "cbsr_bank_packed",
+    "spgemm_forward_packed", "use_packed", "maxk_forward_banked", "spgemm_forward_banked",
     "spgemm_backward_banked", "set_banked", "set_backward_tma", "use_banked", "forward_variant", "partition_blocked", "backward_blocks",
     "set_backward_block_mb", "add_layernorm_supported", "add_layernorm_forward", "layernorm_backward",
 ]
@@ -46,6 +47,7 @@ _BWD_MAX_NZ = int(os.environ.get("MAXK_BWD_MAX_NZ", "0"))      # 0: same as the 
 _EXEC_SORTED = os.environ.get("MAXK_EXEC_ORDER", "1") != "0"
 _BANKED = os.environ.get("MAXK_BANKED", "1") != "0"
 _BANKED_MIN_RECORD = 96   # mean stored entries per work record below which banking does not pay
+_PACKED = os.environ.get("MAXK_PACKED", "1") != "0"   # k = 8, 16: banked + packed 8-byte entries
 # experimental backward: this many of the 4 neighbours of a warp step (k = 32) reduce through the TMA
 # unit (csrc/sspmm_bwd.cu, mk_sspmm_bwd_tma; measured slower); 0 = the shipped kernel
 _BWD_TMA = int(os.environ.get("MAXK_BWD_TMA", "0"))
@@ -90,10 +92,18 @@ def use_banked(num_parts: int, num_edges: int, dim_sparse: int, dim_origin: int)
             and num_edges >= _BANKED_MIN_RECORD * max(num_parts, 1))
 
 
+def use_packed(num_parts: int, num_edges: int, dim_sparse: int, dim_origin: int) -> bool:
+    """k = 8, 16 on long records: the banked forward on the packed table (8-byte entries)."""
+    return (_BANKED and _PACKED and dim_sparse in (8, 16) and packed_supported(dim_sparse, dim_origin)
+            and num_edges >= _BANKED_MIN_RECORD * max(num_parts, 1))
+
+
 def forward_variant(num_parts: int, num_edges: int, dim_sparse: int, dim_origin: int) -> str:
     """Which forward `spgemm_forward` runs for this shape (reported by bench.py)."""
     if use_banked(num_parts, num_edges, dim_sparse, dim_origin):
         return "banked (mk_cbsr_bank + mk_spgemm_fwd_banked, both inside the forward time)"
+    if use_packed(num_parts, num_edges, dim_sparse, dim_origin):
+        return "packed banked (mk_cbsr_bank_packed + mk_spgemm_fwd_packed, both inside the forward time)"
     return "plain (mk_spgemm_fwd)"
 
 
@@ -223,15 +233,28 @@ class _Partition:
     __slots__ = ("parts", "num_parts", "num_slots", "max_nz", "partial", "ptr_ref", "version", "_exec")
 
     def exec_parts(self) -> torch.Tensor:
-        """The records in the order the CTAs take them: longest first (stable, so equal lengths keep
-        their row order), or the row order itself with MAXK_EXEC_ORDER=0."""
+        """The records in the order the CTAs take them.  Long records (mean >= 96 stored entries):
+        longest first (stable), so that the grid drains on the shortest records instead of on a
+        straggling max_nz one -- Reddit shape: forward 2.89 -> 2.83 ms, on an 8-way shard 0.427 ->
+        0.385 ms (profiles/r2/exec_order_call2.log).  Short records (products shape, mean 51): only the
+        heavy tail (> 8x the mean) moves to the front, the rest stays in row order, which is what keeps
+        the edge arrays and the dense rows streaming.  MAXK_EXEC_ORDER=0: row order."""
         ex = getattr(self, "_exec", None)
         if ex is None:
+            ex = self.parts
             if _EXEC_SORTED and self.num_parts > 1:
-                order = torch.argsort(self.parts[: self.num_parts, 2], descending=True, stable=True)
-                ex = self.parts[order].contiguous()
-            else:
-                ex = self.parts
+                lens = self.parts[: self.num_parts, 2]
+                mean = float(lens.sum().item()) / self.num_parts
+                if mean >= 96:
+                    order = torch.argsort(lens, descending=True, stable=True)
+                    ex = self.parts[order].contiguous()
+                else:
+                    heavy = lens > max(8.0 * mean, 128.0)
+                    hi = heavy.nonzero().squeeze(1)
+                    if hi.numel() > 0:
+                        hi = hi[torch.argsort(lens[hi], descending=True, stable=True)]
+                        order = torch.cat([hi, (~heavy).nonzero().squeeze(1)])
+                        ex = self.parts[order].contiguous()
             self._exec = ex
         return ex
 
@@ -418,6 +441,10 @@ def spgemm_forward(ptr, idx, val, sp_data, sp_index, num_nodes, num_edges, dim_s
         out = spgemm_forward_banked(ptr, idx, val, bk_data, bk_slot, num_nodes, num_edges,
                                     dim_sparse, dim_origin)
         return out, sp_index
+    if allow_banked and use_packed(part.num_parts, num_edges, dim_sparse, dim_origin):
+        bk_pack = cbsr_bank_packed(sp_data, sp_index, dim_origin)
+        out = spgemm_forward_packed(ptr, idx, val, bk_pack, num_nodes, num_edges, dim_sparse, dim_origin)
+        return out, sp_index
     out = torch.empty((num_nodes, dim_origin), dtype=torch.float32, device=sp_data.device)
     partial = part.partial_for(dim_origin, sp_data.device)
     with torch.cuda.device(sp_data.device):
@@ -582,6 +609,63 @@ def spgemm_forward_banked(ptr, idx, val, bk_data, bk_slot, num_nodes, num_edges,
             split.data_ptr() if split is not None else None, w_ptr, int(w_world), int(w_rank),
             int(w_rows), int(w_tmo), _stream())
     _lib.check(rc, "mk_spgemm_fwd_banked_ex")
+    _launches += 1 + (1 if part.num_slots else 0)
+    return out
+
+
+def packed_supported(k: int, dim_origin: int) -> bool:
+    return bool(_lib.lib().mk_packed_supported(int(k), int(dim_origin)))
+
+
+def cbsr_bank_packed(sp_data: torch.Tensor, sp_index: torch.Tensor, dim_origin: int, *, out=None) -> torch.Tensor:
+    """(sp_data, sp_index) -> bk_pack int32 [n, k, 2]: the banked row with value bits, cell offset and
+    column of every entry in 8 bytes (k = 8, 16).  `out`: write into this buffer (rows of a peer window)."""
+    global _launches
+    _cuda_contig(sp_data, "sp_data")
+    _cuda_contig(sp_index, "sp_index")
+    _chk(sp_data.dtype == torch.float32, "sp_data must be float32")
+    _chk(sp_data.dim() == 2 and sp_index.shape == sp_data.shape, "sp_index must have the shape of sp_data")
+    n, k = sp_data.shape
+    _chk(packed_supported(k, dim_origin), "packed CBSR needs k in {8,16}, dim % 8 == 0, dim <= 512")
+    ib = _index_bytes(sp_index, dim_origin)
+    if out is None:
+        out = torch.empty((n, k, 2), dtype=torch.int32, device=sp_data.device)
+    else:
+        _cuda_contig(out, "out")
+        _chk(out.dtype == torch.int32 and tuple(out.shape) == (n, k, 2), "out must be int32 [n, k, 2]")
+    with torch.cuda.device(sp_data.device):
+        rc = _lib.lib().mk_cbsr_bank_packed(sp_data.data_ptr(), sp_index.data_ptr(), ib, out.data_ptr(),
+                                            n, k, dim_origin, _stream())
+    _lib.check(rc, "mk_cbsr_bank_packed")
+    _launches += 1
+    return out
+
+
+def spgemm_forward_packed(ptr, idx, val, bk_pack, num_nodes, num_edges, dim_sparse, dim_origin,
+                          *, split: Optional[torch.Tensor] = None, wait=None):
+    """`spgemm_forward` on a packed banked table (k = 8, 16); `split` / `wait` as in
+    `spgemm_forward_banked`."""
+    global _launches
+    _check_graph(ptr, idx, val)
+    _cuda_contig(bk_pack, "sp_data")
+    _chk(bk_pack.dtype == torch.int32 and bk_pack.dim() == 3 and bk_pack.shape[1] == dim_sparse
+         and bk_pack.shape[2] == 2, "bk_pack must be int32 [n_src, dim_sparse, 2]")
+    if split is not None:
+        _cuda_contig(split, "split")
+        _chk(split.dtype == torch.int32 and split.numel() >= num_nodes, "split must be int32 [num_nodes]")
+    part = partition(ptr, num_nodes)
+    out = torch.empty((num_nodes, dim_origin), dtype=torch.float32, device=bk_pack.device)
+    partial = part.partial_for(dim_origin, bk_pack.device)
+    ex = part.exec_parts()
+    w_ptr, w_world, w_rank, w_rows, w_tmo = wait if wait is not None else (None, 1, 0, 1, 0)
+    with torch.cuda.device(bk_pack.device):
+        rc = _lib.lib().mk_spgemm_fwd_packed_ex(
+            part.parts.data_ptr(), part.num_parts, part.num_slots,
+            ex.data_ptr() if ex is not part.parts else None, idx.data_ptr(), val.data_ptr(),
+            bk_pack.data_ptr(), out.data_ptr(), partial.data_ptr() if partial is not None else None,
+            num_nodes, dim_sparse, dim_origin, split.data_ptr() if split is not None else None,
+            w_ptr, int(w_world), int(w_rank), int(w_rows), int(w_tmo), _stream())
+    _lib.check(rc, "mk_spgemm_fwd_packed_ex")
     _launches += 1 + (1 if part.num_slots else 0)
     return out
 

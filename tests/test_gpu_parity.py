@@ -768,3 +768,39 @@ def test_forward_arrival_order_walk_and_sorted_records(mk, k):
     finally:
         mk.set_max_nz(1024)
         mk.clear_partition_cache()
+
+
+@pytest.mark.parametrize("n,deg,d,k", [(1500, 150, 256, 8), (1500, 150, 256, 16), (800, 200, 128, 8),
+                                       (600, 180, 384, 16), (700, 120, 64, 16)])
+def test_packed_banked_forward_k8_k16(mk, n, deg, d, k):
+    """k = 8, 16 on long records go through the packed banked table (8-byte entries): the packed
+    table is the banked table re-encoded, and the forward meets the oracle at the 1e-5 bar; the
+    reference-named spgemm_forward takes that route by itself."""
+    from oracle import c_oracle
+    from conftest import small_graph
+    g = small_graph(n, deg, seed=k + d, device="cuda")
+    e = g.num_edges()
+    rng = np.random.default_rng(n + k)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x[7] = 0.0                                          # zero row: every entry skipped
+    val = g.edge_weights("mean")
+    sd, si = mk.maxk_forward_cbsr(dev(x), k)
+    assert mk.packed_supported(k, d)
+    pack = mk.cbsr_bank_packed(sd, si, d)
+    bd, bi, bs = mk.cbsr_bank(sd, si, d)
+    pk = pack.cpu().numpy().view(np.uint32)
+    assert np.array_equal(pk[:, :, 0], bd.cpu().numpy().view(np.uint32))
+    assert np.array_equal(pk[:, :, 1] & 0xffff, bs.cpu().numpy().view(np.uint16).astype(np.uint32))
+    assert np.array_equal(pk[:, :, 1] >> 16, _np_index(bi, d).astype(np.uint32))
+    out = mk.spgemm_forward_packed(g.indptr, g.indices, val, pack, n, e, k, d)
+    ptr, idx = g.indptr.cpu().numpy(), g.indices.cpu().numpy()
+    wd, wi = sd.cpu().numpy(), _np_index(si, d)
+    want = c_oracle.spgemm_fwd(ptr, idx, val.cpu().numpy(), wd, wi, d)
+    bound = c_oracle.spgemm_fwd(ptr, idx, np.abs(val.cpu().numpy()), np.abs(wd), wi, d)
+    assert_rel(out, want, bound, "packed banked forward")
+    part = mk.partition(g.indptr, n)
+    assert mk.use_packed(part.num_parts, e, k, d)
+    auto, _ = mk.spgemm_forward(g.indptr, g.indices, val, sd, si, n, e, k, d)
+    assert torch.equal(auto, out)
+    plain, _ = mk.spgemm_forward(g.indptr, g.indices, val, sd, si, n, e, k, d, allow_banked=False)
+    assert_rel(plain, want, bound, "plain forward")
