@@ -253,6 +253,12 @@ MK_API int mk_peer_begin_push(void* window, int world, int rank, int buffer, int
 MK_API int mk_peer_publish(void* window, int rank, int buffer, void* stream);
 MK_API int mk_peer_push(void* const* h_windows, int world, int rank, int n_seg,
                         const int64_t* h_offsets, const int64_t* h_bytes, void* stream);
+/* the steps first_step, first_step + step_stride, ... of mk_peer_push (step s sends to rank - s):
+ * several side streams, one call each, put several copy engines to work while every stream still
+ * visits its peers nearest first                                                                   */
+MK_API int mk_peer_push_steps(void* const* h_windows, int world, int rank, int n_seg,
+                              const int64_t* h_offsets, const int64_t* h_bytes, int first_step,
+                              int step_stride, void* stream);
 MK_API int mk_peer_wait_all(void* window, int world, int timeout_ms, void* stream);
 MK_API int mk_peer_release(void* const* h_windows, int world, int rank, void* stream);
 /* Reduce-scatter by loads (the backward): out[0 .. block_bytes/4) = sum over q (rank order, fixed) of

@@ -256,8 +256,19 @@ extern "C" int mk_peer_release(void* const* h_windows, int world, int rank, void
     return MK_OK;
 }
 
+extern "C" int mk_peer_push_steps(void* const* h_windows, int world, int rank, int n_seg,
+                                  const int64_t* h_offsets, const int64_t* h_bytes, int first_step,
+                                  int step_stride, void* stream);
+
 extern "C" int mk_peer_push(void* const* h_windows, int world, int rank, int n_seg,
                             const int64_t* h_offsets, const int64_t* h_bytes, void* stream) {
+    return mk_peer_push_steps(h_windows, world, rank, n_seg, h_offsets, h_bytes, 1, 1, stream);
+}
+
+extern "C" int mk_peer_push_steps(void* const* h_windows, int world, int rank, int n_seg,
+                                  const int64_t* h_offsets, const int64_t* h_bytes, int first_step,
+                                  int step_stride, void* stream) {
+    if (first_step < 1 || step_stride < 1) return MK_EINVAL;
     if (world < 1 || world > mk::kMaxPeers || rank < 0 || rank >= world || !h_windows) return MK_EINVAL;
     if (n_seg < 1 || n_seg > 8 || !h_offsets || !h_bytes) return MK_EINVAL;
     for (int q = 0; q < world; ++q)
@@ -266,7 +277,7 @@ extern "C" int mk_peer_push(void* const* h_windows, int world, int rank, int n_s
         if (h_bytes[g] < 0 || h_offsets[g] < MK_PEER_HEADER_BYTES) return MK_EINVAL;
     cudaStream_t st = mk::as_stream(stream);
     unsigned char* mine = static_cast<unsigned char*>(h_windows[rank]);
-    for (int s = 1; s < world; ++s) {
+    for (int s = first_step; s < world; s += step_stride) {
         unsigned char* dst = static_cast<unsigned char*>(h_windows[(rank - s + world) % world]);
         for (int g = 0; g < n_seg; ++g) {
             if (h_bytes[g] == 0) continue;

@@ -92,8 +92,10 @@ __device__ __forceinline__ bool wait_flag(const uint32_t* p, uint32_t e, uint32_
     if (static_cast<int32_t>(ld_acquire_sys(p) - e) >= 0) return true;
     if (*reinterpret_cast<volatile uint32_t*>(err) != 0u) return false;
     const uint64_t t0 = global_ns();
+    unsigned nap = 200;  // thousands of CTAs may wait for the same word: back off to one poll per ~4 us
     while (static_cast<int32_t>(ld_acquire_sys(p) - e) < 0) {
-        __nanosleep(100);
+        __nanosleep(nap);
+        if (nap < 4000) nap <<= 1;
         if (global_ns() - t0 > timeout_ns) {
             *reinterpret_cast<volatile uint32_t*>(err) = e ? e : 1u;
             __threadfence_system();

@@ -194,7 +194,7 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
             buf = win.next_buffer()
             o = offs[len(per_rank) * buf: len(per_rank) * (buf + 1)]
             mine = slice(rank * r, (rank + 1) * r)
-            wait = (win.local, world, rank, r, peer.timeout_ms())
+            wait = (win.local, world, rank, r, peer.timeout_ms()) if peer.overlap() else None
             peer.begin_push(win, buf)
             full_index = win.view(o[-1], (rows, k), sp_index.dtype)
             full_index[mine].copy_(sp_index)
@@ -204,12 +204,16 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
                 maxk_kernels.cbsr_bank(sp_data, sp_index, dim_origin, with_index=False,
                                        out=(full_data[mine], full_slot[mine]))
                 peer.publish_and_push(win, buf, o, per_rank)
+                if wait is None:
+                    peer.wait_all(win)
                 out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, full_data, full_slot, num_rows, e, k,
                                                          dim_origin, split=split, wait=wait)
             elif form == "packed":
                 full_pack = win.view(o[0], (rows, k, 2), torch.int32)
                 maxk_kernels.cbsr_bank_packed(sp_data, sp_index, dim_origin, out=full_pack[mine])
                 peer.publish_and_push(win, buf, o, per_rank)
+                if wait is None:
+                    peer.wait_all(win)
                 out = maxk_kernels.spgemm_forward_packed(ptr, idx, val, full_pack, num_rows, e, k, dim_origin,
                                                          split=split, wait=wait)
             else:

@@ -45,6 +45,12 @@ _ALIGN = 256
 
 _ENABLED = os.environ.get("MAXK_PEER_EXCHANGE", "1") != "0"   # "0": stay on NCCL collectives
 _TIMEOUT_MS = int(os.environ.get("MAXK_PEER_TIMEOUT_MS", "120000"))
+# side streams (copy engines) the pushes of one collective are spread over; every stream visits its
+# share of the peers nearest first
+_PUSH_STREAMS = max(1, int(os.environ.get("MAXK_PEER_STREAMS", "2")))
+# 1: the forward SpGEMM starts with the pushes and waits per source block; 0: it starts when the whole
+# table has arrived (mk_peer_wait_all)
+_OVERLAP = os.environ.get("MAXK_PEER_OVERLAP", "1") != "0"
 _launches = 0
 
 
@@ -67,6 +73,10 @@ def launch_count() -> int:
 
 def timeout_ms() -> int:
     return _TIMEOUT_MS
+
+
+def overlap() -> bool:
+    return _OVERLAP
 
 
 def available(group=None) -> bool:
@@ -196,12 +206,13 @@ class PeerWindow:
             raise ValueError("view outside the window payload")
         return self._bytes[offset:offset + nb].view(dtype).view(*shape)
 
-    def side_stream(self) -> torch.cuda.Stream:
+    def side_streams(self) -> List[torch.cuda.Stream]:
         if self._side is None:
             if torch.cuda.is_current_stream_capturing():
-                raise RuntimeError("the push stream must exist before CUDA graph capture (run one eager step first)")
+                raise RuntimeError("the push streams must exist before CUDA graph capture (run one eager step first)")
             with torch.cuda.device(self.device):
-                self._side = torch.cuda.Stream(device=self.device)
+                self._side = [torch.cuda.Stream(device=self.device)
+                              for _ in range(max(1, min(_PUSH_STREAMS, self.world - 1)))]
         return self._side
 
     def next_buffer(self) -> int:
@@ -284,23 +295,29 @@ def publish_and_push(win: PeerWindow, buf: int, offsets: Sequence[int], bytes_pe
     nbytes = (ctypes.c_int64 * n)(*[int(b) for b in bytes_per_rank])
     L = _lib.lib()
     main = torch.cuda.current_stream()
-    side = win.side_stream()
+    sides = win.side_streams()
     with torch.cuda.device(win.device):
         _lib.check(L.mk_peer_publish(win.local, win.rank, int(buf), main.cuda_stream), "mk_peer_publish")
         ev = torch.cuda.Event()
         ev.record(main)
-        side.wait_event(ev)
-        _lib.check(L.mk_peer_push(win.ptrs, win.world, win.rank, n, offs, nbytes, side.cuda_stream), "mk_peer_push")
-        win._pushed = torch.cuda.Event()
-        win._pushed.record(side)
+        win._pushed = []
+        for i, side in enumerate(sides):
+            side.wait_event(ev)
+            _lib.check(L.mk_peer_push_steps(win.ptrs, win.world, win.rank, n, offs, nbytes, 1 + i, len(sides),
+                                            side.cuda_stream), "mk_peer_push_steps")
+            done = torch.cuda.Event()
+            done.record(side)
+            win._pushed.append(done)
     _launches += 1
 
 
 def join_push(win: PeerWindow) -> None:
     """The current stream continues only after the window's pushes have left (joins the side stream;
     needed before the next producer touches the window, and before a CUDA graph capture ends)."""
-    if win._pushed is not None:
-        torch.cuda.current_stream().wait_event(win._pushed)
+    if win._pushed:
+        cur = torch.cuda.current_stream()
+        for ev in win._pushed:
+            cur.wait_event(ev)
         win._pushed = None
 
 
