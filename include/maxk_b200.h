@@ -162,22 +162,42 @@ MK_API int mk_spgemm_fwd_banked(const mk_part* parts, int64_t num_parts, int64_t
                                 const int32_t* idx, const float* val, const float* bk_data,
                                 const uint16_t* bk_slot, float* out, float* partial, int64_t n_rows,
                                 int k, int d, void* stream);
+/* The exchange a row-partitioned forward runs under (nullable everywhere it is taken).
+ *   window        this rank's window of the table that is still arriving: the kernel checks done[q]
+ *                 (peer.cuh) before it reads rows [q*rows_per_rank, (q+1)*rows_per_rank), and when it
+ *                 has finished the whole table has arrived;
+ *   h_windows     (nullable) every rank's window as mapped here, h_windows[rank] == window: the
+ *                 kernel ITSELF is the all-gather -- the first `pushers` CTAs to start copy this rank's
+ *                 rows of the n_seg table segments (rank r's part of segment g: h_bytes[g] bytes at
+ *                 h_offsets[g] + r*h_bytes[g] of every window, multiples of 16) to the peers rank-1,
+ *                 rank-2, ... over NVLink and raise done[rank] there, while the other CTAs already
+ *                 compute on the blocks that have arrived.  NULL: somebody else moves the rows
+ *                 (mk_peer_push, NCCL + a caller that raises the flags).                              */
+typedef struct mk_fwd_exchange {
+    const void* window;
+    int32_t world, rank;
+    int64_t rows_per_rank;
+    int32_t timeout_ms; /* <= 0: 30 s */
+    int32_t pushers;
+    void* const* h_windows;
+    int32_t n_seg;
+    const int64_t* h_offsets;
+    const int64_t* h_bytes;
+} mk_fwd_exchange;
+
 /* mk_spgemm_fwd_banked with the knobs of the row-partitioned and the load-balanced forms:
- *   exec_parts  (nullable) the same records in the order the CTAs should take them (peer.py /
- *               maxk_kernels.py sort them longest first, so that the grid drains on short records);
- *               `parts` stays in row order for the fold of the multi-record rows;
+ *   exec_parts  (nullable) the same records in the order the CTAs should take them (maxk_kernels.py
+ *               sorts them longest first, so that the grid drains on short records); `parts` stays in
+ *               row order for the fold of the multi-record rows;
  *   split       (nullable) int32 [n_rows]: position in idx of the first stored entry of the row whose
  *               column is >= rank * rows_per_rank; a record walks [split, end) first, [begin, split)
- *               second -- the order in which mk_peer_push lets the source blocks arrive;
- *   wait_window (nullable) this rank's window of the table that is still arriving: the kernel checks
- *               done[q] (peer.cuh) before it reads rows [q*rows_per_rank, (q+1)*rows_per_rank), and
- *               when it has finished the whole table has arrived.                                  */
+ *               second -- the order in which the source blocks arrive;
+ *   xchg        (nullable) see mk_fwd_exchange.                                                     */
 MK_API int mk_spgemm_fwd_banked_ex(const mk_part* parts, int64_t num_parts, int64_t num_slots,
                                    const mk_part* exec_parts, const int32_t* idx, const float* val,
                                    const float* bk_data, const uint16_t* bk_slot, float* out,
                                    float* partial, int64_t n_rows, int k, int d, const int32_t* split,
-                                   const void* wait_window, int world, int rank, int64_t rows_per_rank,
-                                   int timeout_ms, void* stream);
+                                   const mk_fwd_exchange* xchg, void* stream);
 /* Packed banked CBSR for k = 8, 16 (mk_packed_supported): one entry = {float value, uint16 cell,
  * uint16 column} in 8 bytes, bk_pack [n, k] of them, so that a lane fetches value and cell offset with
  * ONE load -- at these widths the forward is bound by L1 wavefronts per gathered row, and the separate
@@ -188,8 +208,7 @@ MK_API int mk_cbsr_bank_packed(const float* sp_data, const void* sp_index, int i
 MK_API int mk_spgemm_fwd_packed_ex(const mk_part* parts, int64_t num_parts, int64_t num_slots,
                                    const mk_part* exec_parts, const int32_t* idx, const float* val,
                                    const void* bk_pack, float* out, float* partial, int64_t n_rows,
-                                   int k, int d, const int32_t* split, const void* wait_window,
-                                   int world, int rank, int64_t rows_per_rank, int timeout_ms,
+                                   int k, int d, const int32_t* split, const mk_fwd_exchange* xchg,
                                    void* stream);
 MK_API int mk_sspmm_bwd_banked(const mk_part* parts, int64_t num_parts, const int32_t* idx,
                                const float* val, const float* dy, const uint16_t* bk_slot,
@@ -259,6 +278,10 @@ MK_API int mk_peer_push(void* const* h_windows, int world, int rank, int n_seg,
 MK_API int mk_peer_push_steps(void* const* h_windows, int world, int rank, int n_seg,
                               const int64_t* h_offsets, const int64_t* h_bytes, int first_step,
                               int step_stride, void* stream);
+/* the same all-gather by NVLink stores from `pushers` CTAs of 32 threads, as a kernel of its own (what
+ * the forward kernel's pusher CTAs do, mk_fwd_exchange): after mk_peer_publish, on the main stream    */
+MK_API int mk_peer_push_sm(void* const* h_windows, int world, int rank, int n_seg,
+                           const int64_t* h_offsets, const int64_t* h_bytes, int pushers, void* stream);
 MK_API int mk_peer_wait_all(void* window, int world, int timeout_ms, void* stream);
 MK_API int mk_peer_release(void* const* h_windows, int world, int rank, void* stream);
 /* Reduce-scatter by loads (the backward): out[0 .. block_bytes/4) = sum over q (rank order, fixed) of

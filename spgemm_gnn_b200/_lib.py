@@ -39,11 +39,11 @@ SIGNATURES = {
     "mk_cbsr_bank": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "mk_spgemm_fwd_banked": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "mk_spgemm_fwd_banked_ex": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
-                                       _vp, _vp, _i32, _i32, _i64, _i32, _vp]),
+                                       _vp, _vp, _vp]),
     "mk_packed_supported": (_i32, [_i32, _i32]),
     "mk_cbsr_bank_packed": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, _i32, _vp]),
     "mk_spgemm_fwd_packed_ex": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
-                                       _vp, _vp, _i32, _i32, _i64, _i32, _vp]),
+                                       _vp, _vp, _vp]),
     "mk_sspmm_bwd_banked": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     "mk_peer_alloc": (_i32, [_i64, ctypes.POINTER(_vp)]),
     "mk_peer_free": (_i32, [_vp]),
@@ -56,11 +56,21 @@ SIGNATURES = {
     "mk_peer_push": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp]),
     "mk_peer_push_steps": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i64),
                                   _i32, _i32, _vp]),
+    "mk_peer_push_sm": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i64),
+                               _i32, _vp]),
     "mk_peer_wait_all": (_i32, [_vp, _i32, _i32, _vp]),
     "mk_peer_release": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _vp]),
     "mk_peer_reduce_scatter": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _i64, _i64, _vp, _i32, _i32, _vp]),
     "mk_peer_reduce_scatter_virtual": (_i32, [ctypes.POINTER(_vp), _i32, _i64, _i64, ctypes.POINTER(_vp), _i32, _i32, _vp]),
 }
+
+class FwdExchange(ctypes.Structure):
+    """`mk_fwd_exchange` of include/maxk_b200.h."""
+    _fields_ = [("window", _vp), ("world", ctypes.c_int32), ("rank", ctypes.c_int32),
+                ("rows_per_rank", _i64), ("timeout_ms", ctypes.c_int32), ("pushers", ctypes.c_int32),
+                ("h_windows", ctypes.POINTER(_vp)), ("n_seg", ctypes.c_int32),
+                ("h_offsets", ctypes.POINTER(_i64)), ("h_bytes", ctypes.POINTER(_i64))]
+
 
 _lib = None
 

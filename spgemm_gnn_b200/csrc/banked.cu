@@ -155,6 +155,11 @@ struct FwdWait {
     int world, rank;
     int rows_per_rank;    // table rows [q*rows_per_rank, (q+1)*rows_per_rank) come from rank q
     uint64_t timeout_ns;
+    // The all-gather itself, fused into this kernel: the first `push.pushers` CTAs TO START copy this
+    // rank's rows to the peers (push_rows, peer.cuh).  They wait for nothing, so every rank's rows
+    // leave while its other CTAs already work on the blocks that have arrived.  pushers == 0:
+    // somebody else moves the rows (mk_peer_push_sm before the kernel, copy engines, NCCL).
+    PushDesc push;
 };
 
 // `split` (nullable): per CSR row, the position in idx of the first stored entry whose column is
@@ -173,13 +178,28 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
     const int lane = lane_id();
     const int g = lane >> 3;
     const int t = lane & 7;
-    const mk_part rec = parts[blockIdx.x];
-
-    // which source blocks have arrived (bit q); refreshed only while something is missing
-    unsigned have = 0xffffffffu;
+    // Role of this CTA.  With pushers, roles are handed out in the order the CTAs START (a ticket),
+    // not by block index: the first `pushers` CTAs that run move the rows, whatever order the
+    // hardware dispatches blocks in -- a waiting consumer can never keep a pusher off the machine.
+    int role = static_cast<int>(blockIdx.x);
     uint32_t epoch = 0;
     if (WAIT) {
         epoch = fw.hdr[kHdrEpoch];
+        if (fw.push.pushers > 0) {
+            if (lane == 0) role = static_cast<int>(atomicAdd(const_cast<uint32_t*>(fw.hdr) + kHdrTicket, 1u));
+            role = __shfl_sync(kFull, role, 0);
+            if (role < fw.push.pushers) {
+                push_rows(fw.push, role, epoch);
+                return;
+            }
+            role -= fw.push.pushers;
+        }
+    }
+    const mk_part rec = parts[role];
+
+    // which source blocks have arrived (bit q); refreshed only while something is missing
+    unsigned have = 0xffffffffu;
+    if (WAIT) {
         const bool there = lane >= fw.world ||
                            static_cast<int32_t>(ld_acquire_sys(fw.hdr + kHdrDone + lane) - epoch) >= 0;
         have = __ballot_sync(kFull, there);
@@ -257,7 +277,7 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
     __syncwarp();
     // the kernel's completion must mean "the whole table has arrived" (the backward reads the
     // gathered column ids after it): one CTA waits for every sender
-    if (WAIT && blockIdx.x == 0 && lane < fw.world)
+    if (WAIT && role == 0 && lane < fw.world)
         wait_flag(fw.hdr + kHdrDone + lane, epoch, const_cast<uint32_t*>(fw.hdr) + kHdrError, fw.timeout_ns);
 
     // ---- fold the 4 groups and the 2 copies.  Lane (s, b) sums, for row 4i+s, the cells of bank
@@ -398,8 +418,10 @@ static int launch_fwd_banked(const mk_part* parts, int64_t num_parts, const int*
         if (smem > 48 * 1024)
             MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem)));
-        kern<<<static_cast<unsigned>(num_parts), 32, smem, st>>>(parts, idx, val, bk_data, bk_slot, out,
-                                                                 partial, d, rows, split, fw);
+        const int64_t grid = num_parts + fw.push.pushers;
+        if (grid > 0x7fffffffLL) return MK_EUNSUPPORTED;
+        kern<<<static_cast<unsigned>(grid), 32, smem, st>>>(parts, idx, val, bk_data, bk_slot, out,
+                                                            partial, d, rows, split, fw);
     } else {
         auto kern = spgemm_fwd_banked_kernel<K, U, false, PACKED>;
         if (smem > 48 * 1024)
@@ -440,17 +462,31 @@ extern "C" int mk_peer_wait_all(void* window, int world, int timeout_ms, void* s
 static int fwd_banked_any(bool packed, const mk_part* parts, int64_t num_parts, int64_t num_slots,
                          const mk_part* exec_parts, const int32_t* idx, const float* val,
                          const float* bk_data, const uint16_t* bk_slot, float* out, float* partial,
-                         int64_t n_rows, int k, int d, const int32_t* split, const void* wait_window,
-                         int world, int rank, int64_t rows_per_rank, int timeout_ms, void* stream) {
+                         int64_t n_rows, int k, int d, const int32_t* split, const mk_fwd_exchange* x,
+                         void* stream) {
     if (n_rows < 0 || num_parts < 0 || num_slots < 0 || d < 1 || k < 1 || k > d) return MK_EINVAL;
     if (!mk_banked_supported(k, d) || (packed && k > 16)) return MK_EUNSUPPORTED;
-    if (wait_window != nullptr &&
-        (world < 1 || world > mk::kMaxPeers || rank < 0 || rank >= world || rows_per_rank < 1 ||
-         rows_per_rank > 0x7fffffffLL))
-        return MK_EINVAL;
-    if (n_rows == 0 || num_parts == 0) {
+    const bool waiting = x != nullptr && x->window != nullptr;
+    if (waiting) {
+        if (x->world < 1 || x->world > mk::kMaxPeers || x->rank < 0 || x->rank >= x->world ||
+            x->rows_per_rank < 1 || x->rows_per_rank > 0x7fffffffLL)
+            return MK_EINVAL;
+        if (x->h_windows != nullptr) {
+            if (x->n_seg < 1 || x->n_seg > 3 || !x->h_offsets || !x->h_bytes || x->pushers < 1 || x->pushers > 65535)
+                return MK_EINVAL;
+            for (int g = 0; g < x->n_seg; ++g)
+                if (x->h_bytes[g] < 0 || (x->h_bytes[g] & 15) || x->h_offsets[g] < MK_PEER_HEADER_BYTES ||
+                    (x->h_offsets[g] & 15))
+                    return MK_EINVAL;
+            for (int q = 0; q < x->world; ++q)
+                if (!x->h_windows[q] || (reinterpret_cast<uintptr_t>(x->h_windows[q]) & 15)) return MK_EINVAL;
+            if (x->h_windows[x->rank] != x->window) return MK_EINVAL;
+        }
+    }
+    const bool pushing = waiting && x->h_windows != nullptr && x->world > 1;
+    if ((n_rows == 0 || num_parts == 0) && !pushing) {
         // nothing to compute, but the collective's contract stands: return once the table is complete
-        if (wait_window != nullptr) return mk_peer_wait_all(const_cast<void*>(wait_window), world, timeout_ms, stream);
+        if (waiting) return mk_peer_wait_all(const_cast<void*>(x->window), x->world, x->timeout_ms, stream);
         return MK_OK;
     }
     if (!parts || !out || !bk_data || (!packed && !bk_slot)) return MK_EINVAL;
@@ -461,11 +497,24 @@ static int fwd_banked_any(bool packed, const mk_part* parts, int64_t num_parts, 
         return MK_EINVAL;
     cudaStream_t st = mk::as_stream(stream);
     mk::FwdWait fw{};
-    fw.hdr = static_cast<const uint32_t*>(wait_window);
-    fw.world = world;
-    fw.rank = rank;
-    fw.rows_per_rank = static_cast<int>(rows_per_rank);
-    fw.timeout_ns = static_cast<uint64_t>(timeout_ms > 0 ? timeout_ms : 30000) * 1000000ull;
+    if (waiting) {
+        fw.hdr = static_cast<const uint32_t*>(x->window);
+        fw.world = x->world;
+        fw.rank = x->rank;
+        fw.rows_per_rank = static_cast<int>(x->rows_per_rank);
+        fw.timeout_ns = static_cast<uint64_t>(x->timeout_ms > 0 ? x->timeout_ms : 30000) * 1000000ull;
+        if (pushing) {
+            for (int q = 0; q < x->world; ++q) fw.push.ps.win[q] = static_cast<unsigned char*>(x->h_windows[q]);
+            fw.push.world = x->world;
+            fw.push.rank = x->rank;
+            fw.push.nseg = x->n_seg;
+            for (int g = 0; g < x->n_seg; ++g) {
+                fw.push.off[g] = x->h_offsets[g];
+                fw.push.bytes[g] = x->h_bytes[g];
+            }
+            fw.push.pushers = x->pushers;
+        }
+    }
     const mk_part* ex = exec_parts ? exec_parts : parts;
     const int rows = mk_banked_rows(d);
     int rc;
@@ -489,21 +538,19 @@ extern "C" int mk_spgemm_fwd_banked_ex(const mk_part* parts, int64_t num_parts, 
                                        const mk_part* exec_parts, const int32_t* idx, const float* val,
                                        const float* bk_data, const uint16_t* bk_slot, float* out,
                                        float* partial, int64_t n_rows, int k, int d,
-                                       const int32_t* split, const void* wait_window, int world,
-                                       int rank, int64_t rows_per_rank, int timeout_ms, void* stream) {
+                                       const int32_t* split, const mk_fwd_exchange* xchg, void* stream) {
     return fwd_banked_any(false, parts, num_parts, num_slots, exec_parts, idx, val, bk_data, bk_slot, out,
-                          partial, n_rows, k, d, split, wait_window, world, rank, rows_per_rank, timeout_ms, stream);
+                          partial, n_rows, k, d, split, xchg, stream);
 }
 
 extern "C" int mk_spgemm_fwd_packed_ex(const mk_part* parts, int64_t num_parts, int64_t num_slots,
                                        const mk_part* exec_parts, const int32_t* idx, const float* val,
                                        const void* bk_pack, float* out, float* partial, int64_t n_rows,
-                                       int k, int d, const int32_t* split, const void* wait_window,
-                                       int world, int rank, int64_t rows_per_rank, int timeout_ms,
+                                       int k, int d, const int32_t* split, const mk_fwd_exchange* xchg,
                                        void* stream) {
     return fwd_banked_any(true, parts, num_parts, num_slots, exec_parts, idx, val,
                           static_cast<const float*>(bk_pack), nullptr, out, partial, n_rows, k, d, split,
-                          wait_window, world, rank, rows_per_rank, timeout_ms, stream);
+                          xchg, stream);
 }
 
 extern "C" int mk_spgemm_fwd_banked(const mk_part* parts, int64_t num_parts, int64_t num_slots,
@@ -511,7 +558,7 @@ extern "C" int mk_spgemm_fwd_banked(const mk_part* parts, int64_t num_parts, int
                                     const uint16_t* bk_slot, float* out, float* partial,
                                     int64_t n_rows, int k, int d, void* stream) {
     return mk_spgemm_fwd_banked_ex(parts, num_parts, num_slots, nullptr, idx, val, bk_data, bk_slot, out,
-                                   partial, n_rows, k, d, nullptr, nullptr, 1, 0, 1, 0, stream);
+                                   partial, n_rows, k, d, nullptr, nullptr, stream);
 }
 
 extern "C" int mk_sspmm_bwd_banked(const mk_part* parts, int64_t num_parts, const int32_t* idx,

@@ -57,6 +57,7 @@ __global__ void peer_publish_kernel(uint32_t* hdr, int rank, int buf) {
     const uint32_t e = hdr[kHdrEpoch] + 1u;
     hdr[kHdrSig] = e;
     hdr[kHdrLastUse + buf] = e;
+    hdr[kHdrTicket] = 0u;  // role tickets of the forward kernel that pushes and consumes this collective
     st_release_sys(hdr + kHdrDone + rank, e);
     hdr[kHdrEpoch] = e;
 }
@@ -72,6 +73,12 @@ __global__ void peer_release_kernel(const PeerSet ps, int world, int rank) {
 __global__ void peer_wait_all_kernel(uint32_t* hdr, int world, uint64_t timeout_ns) {
     const uint32_t e = hdr[kHdrEpoch];
     if (threadIdx.x < world) wait_flag(hdr + kHdrDone + threadIdx.x, e, hdr + kHdrError, timeout_ns);
+}
+
+// The all-gather as a kernel of its own (consumers that cannot wait per block; tests).
+__global__ void __launch_bounds__(32) peer_push_sm_kernel(const PushDesc pd) {
+    const uint32_t e = peer_hdr(pd.ps, pd.rank)[kHdrEpoch];
+    push_rows(pd, static_cast<int>(blockIdx.x), e);
 }
 
 struct OutSet {
@@ -289,6 +296,30 @@ extern "C" int mk_peer_push_steps(void* const* h_windows, int world, int rank, i
         MK_CUDA_TRY(cudaMemcpyAsync(dst + 4 * (mk::kHdrDone + rank), mine + 4 * mk::kHdrSig, 4,
                                     cudaMemcpyDeviceToDevice, st));
     }
+    return MK_OK;
+}
+
+extern "C" int mk_peer_push_sm(void* const* h_windows, int world, int rank, int n_seg,
+                               const int64_t* h_offsets, const int64_t* h_bytes, int pushers, void* stream) {
+    mk::PeerSet ps;
+    const int rc = mk::fill_peers(ps, h_windows, world, rank);
+    if (rc != MK_OK) return rc;
+    if (n_seg < 1 || n_seg > 3 || !h_offsets || !h_bytes || pushers < 1 || pushers > 65535) return MK_EINVAL;
+    mk::PushDesc pd{};
+    pd.ps = ps;
+    pd.world = world;
+    pd.rank = rank;
+    pd.nseg = n_seg;
+    pd.pushers = pushers;
+    for (int g = 0; g < n_seg; ++g) {
+        if (h_bytes[g] < 0 || (h_bytes[g] & 15) || h_offsets[g] < MK_PEER_HEADER_BYTES || (h_offsets[g] & 15))
+            return MK_EINVAL;
+        pd.off[g] = h_offsets[g];
+        pd.bytes[g] = h_bytes[g];
+    }
+    if (world == 1) return MK_OK;
+    mk::peer_push_sm_kernel<<<static_cast<unsigned>(pushers), 32, 0, mk::as_stream(stream)>>>(pd);
+    MK_LAUNCH_CHECK("peer_push_sm_kernel");
     return MK_OK;
 }
 

@@ -219,6 +219,54 @@ __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
     return r;
 }
 
+// The rows one rank contributes to a table that lives in every rank's window: rank r's part of
+// segment g is the `bytes[g]` bytes (a multiple of 16) at off[g] + r*bytes[g] of every window.
+struct PushDesc {
+    PeerSet ps;
+    int world, rank;
+    int64_t off[3], bytes[3];
+    int nseg, pushers;
+};
+
+// The all-gather by NVLink stores.  `pushers` CTAs of 32 threads (id in [0, pushers)) copy this rank's
+// rows to the peers rank-1, rank-2, ... (every rank then receives from one sender at a time, and
+// from its successor first); the pusher that finishes a peer last raises done[rank] = epoch there.
+// A pusher CTA (32 threads).  `id` in [0, pushers).
+__device__ __forceinline__ void push_rows(const PushDesc& fw, int id, uint32_t epoch) {
+    const int lane = lane_id();
+    uint32_t* hdr = peer_hdr(fw.ps, fw.rank);
+    const int64_t stride = static_cast<int64_t>(fw.pushers) * 32;
+    for (int s = 1; s < fw.world; ++s) {
+        const int q = (fw.rank - s + fw.world) % fw.world;
+        for (int g = 0; g < fw.nseg; ++g) {
+            const int64_t base = fw.off[g] + fw.rank * fw.bytes[g];
+            const int64_t n16 = fw.bytes[g] >> 4;
+            const uint4* __restrict__ src = reinterpret_cast<const uint4*>(fw.ps.win[fw.rank] + base);
+            uint4* __restrict__ dst = reinterpret_cast<uint4*>(fw.ps.win[q] + base);
+            int64_t i = static_cast<int64_t>(id) * 32 + lane;
+            for (; i + 3 * stride < n16; i += 4 * stride) {  // four loads in flight per thread
+                const uint4 a = ld_cg_16(src + i), b = ld_cg_16(src + i + stride);
+                const uint4 c = ld_cg_16(src + i + 2 * stride), d = ld_cg_16(src + i + 3 * stride);
+                st_peer_16(dst + i, a);
+                st_peer_16(dst + i + stride, b);
+                st_peer_16(dst + i + 2 * stride, c);
+                st_peer_16(dst + i + 3 * stride, d);
+            }
+            for (; i < n16; i += stride) st_peer_16(dst + i, ld_cg_16(src + i));
+        }
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t t = atomicAdd(hdr + kHdrStep + s, 1u);
+            if (t == static_cast<uint32_t>(fw.pushers) - 1u) {
+                hdr[kHdrStep + s] = 0u;
+                __threadfence_system();  // the other pushers' stores (fenced before their tickets) first
+                st_release_sys(peer_hdr(fw.ps, q) + kHdrDone + fw.rank, epoch);
+            }
+        }
+    }
+}
+
 // Largest grid of `threads`-wide blocks of kernel `fn` that is resident at once on the device.
 template <typename F>
 static int coresident_blocks(F fn, int threads, size_t smem) {

@@ -31,7 +31,10 @@ from .graph import CSRGraph, ceil_div
 
 
 def rows_per_rank(num_nodes: int, world: int) -> int:
-    return ceil_div(num_nodes, world)
+    """Rows of the padded table every rank owns: ceil(N / P) rounded up to a multiple of 16, so that a
+    rank's block of every table segment (k bytes per row at the narrowest) is a whole number of
+    16-byte units -- what the NVLink stores of the exchange move."""
+    return ceil_div(ceil_div(num_nodes, world), 16) * 16
 
 
 def shard_graph(g: CSRGraph, rank: int, world: int) -> Tuple[CSRGraph, int, int]:
@@ -194,7 +197,14 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
             buf = win.next_buffer()
             o = offs[len(per_rank) * buf: len(per_rank) * (buf + 1)]
             mine = slice(rank * r, (rank + 1) * r)
-            wait = (win.local, world, rank, r, peer.timeout_ms()) if peer.overlap() else None
+            # who moves the rows: pusher CTAs inside the forward kernel ("sm": needs 16-byte multiples),
+            # or the copy engines on side streams ("dma"), with or without per-block waiting
+            fused = (form != "plain" and peer.push_mode() == "sm" and all(b % 16 == 0 for b in per_rank))
+            wait = None
+            if fused:
+                wait = peer.exchange(win, r, o, per_rank)
+            elif peer.overlap() and form != "plain":
+                wait = peer.exchange(win, r)
             peer.begin_push(win, buf)
             full_index = win.view(o[-1], (rows, k), sp_index.dtype)
             full_index[mine].copy_(sp_index)
@@ -203,24 +213,29 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
                 full_slot = win.view(o[1], (rows, k), torch.int16)
                 maxk_kernels.cbsr_bank(sp_data, sp_index, dim_origin, with_index=False,
                                        out=(full_data[mine], full_slot[mine]))
-                peer.publish_and_push(win, buf, o, per_rank)
-                if wait is None:
-                    peer.wait_all(win)
-                out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, full_data, full_slot, num_rows, e, k,
-                                                         dim_origin, split=split, wait=wait)
             elif form == "packed":
                 full_pack = win.view(o[0], (rows, k, 2), torch.int32)
                 maxk_kernels.cbsr_bank_packed(sp_data, sp_index, dim_origin, out=full_pack[mine])
-                peer.publish_and_push(win, buf, o, per_rank)
-                if wait is None:
-                    peer.wait_all(win)
-                out = maxk_kernels.spgemm_forward_packed(ptr, idx, val, full_pack, num_rows, e, k, dim_origin,
-                                                         split=split, wait=wait)
             else:
                 full_data = win.view(o[0], (rows, k), torch.float32)
                 full_data[mine].copy_(sp_data)
-                peer.publish_and_push(win, buf, o, per_rank)
+            if fused:
+                peer.publish(win, buf)
+            elif peer.push_mode() == "sm" and all(b % 16 == 0 for b in per_rank):
+                peer.publish(win, buf)           # un-banked table: the same stores as a kernel of its own
+                peer.push_sm(win, o, per_rank)
                 peer.wait_all(win)
+            else:
+                peer.publish_and_push(win, buf, o, per_rank)
+                if wait is None:
+                    peer.wait_all(win)
+            if form == "banked":
+                out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, full_data, full_slot, num_rows, e, k,
+                                                         dim_origin, split=split, wait=wait)
+            elif form == "packed":
+                out = maxk_kernels.spgemm_forward_packed(ptr, idx, val, full_pack, num_rows, e, k, dim_origin,
+                                                         split=split, wait=wait)
+            else:
                 out, _ = maxk_kernels.spgemm_forward(ptr, idx, val, full_data, full_index, num_rows, e, k,
                                                      dim_origin, allow_banked=False)
             peer.join_push(win)

@@ -33,7 +33,7 @@ __all__ = [
     "maxk_forward_cbsr", "cbsr_scatter", "cbsr_gather", "partition",
     "clear_partition_cache", "install_partition", "set_max_nz", "get_max_nz", "launch_count",
     "banked_supported", "cbsr_bank", "block_split", "packed_supported", "cbsr_bank_packed",
-    "spgemm_forward_packed", "use_packed", "maxk_forward_banked", "spgemm_forward_banked",
+    "spgemm_forward_packed", "use_packed", "ForwardExchange", "maxk_forward_banked", "spgemm_forward_banked",
     "spgemm_backward_banked", "set_banked", "set_backward_tma", "use_banked", "forward_variant", "partition_blocked", "backward_blocks",
     "set_backward_block_mb", "add_layernorm_supported", "add_layernorm_forward", "layernorm_backward",
 ]
@@ -411,6 +411,31 @@ def install_partition(ptr: torch.Tensor, num_nodes: int, max_nz: int, parts: tor
 # ---------------------------------------------------------------------------------------
 # SpGEMM forward / SSpMM backward
 # ---------------------------------------------------------------------------------------
+class ForwardExchange:
+    """What a row-partitioned forward needs to run while its table is still arriving (built by
+    peer.py, handed to `spgemm_forward_banked` / `spgemm_forward_packed` as `wait=`): the rank's own
+    window, the rank layout and -- when the kernel itself is the all-gather -- every rank's window
+    and the table segments its pusher CTAs copy to the peers."""
+
+    def __init__(self, window_ptr, world, rank, rows_per_rank, timeout_ms, windows=None, offsets=None,
+                 bytes_per_rank=None, pushers=0):
+        x = _lib.FwdExchange()
+        x.window = window_ptr
+        x.world, x.rank, x.rows_per_rank, x.timeout_ms = int(world), int(rank), int(rows_per_rank), int(timeout_ms)
+        self._keep = None
+        if windows is not None and pushers > 0:
+            n = len(offsets)
+            offs = (ctypes.c_int64 * n)(*[int(o) for o in offsets])
+            nb = (ctypes.c_int64 * n)(*[int(b) for b in bytes_per_rank])
+            x.h_windows = ctypes.cast(windows, ctypes.POINTER(ctypes.c_void_p))
+            x.n_seg, x.h_offsets, x.h_bytes, x.pushers = n, offs, nb, int(pushers)
+            self._keep = (windows, offs, nb)
+        self.struct = x
+
+    def ref(self):
+        return ctypes.byref(self.struct)
+
+
 def _check_graph(ptr, idx, val):
     _cuda_contig(ptr, "ptr")
     _cuda_contig(idx, "idx")
@@ -582,8 +607,8 @@ def spgemm_forward_banked(ptr, idx, val, bk_data, bk_slot, num_nodes, num_edges,
                           *, split: Optional[torch.Tensor] = None, wait=None):
     """`spgemm_forward` on a banked table: same result, no shared-memory bank conflicts.
     Row-partitioned form (dist.py): `split` int32 [num_nodes] makes every record walk the source
-    blocks in arrival order, `wait = (window base pointer, world, rank, rows_per_rank, timeout_ms)`
-    lets the kernel run while the peers' rows are still arriving (peer.py)."""
+    blocks in arrival order, `wait` (a `ForwardExchange`) lets the kernel run while the peers' rows are
+    still arriving and, with pushers, makes it the all-gather itself (peer.py)."""
     global _launches
     _check_graph(ptr, idx, val)
     _cuda_contig(bk_data, "sp_data")
@@ -599,15 +624,14 @@ def spgemm_forward_banked(ptr, idx, val, bk_data, bk_slot, num_nodes, num_edges,
     out = torch.empty((num_nodes, dim_origin), dtype=torch.float32, device=bk_data.device)
     partial = part.partial_for(dim_origin, bk_data.device)
     ex = part.exec_parts()
-    w_ptr, w_world, w_rank, w_rows, w_tmo = wait if wait is not None else (None, 1, 0, 1, 0)
     with torch.cuda.device(bk_data.device):
         rc = _lib.lib().mk_spgemm_fwd_banked_ex(
             part.parts.data_ptr(), part.num_parts, part.num_slots,
             ex.data_ptr() if ex is not part.parts else None, idx.data_ptr(), val.data_ptr(),
             bk_data.data_ptr(), bk_slot.data_ptr(), out.data_ptr(),
             partial.data_ptr() if partial is not None else None, num_nodes, dim_sparse, dim_origin,
-            split.data_ptr() if split is not None else None, w_ptr, int(w_world), int(w_rank),
-            int(w_rows), int(w_tmo), _stream())
+            split.data_ptr() if split is not None else None, wait.ref() if wait is not None else None,
+            _stream())
     _lib.check(rc, "mk_spgemm_fwd_banked_ex")
     _launches += 1 + (1 if part.num_slots else 0)
     return out
@@ -657,14 +681,13 @@ def spgemm_forward_packed(ptr, idx, val, bk_pack, num_nodes, num_edges, dim_spar
     out = torch.empty((num_nodes, dim_origin), dtype=torch.float32, device=bk_pack.device)
     partial = part.partial_for(dim_origin, bk_pack.device)
     ex = part.exec_parts()
-    w_ptr, w_world, w_rank, w_rows, w_tmo = wait if wait is not None else (None, 1, 0, 1, 0)
     with torch.cuda.device(bk_pack.device):
         rc = _lib.lib().mk_spgemm_fwd_packed_ex(
             part.parts.data_ptr(), part.num_parts, part.num_slots,
             ex.data_ptr() if ex is not part.parts else None, idx.data_ptr(), val.data_ptr(),
             bk_pack.data_ptr(), out.data_ptr(), partial.data_ptr() if partial is not None else None,
             num_nodes, dim_sparse, dim_origin, split.data_ptr() if split is not None else None,
-            w_ptr, int(w_world), int(w_rank), int(w_rows), int(w_tmo), _stream())
+            wait.ref() if wait is not None else None, _stream())
     _lib.check(rc, "mk_spgemm_fwd_packed_ex")
     _launches += 1 + (1 if part.num_slots else 0)
     return out

@@ -51,6 +51,11 @@ _PUSH_STREAMS = max(1, int(os.environ.get("MAXK_PEER_STREAMS", "2")))
 # 1: the forward SpGEMM starts with the pushes and waits per source block; 0: it starts when the whole
 # table has arrived (mk_peer_wait_all)
 _OVERLAP = os.environ.get("MAXK_PEER_OVERLAP", "1") != "0"
+# who moves the rows to the peers: "sm" = pusher CTAs inside the forward SpGEMM kernel (default; NVLink
+# stores, progressive arrival), "dma" = copy engines on side streams (measured slower: small transfers
+# pay ~4 us each and concurrent flows interfere -- profiles/r2/push_probe_call6.log, exchange_forms8_call7.log)
+_PUSH = os.environ.get("MAXK_PEER_PUSH", "sm")
+_PUSHERS = int(os.environ.get("MAXK_PEER_PUSHERS", "592"))   # pusher CTAs (32 threads each)
 _launches = 0
 
 
@@ -77,6 +82,40 @@ def timeout_ms() -> int:
 
 def overlap() -> bool:
     return _OVERLAP
+
+
+def push_mode() -> str:
+    return _PUSH if _OVERLAP else "dma"
+
+
+def publish(win: "PeerWindow", buf: int) -> None:
+    """Open the collective whose rows this rank has just written into its own window (no transfer:
+    the consumer's pusher CTAs, or `push_dma`, move them)."""
+    global _launches
+    with torch.cuda.device(win.device):
+        _lib.check(_lib.lib().mk_peer_publish(win.local, win.rank, int(buf), _stream()), "mk_peer_publish")
+    _launches += 1
+
+
+def push_sm(win: "PeerWindow", offsets: Sequence[int], bytes_per_rank: Sequence[int]) -> None:
+    """The all-gather by NVLink stores as a kernel of its own (after `publish`, current stream)."""
+    global _launches
+    n = len(offsets)
+    offs = (ctypes.c_int64 * n)(*[int(o) for o in offsets])
+    nbytes = (ctypes.c_int64 * n)(*[int(b) for b in bytes_per_rank])
+    with torch.cuda.device(win.device):
+        rc = _lib.lib().mk_peer_push_sm(win.ptrs, win.world, win.rank, n, offs, nbytes, _PUSHERS, _stream())
+    _lib.check(rc, "mk_peer_push_sm")
+    _launches += 1
+
+
+def exchange(win: "PeerWindow", rows_per_rank: int, offsets=None, bytes_per_rank=None):
+    """The `wait=` argument of the forward kernels for this window; with offsets, the kernel pushes."""
+    from .maxk_kernels import ForwardExchange
+    pushing = offsets is not None and win.world > 1
+    return ForwardExchange(win.local, win.world, win.rank, rows_per_rank, _TIMEOUT_MS,
+                           windows=win.ptrs if pushing else None, offsets=offsets,
+                           bytes_per_rank=bytes_per_rank, pushers=_PUSHERS if pushing else 0)
 
 
 def available(group=None) -> bool:

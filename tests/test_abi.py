@@ -97,11 +97,23 @@ def test_peer_argument_validation_without_a_device(built_lib):
     assert L.mk_peer_reduce_scatter(wins, 2, 0, 1000, 64, None, 0, 0, None) == E     # offset in header
     assert L.mk_peer_reduce_scatter(wins, 2, 0, 1024, 64, None, 0, 0, None) == E     # no output
     assert L.mk_peer_reduce_scatter(wins, 2, 0, 1024, 24, None, 0, 0, None) == E     # not 16-byte units
-    # waiting forward: bad rank layout is rejected before any CUDA call
-    assert L.mk_spgemm_fwd_banked_ex(None, 5, 0, None, None, None, None, None, None, None, 5, 32, 256,
-                                     None, 0x1000, 2, 2, 100, 0, None) == E
-    assert L.mk_spgemm_fwd_banked_ex(None, 5, 0, None, None, None, None, None, None, None, 5, 32, 256,
-                                     None, 0x1000, 2, 0, 0, 0, None) == E
+    # waiting / pushing forward: a bad exchange description is rejected before any CUDA call
+    x = _lib.FwdExchange()
+    x.window, x.world, x.rank, x.rows_per_rank = 0x1000, 2, 2, 100
+    fwd = lambda: L.mk_spgemm_fwd_banked_ex(None, 5, 0, None, None, None, None, None, None, None, 5, 32, 256,
+                                            None, ctypes.byref(x), None)
+    assert fwd() == E                                                  # rank >= world
+    x.rank, x.rows_per_rank = 0, 0
+    assert fwd() == E                                                  # no rows per rank
+    x.rows_per_rank, x.pushers, x.n_seg = 100, 4, 1
+    x.h_windows, x.h_offsets, x.h_bytes = ctypes.cast(wins, ctypes.POINTER(VP)), off, nb
+    nb[0] = 24
+    assert fwd() == E                                                  # segment not in 16-byte units
+    nb[0] = 64
+    x.window = 0x5000
+    assert fwd() == E                                                  # h_windows[rank] is not the window
+    assert L.mk_peer_push_sm(wins, 2, 0, 1, off, nb, 0, None) == E     # no pushers
+    assert L.mk_peer_push_sm(wins, 2, 0, 4, off, nb, 8, None) == E     # > 3 segments
     p = VP(0)
     assert L.mk_peer_alloc(16, ctypes.byref(p)) == E                                # smaller than the header
     assert L.mk_peer_free(None) == _lib.MK_OK and L.mk_peer_close(None) == _lib.MK_OK

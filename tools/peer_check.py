@@ -47,6 +47,7 @@ def virtual(world: int) -> int:
         shards = [mdist.shard_graph(g, q, world) for q in range(world)]
         vals = [mdist.shard_edge_weights(g, sh[0], sh[1], sh[2], "mean") for sh in shards]
         for rnd in range(4):   # rounds 2, 3 re-use the two table buffers: release / begin_push handshake
+            mode = ("dma", "sm", "sm", "dma")[rnd]     # who moves the rows: copy engines / NVLink-store CTAs
             xs = [torch.randn(r, d, device=dev, generator=gen) for _ in range(world)]
             cb = [mk.maxk_forward_cbsr(x, kk) for x in xs]
             ref = [mk.cbsr_bank(sd, si, d, with_index=False) for sd, si in cb]
@@ -62,9 +63,22 @@ def virtual(world: int) -> int:
                 fd = w.view(o[0], (rows, kk), torch.float32)
                 fs = w.view(o[1], (rows, kk), torch.int16)
                 fi = w.view(o[2], (rows, kk), torch.uint8)
+                fd.zero_(); fs.zero_(); fi.zero_()          # nothing of the previous round survives
+            for q in range(world):
+                w = wins[q]
+                buf = w._buf
+                o = offs[3 * buf: 3 * buf + 3]
+                mine = slice(q * r, (q + 1) * r)
+                fd = w.view(o[0], (rows, kk), torch.float32)
+                fs = w.view(o[1], (rows, kk), torch.int16)
+                fi = w.view(o[2], (rows, kk), torch.uint8)
                 fi[mine].copy_(cb[q][1])
                 mk.cbsr_bank(cb[q][0], cb[q][1], d, with_index=False, out=(fd[mine], fs[mine]))
-                peer.publish_and_push(w, buf, o, per_rank)
+                if mode == "dma":
+                    peer.publish_and_push(w, buf, o, per_rank)
+                else:                                       # the pushers wait for nobody: ranks can take turns
+                    peer.publish(w, buf)
+                    peer.push_sm(w, o, per_rank)
             for q in range(world):
                 w = wins[q]
                 buf = w._buf
@@ -74,8 +88,11 @@ def virtual(world: int) -> int:
                 fi = w.view(o[2], (rows, kk), torch.uint8)
                 local = shards[q][0]
                 split = mk.block_split(local.indptr, local.indices, r, world, q, r)
+                # round 2: the forward kernel carries pusher CTAs as well (they re-send rows that are
+                # already there -- on one device the real overlap cannot be staged, the code path can)
+                x = peer.exchange(w, r, o, per_rank) if rnd == 2 else peer.exchange(w, r)
                 out = mk.spgemm_forward_banked(local.indptr, local.indices, vals[q], fd, fs, r, local.num_edges(),
-                                               kk, d, split=split, wait=(w.local, world, q, r, 8000))
+                                               kk, d, split=split, wait=x)
                 peer.join_push(w)
                 outs.append((out, fd.clone(), fs.clone(), fi.clone()))
                 peer.release(w)
@@ -91,7 +108,7 @@ def virtual(world: int) -> int:
                 ep, err = wins[q].epoch()
                 good &= (ep == rnd + 1 and err == 0)
                 ok &= bool(good)
-            print(f"push + waiting forward k={kk} round {rnd}: {'OK' if ok else 'FAIL'}")
+            print(f"push ({mode}) + waiting forward k={kk} round {rnd}: {'OK' if ok else 'FAIL'}")
 
     # ---- reduce-scatter by loads: fixed rank order, so bit-equal to the same fold in torch
     k, r = 32, 1000
