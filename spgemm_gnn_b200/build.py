@@ -89,7 +89,53 @@ def build(force: bool = False, verbose: bool = False, defs=(), out: str = None) 
     return so
 
 
+BINDING_SRC = os.path.join(HERE, "binding", "maxk_bindings.cpp")
+
+
+def binding_path() -> str:
+    import sysconfig
+    return os.path.join(HERE, "maxk_kernels_ext" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_binding(force: bool = False) -> str:
+    """The compiled `maxk_kernels` front end (pybind11 / ATen, binding/maxk_bindings.cpp) over
+    libmaxk_b200.so -- what the reference's setup.py:25-31 builds, minus the kernels, which stay behind
+    the C ABI.  One g++ call with torch's own include / library paths (binding/setup.py is the
+    setuptools form of the same build); in-tree, next to the library, so that it travels with it."""
+    import hashlib
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension as ce
+    build()
+    out = binding_path()
+    stamp = out + ".srchash"
+    h = hashlib.sha256()
+    for f in (BINDING_SRC, os.path.join(ROOT, "include", "maxk_b200.h")):
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(torch.__version__.encode())
+    digest = h.hexdigest()
+    if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        return out
+    inc = ce.include_paths(device_type="cuda") + [sysconfig.get_paths()["include"], os.path.join(ROOT, "include")]
+    libs = ce.library_paths(device_type="cuda")
+    cmd = (["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=maxk_kernels_ext",
+            "-DTORCH_API_INCLUDE_EXTENSION_H", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
+           + [f"-I{i}" for i in inc] + [BINDING_SRC, "-o", out] + [f"-L{l}" for l in libs]
+           + [f"-L{HERE}", "-lmaxk_b200", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch",
+              "-ltorch_python", "-Wl,-rpath," + HERE] + [f"-Wl,-rpath,{l}" for l in libs])
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout.decode())
+        raise RuntimeError("building the maxk_kernels binding failed")
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return out
+
+
 if __name__ == "__main__":
     defs = [a for a in sys.argv[1:] if a.startswith("-D")]
     out = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")), None)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defs=defs, out=out))
+    if "--binding" in sys.argv:
+        print(build_binding(force="--force" in sys.argv))
