@@ -37,18 +37,45 @@ def rows_per_rank(num_nodes: int, world: int) -> int:
     return ceil_div(ceil_div(num_nodes, world), 16) * 16
 
 
-def shard_graph(g: CSRGraph, rank: int, world: int) -> Tuple[CSRGraph, int, int]:
-    """Rank's row block of `g`, padded to R rows with empty rows; columns stay global and the
-    column space is padded to world*R so that gathered tables index directly by global id."""
+def shard_bounds(g: CSRGraph, world: int, balance: str = "rows") -> list:
+    """world+1 row offsets of the 1-D partition.  "rows": equal row counts (fine for node orders that
+    are random, as the synthetic shapes are).  "nnz": contiguous row ranges with equal numbers of
+    stored entries ("balance by nnz, not rows, for skewed graphs") -- no
+    relabelling, so whatever locality the node order has is kept."""
     n = g.num_nodes()
-    r = rows_per_rank(n, world)
-    r0, r1 = min(rank * r, n), min((rank + 1) * r, n)
+    if balance == "rows":
+        r = ceil_div(n, world)
+        return [min(p * r, n) for p in range(world + 1)]
+    if balance == "nnz":
+        from .graph import row_partition_bounds
+        return row_partition_bounds(g.indptr, world)
+    raise ValueError(f"unknown shard balance {balance!r}")
+
+
+def shard_graph(g: CSRGraph, rank: int, world: int, bounds=None) -> Tuple[CSRGraph, int, int]:
+    """Rank's row block of `g`, padded to R rows with empty rows, R = the largest block rounded up to
+    a multiple of 16.  The column space is world*R wide: node j of block q sits at table row
+    q*R + (j - bounds[q]), so that gathered tables index directly by column id.  With equal-row
+    blocks of width R that IS the global id; otherwise the ids are remapped here, once."""
+    n = g.num_nodes()
+    if bounds is None:
+        r = rows_per_rank(n, world)
+        bounds = [min(p * r, n) for p in range(world + 1)]
+    else:
+        r = ceil_div(max(bounds[p + 1] - bounds[p] for p in range(world)), 16) * 16
+    r0, r1 = bounds[rank], bounds[rank + 1]
     s = g.row_slice(r0, r1)
     ptr = s.indptr
     if r1 - r0 < r:  # pad with empty rows
         pad = ptr[-1:].expand(r - (r1 - r0))
         ptr = torch.cat([ptr, pad]).contiguous()
-    local = CSRGraph(ptr, s.indices, num_src=world * r)
+    cols = s.indices
+    if any(bounds[p] != p * r for p in range(world)):
+        b = torch.tensor(bounds[:-1], dtype=torch.int64, device=cols.device)
+        c64 = cols.to(torch.int64)
+        q = torch.searchsorted(b, c64, right=True) - 1
+        cols = (q * r + (c64 - b[q])).to(torch.int32)     # blocks are contiguous: rows stay ascending
+    local = CSRGraph(ptr, cols.contiguous(), num_src=world * r)
     local._cache["symmetric"] = False
     return local, r0, r1
 
@@ -306,13 +333,15 @@ class ShardedGraph(CSRGraph):
     the aggregation then goes through `DistSpGEMMFunction` (all-gather / reduce-scatter).
     Built from the FULL graph so that the per-edge weights use global degrees."""
 
-    def __init__(self, full: CSRGraph, rank: int, world: int, group=None):
-        local, r0, r1 = shard_graph(full, rank, world)
+    def __init__(self, full: CSRGraph, rank: int, world: int, group=None, balance: str = "rows"):
+        self.balance = balance
+        self.bounds = None if balance == "rows" else shard_bounds(full, world, balance)
+        local, r0, r1 = shard_graph(full, rank, world, self.bounds)
         super().__init__(local.indptr, local.indices, local.num_src)
         self.rank, self.world, self.group = rank, world, group
         self.row_begin, self.row_end = r0, r1
         self.global_nodes = full.num_nodes()
-        self.rows_per_rank = rows_per_rank(full.num_nodes(), world)
+        self.rows_per_rank = local.num_nodes()
         self._weights = {k: shard_edge_weights(full, local, r0, r1, k) for k in ("mean", "both", "sum")}
         self._cache["symmetric"] = False
         # padded rows are empty by construction; only real rows count for GraphConv's check
@@ -348,3 +377,53 @@ def dist_maxk_aggregate(local: CSRGraph, val: torch.Tensor, feat: torch.Tensor, 
     sp_data, sp_index = MaxKCBSRFunction.apply(feat, k)
     return DistSpGEMMFunction.apply(sp_data, sp_index, local.indptr, local.indices, val,
                                     local.num_nodes(), feat.shape[1], group)
+
+
+# ---------------------------------------------------------------------------------------
+# shards on disk (f-4: the `.warp4` successor for the row-partitioned path)
+# ---------------------------------------------------------------------------------------
+SHARD_MAGIC = "maxk-b200-shard-v1"
+
+
+def save_shard(sg: "ShardedGraph", path: str) -> None:
+    """One rank's shard: local CSR (table-row column ids), per-edge weights from the global degrees,
+    the partition bounds and, on a CUDA device, the work records of `mk_partition` -- everything a
+    rank needs to start without ever holding the full graph."""
+    import numpy as np
+    from . import maxk_kernels
+    blob = {"magic": np.array(SHARD_MAGIC), "indptr": sg.indptr.cpu().numpy(), "indices": sg.indices.cpu().numpy(),
+            "num_src": np.int64(sg.num_src), "rank": np.int64(sg.rank), "world": np.int64(sg.world),
+            "row_begin": np.int64(sg.row_begin), "row_end": np.int64(sg.row_end),
+            "global_nodes": np.int64(sg.global_nodes), "balance": np.array(sg.balance),
+            "bounds": np.array(sg.bounds if sg.bounds is not None else [], dtype=np.int64)}
+    for kind, w in sg._weights.items():
+        blob["w_" + kind] = w.cpu().numpy()
+    if sg.indptr.is_cuda:
+        part = maxk_kernels.partition(sg.indptr, sg.num_nodes())
+        blob.update(parts=part.parts[: part.num_parts].cpu().numpy(), num_slots=np.int64(part.num_slots),
+                    max_nz=np.int64(part.max_nz))
+    np.savez(path, **blob)
+
+
+def load_shard(path: str, device="cpu", group=None) -> "ShardedGraph":
+    """Inverse of `save_shard` (the file of THIS rank); stored work records go into the partition cache."""
+    import numpy as np
+    z = np.load(path if path.endswith(".npz") else path + ".npz")
+    if str(z["magic"]) != SHARD_MAGIC:
+        raise ValueError(f"{path}: not a {SHARD_MAGIC} file")
+    sg = ShardedGraph.__new__(ShardedGraph)
+    CSRGraph.__init__(sg, torch.from_numpy(z["indptr"]).to(device), torch.from_numpy(z["indices"]).to(device),
+                      int(z["num_src"]))
+    sg.rank, sg.world, sg.group = int(z["rank"]), int(z["world"]), group
+    sg.row_begin, sg.row_end = int(z["row_begin"]), int(z["row_end"])
+    sg.global_nodes, sg.balance = int(z["global_nodes"]), str(z["balance"])
+    sg.bounds = [int(v) for v in z["bounds"]] or None
+    sg.rows_per_rank = sg.num_nodes()
+    sg._weights = {k[2:]: torch.from_numpy(z[k]).to(device) for k in z.files if k.startswith("w_")}
+    sg._cache["symmetric"] = False
+    sg._cache["has_zero_in"] = bool((sg.in_degrees()[: sg.row_end - sg.row_begin] == 0).any())
+    if "parts" in z.files and torch.device(device).type == "cuda":
+        from . import maxk_kernels
+        maxk_kernels.install_partition(sg.indptr, sg.num_nodes(), int(z["max_nz"]),
+                                       torch.from_numpy(z["parts"]).to(device), int(z["num_slots"]))
+    return sg

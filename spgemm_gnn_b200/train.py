@@ -187,6 +187,8 @@ def main(argv=None):
     ap.add_argument("--norm", action="store_true")
     ap.add_argument("--gpu", type=int, default=0)
     ap.add_argument("--seed", type=int, default=97)
+    ap.add_argument("--shard_balance", default="rows", choices=["rows", "nnz"],
+                    help="multi-GPU row partition: equal rows (random node orders) or equal stored entries")
     ap.add_argument("--no_tf32", dest="tf32", action="store_false",
                     help="fp32 GEMMs (default: TF32, as the reference sets at maxk_gnn_dgl.py:30-33)")
     ap.add_argument("--eval_every", type=int, default=1, help="eval forward every n epochs (reference: 1)")
@@ -214,7 +216,7 @@ def main(argv=None):
     n_nodes, n_edges = g.num_nodes(), g.num_edges()
     if world > 1:  # 1-D row partition: every rank keeps its rows of the graph and of the node data
         from .dist import ShardedGraph
-        sg = ShardedGraph(g, rank, world)
+        sg = ShardedGraph(g, rank, world, balance=a.shard_balance)
         feats, labels, train_mask = sg.local_rows(feats), sg.local_rows(labels), sg.local_rows(train_mask)
         g = sg
         # weights were initialised from the common seed above; from here on every rank draws its own

@@ -103,3 +103,80 @@ def test_random_relabel_keeps_the_graph_and_balances_shards():
         nnz = [int(gr.indptr[min((p + 1) * r, n)] - gr.indptr[min(p * r, n)]) for p in range(8)]
         return max(nnz) / (sum(nnz) / 8)
     assert imbalance(g) > 3.0 and imbalance(g2) < 1.3
+
+
+def _worker_nnz(rank, world, port, ret, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import c_oracle
+        from spgemm_gnn_b200 import dist as mdist
+        from spgemm_gnn_b200.graph import from_edges
+
+        # power-law graph with the heavy rows at the FRONT: equal-row shards would be badly unbalanced
+        n, d, k = 3000, 64, 16
+        rng = np.random.default_rng(9)
+        deg = np.maximum((600.0 / (1.0 + np.arange(n)) ** 0.7).astype(np.int64), 2)
+        rows = np.repeat(np.arange(n), deg)
+        cols = rng.integers(0, n, rows.size)
+        g = from_edges(torch.from_numpy(rows), torch.from_numpy(cols), n)
+        sg = mdist.ShardedGraph(g, rank, world, balance="nnz")
+        # nnz imbalance below 2 % WITHOUT relabelling; the row counts differ a lot
+        nnz = torch.tensor([float(sg.num_edges())])
+        alln = [torch.zeros(1) for _ in range(world)]
+        dist.all_gather(alln, nnz)
+        alln = torch.cat(alln)
+        assert float(alln.max() / alln.mean()) < 1.02, alln
+        b = sg.bounds
+        assert b[0] == 0 and b[-1] == n and (b[1] - b[0]) * 3 < (b[-1] - b[-2])
+        r = sg.rows_per_rank
+        assert r % 16 == 0 and r >= max(b[p + 1] - b[p] for p in range(world)) and sg.num_src == world * r
+        # column ids are table rows: block q starts at q * r
+        x = rng.standard_normal((n, d)).astype(np.float32)
+        dy = rng.standard_normal((n, d)).astype(np.float32)
+        xl = sg.local_rows(torch.from_numpy(x)).numpy()
+        sd, si = c_oracle.maxk_cbsr(xl, k)
+        fd, fi = mdist.allgather_cbsr(torch.from_numpy(sd), torch.from_numpy(si))
+        wd, wi = c_oracle.maxk_cbsr(x, k)
+        for q in range(world):                               # gathered table == global table, block by block
+            assert np.array_equal(fd.numpy()[q * r: q * r + b[q + 1] - b[q]], wd[b[q]:b[q + 1]])
+        val = sg.edge_weights("mean")
+        out = c_oracle.spgemm_fwd(sg.indptr.numpy(), sg.indices.numpy(), val.numpy(), fd.numpy(), fi.numpy(), d)
+        want = c_oracle.spgemm_fwd(g.indptr.numpy(), g.indices.numpy(), g.edge_weights("mean").numpy(), wd, wi, d)
+        nloc = sg.row_end - sg.row_begin
+        np.testing.assert_allclose(out[:nloc], want[sg.row_begin:sg.row_end], rtol=1e-12, atol=1e-12)
+        assert not out[nloc:].any()
+        dyl = sg.local_rows(torch.from_numpy(dy)).numpy()
+        part = c_oracle.sspmm_bwd(sg.indptr.numpy(), sg.indices.numpy(), val.numpy(), dyl, fi.numpy())
+        mine = mdist.reduce_scatter_rows(torch.from_numpy(part))
+        want_b = c_oracle.sspmm_bwd(g.indptr.numpy(), g.indices.numpy(), g.edge_weights("mean").numpy(), dy, wi)
+        np.testing.assert_allclose(mine.numpy()[:nloc], want_b[sg.row_begin:sg.row_end], rtol=1e-10, atol=1e-12)
+        # shard file round trip: a rank can start from its file alone
+        path = os.path.join(tmp, f"shard{rank}")
+        mdist.save_shard(sg, path)
+        sg2 = mdist.load_shard(path)
+        assert torch.equal(sg2.indptr, sg.indptr) and torch.equal(sg2.indices, sg.indices)
+        assert sg2.bounds == sg.bounds and sg2.rows_per_rank == r and sg2.rank == rank and sg2.world == world
+        assert all(torch.equal(sg2.edge_weights(kd), sg.edge_weights(kd)) for kd in ("mean", "both", "sum"))
+        with pytest.raises(RuntimeError):
+            sg.row_slice(0, 1)
+        assert sg.to("cpu") is sg
+        ret[rank] = "ok"
+    except Exception:
+        import traceback
+        ret[rank] = traceback.format_exc()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_nnz_balanced_shards_gloo_world3(tmp_path):
+    """f-4: nnz-balanced contiguous row ranges (no relabel), remapped table-row column ids, forward /
+    backward against the single-process oracle, shard files."""
+    world = 3
+    port = 29500 + (os.getpid() % 2000) + 17
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_nnz, args=(world, port, ret, str(tmp_path)), nprocs=world, join=True)
+    assert dict(ret) == {r: "ok" for r in range(world)}, dict(ret)
