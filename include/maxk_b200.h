@@ -135,6 +135,16 @@ MK_API int mk_sspmm_bwd(const mk_part* parts, int64_t num_parts, const int32_t* 
                         const float* val, const float* dy, const void* sp_index, int index_bytes,
                         float* dxs, int64_t n_rows, int64_t n_src, int k, int d, void* stream);
 
+/* mk_sspmm_bwd for CBSR gradients that do not fit L2 (products-shaped graphs: 313 MB): the sources are
+ * cut into n_blocks column blocks of `block_width` (the one given to mk_block_ptr, whose output
+ * blk_ptr [(n_blocks+1) * n_rows] is taken here), and the grid walks block 0 of every 8-row tile first,
+ * then block 1, ...: the reductions of all CTAs in flight stay inside one L2-sized slice of dxs
+ * instead of becoming DRAM read-modify-writes.  dY is staged once per (tile, block).  Same result as
+ * mk_sspmm_bwd (summation order not fixed).  k in {8,16,32,64}, d % 4 == 0, ascending column ids.   */
+MK_API int mk_sspmm_bwd_tiled(const int32_t* blk_ptr, int n_blocks, const int32_t* idx, const float* val,
+                              const float* dy, const void* sp_index, int index_bytes, float* dxs,
+                              int64_t n_rows, int64_t n_src, int k, int d, void* stream);
+
 /* Experimental form of mk_sspmm_bwd (same contract, k == 32, uint8 ids): `tma_neighbours` (1, 2 or 4)
  * of the 4 neighbours a warp handles per step send their k contributions as ONE bulk reduction from
  * shared memory (cp.reduce.async.bulk, the TMA unit) instead of k/4 vector reductions through

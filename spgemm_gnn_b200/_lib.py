@@ -30,6 +30,7 @@ SIGNATURES = {
                                    ctypes.POINTER(_i64), _vp]),
     "mk_spgemm_fwd": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _i32, _vp]),
     "mk_sspmm_bwd": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _i32, _vp]),
+    "mk_sspmm_bwd_tiled": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _i32, _vp]),
     "mk_sspmm_bwd_tma": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
     "mk_layernorm_parts": (_i32, []),
     "mk_add_layernorm_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, ctypes.c_float, _vp]),

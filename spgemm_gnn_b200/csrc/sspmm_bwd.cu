@@ -111,6 +111,105 @@ sspmm_bwd_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
     sspmm_bwd_body<K, IdxT, U>(parts, idx, val, dy, sp_index, dxs, d, vec_dy);
 }
 
+// ---- column-blocked, row-tiled form for CBSR gradients that do not fit L2 -------------------------
+// On a products-shaped graph (2.45 M nodes, mean degree 51) dXs is 313 MB: every vector reduction of
+// the kernel above misses L2 and becomes a DRAM read-modify-write (ncu: 36.2 GB of DRAM traffic for
+// 24 GB algorithmic, profiles/r1_products_plain_k32.summary.txt).  Here the sources are cut into
+// `n_blocks` column blocks whose slice of dXs (+ of the column ids) fits L2, and the grid walks
+// block 0 of every row first, then block 1, ...: all CTAs in flight reduce into the same ~64-80 MB.
+// One record = one column block of TR consecutive rows (blk_ptr from mk_block_ptr gives every row's
+// segment), so a CTA stages TR rows of dY once and works through ~TR * deg / n_blocks stored entries
+// -- round 1's per-row blocked records (one row, ~12 entries, dY re-staged each time) were too
+// short to pay.  Price: dY is read n_blocks times (2.5 GB each on that shape) against ~25 GB of
+// read-modify-write traffic saved.
+template <int K, typename IdxT, int TR>
+__global__ void __launch_bounds__(32)
+sspmm_bwd_tiled_kernel(const int* __restrict__ blk_ptr, const int* __restrict__ idx,
+                       const float* __restrict__ val, const float* __restrict__ dy,
+                       const IdxT* __restrict__ sp_index, float* __restrict__ dxs, int d, int64_t n_rows,
+                       int n_tiles) {
+    constexpr int LPN = K / 4;   // lanes per neighbour
+    constexpr int G = 32 / LPN;  // neighbours per warp step
+    constexpr int U = (K / 4 >= 8) ? 4 : (K / 4);
+    extern __shared__ __align__(16) float dys[];  // TR rows of d floats
+    const int lane = lane_id();
+    const int g = lane / LPN;
+    const int t = lane % LPN;
+    const int b = blockIdx.x / n_tiles;            // column block: the slow index of the grid
+    const int64_t row0 = static_cast<int64_t>(blockIdx.x % n_tiles) * TR;
+    const int nr = static_cast<int>(min(static_cast<int64_t>(TR), n_rows - row0));
+    const int* __restrict__ seg_lo = blk_ptr + static_cast<int64_t>(b) * n_rows + row0;
+    const int* __restrict__ seg_hi = seg_lo + n_rows;
+
+    // segment bounds of the tile's rows (lane i: row i), and whether there is anything to do
+    int lo = 0, hi = 0;
+    if (lane < nr) {
+        lo = __ldg(seg_lo + lane);
+        hi = __ldg(seg_hi + lane);
+    }
+    if (__ballot_sync(kFull, hi > lo) == 0u) return;
+
+    const float* __restrict__ dyr = dy + row0 * d;
+    for (int c = lane * 4; c < nr * d; c += 128)
+        *reinterpret_cast<float4*>(dys + c) = ld_stream_f4(dyr + c);
+    __syncwarp();
+
+    for (int i = 0; i < nr; ++i) {
+        const int r_lo = __shfl_sync(kFull, lo, i), r_hi = __shfl_sync(kFull, hi, i);
+        const float* __restrict__ dyi = dys + i * d;
+        for (int base = r_lo; base < r_hi; base += 32) {
+            const int n_here = min(32, r_hi - base);
+            int my_nz = 0;
+            float my_v = 0.f;
+            if (lane < n_here) {
+                my_nz = ld_stream_i1(idx + base + lane);
+                my_v = ld_stream_f1(val + base + lane);
+            }
+            for (int j = 0; j < n_here; j += G * U) {
+                int cv[U][4];
+                int nzv[U];
+                float vv[U];
+                bool ok[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = j + u * G + g;
+                    nzv[u] = __shfl_sync(kFull, my_nz, e & 31);
+                    vv[u] = __shfl_sync(kFull, my_v, e & 31);
+                    ok[u] = e < n_here;
+                    if (ok[u]) load_cols4<IdxT>(sp_index + static_cast<int64_t>(nzv[u]) * K + 4 * t, cv[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (ok[u]) {
+                        const float v = vv[u];
+                        red_add_f4(dxs + static_cast<int64_t>(nzv[u]) * K + 4 * t, v * dyi[cv[u][0]],
+                                   v * dyi[cv[u][1]], v * dyi[cv[u][2]], v * dyi[cv[u][3]]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int K, typename IdxT>
+static int launch_bwd_tiled(const int* blk_ptr, int n_blocks, const int* idx, const float* val,
+                            const float* dy, const void* sp_index, float* dxs, int d, int64_t n_rows,
+                            cudaStream_t st) {
+    constexpr int TR = 8;
+    const int64_t n_tiles = (n_rows + TR - 1) / TR;
+    const int64_t grid = n_tiles * n_blocks;
+    if (grid > 0x7fffffffLL || n_tiles > 0x7fffffffLL) return MK_EUNSUPPORTED;
+    const size_t smem = static_cast<size_t>(TR) * d * 4;
+    if (smem > 200 * 1024) return MK_EUNSUPPORTED;
+    auto kern = sspmm_bwd_tiled_kernel<K, IdxT, TR>;
+    if (smem > 48 * 1024)
+        MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<static_cast<unsigned>(grid), 32, smem, st>>>(blk_ptr, idx, val, dy, static_cast<const IdxT*>(sp_index),
+                                                        dxs, d, n_rows, static_cast<int>(n_tiles));
+    MK_LAUNCH_CHECK("sspmm_bwd_tiled_kernel");
+    return MK_OK;
+}
+
 // ---- experimental: part of the reductions through the TMA unit ---------------------------------
 // The kernel above is bound by the SM -> L2 request path (l1tex__m_l1tex2xbar_req_cycles_active 91 %,
 // profiles/r1_final_*): every stored entry costs k/4 lane-level REDG.128.  Here NT of the G
@@ -371,4 +470,33 @@ extern "C" int mk_sspmm_bwd_tma(const mk_part* parts, int64_t num_parts, const i
     if (!parts || !dy || !sp_index) return MK_EINVAL;
     if (num_parts > 0x7fffffffLL) return MK_EUNSUPPORTED;
     return mk::launch_bwd_tma<32, uint8_t>(parts, num_parts, idx, val, dy, sp_index, dxs, d, tma_neighbours, st);
+}
+
+extern "C" int mk_sspmm_bwd_tiled(const int32_t* blk_ptr, int n_blocks, const int32_t* idx, const float* val,
+                                  const float* dy, const void* sp_index, int index_bytes, float* dxs,
+                                  int64_t n_rows, int64_t n_src, int k, int d, void* stream) {
+    if (n_rows < 0 || n_src < 0 || n_blocks < 1 || d < 1 || k < 1 || k > d) return MK_EINVAL;
+    if (index_bytes != 1 && index_bytes != 2) return MK_EINVAL;
+    if ((index_bytes == 1 && d > 256) || d > 65536) return MK_EINVAL;
+    if (k != 8 && k != 16 && k != 32 && k != 64) return MK_EUNSUPPORTED;
+    if (d % 4 != 0) return MK_EUNSUPPORTED;
+    if (n_src == 0) return MK_OK;
+    if (!dxs || (reinterpret_cast<uintptr_t>(dxs) & 15)) return MK_EINVAL;
+    cudaStream_t st = mk::as_stream(stream);
+    MK_CUDA_TRY(cudaMemsetAsync(dxs, 0, static_cast<size_t>(n_src) * k * sizeof(float), st));
+    if (n_rows == 0) return MK_OK;
+    if (!blk_ptr || !dy || !sp_index || !idx || !val) return MK_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(sp_index) & (4 * index_bytes - 1)))
+        return MK_EINVAL;
+#define MK_TILED(KK)                                                                                              \
+    return index_bytes == 1                                                                                       \
+               ? mk::launch_bwd_tiled<KK, uint8_t>(blk_ptr, n_blocks, idx, val, dy, sp_index, dxs, d, n_rows, st)  \
+               : mk::launch_bwd_tiled<KK, uint16_t>(blk_ptr, n_blocks, idx, val, dy, sp_index, dxs, d, n_rows, st)
+    switch (k) {
+        case 8: MK_TILED(8);
+        case 16: MK_TILED(16);
+        case 32: MK_TILED(32);
+        default: MK_TILED(64);
+    }
+#undef MK_TILED
 }

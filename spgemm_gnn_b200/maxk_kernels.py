@@ -33,7 +33,8 @@ __all__ = [
     "maxk_forward_cbsr", "cbsr_scatter", "cbsr_gather", "partition",
     "clear_partition_cache", "install_partition", "set_max_nz", "get_max_nz", "launch_count",
     "banked_supported", "cbsr_bank", "block_split", "packed_supported", "cbsr_bank_packed",
-    "spgemm_forward_packed", "use_packed", "ForwardExchange", "maxk_forward_banked", "spgemm_forward_banked",
+    "spgemm_forward_packed", "use_packed", "ForwardExchange", "set_backward_tiled", "backward_tiles",
+    "block_pointers", "maxk_forward_banked", "spgemm_forward_banked",
     "spgemm_backward_banked", "set_banked", "set_backward_tma", "use_banked", "forward_variant", "partition_blocked", "backward_blocks",
     "set_backward_block_mb", "add_layernorm_supported", "add_layernorm_forward", "layernorm_backward",
 ]
@@ -284,6 +285,7 @@ def clear_partition_cache() -> None:
     _part_cache.clear()
     _block_cache.clear()
     _split_cache.clear()
+    _blkptr_cache.clear()
 
 
 def partition(ptr: torch.Tensor, num_nodes: int, max_nz: Optional[int] = None) -> _Partition:
@@ -483,6 +485,66 @@ def spgemm_forward(ptr, idx, val, sp_data, sp_index, num_nodes, num_edges, dim_s
     return out, sp_index
 
 
+# Column-blocked, row-tiled backward (csrc/sspmm_bwd.cu, mk_sspmm_bwd_tiled) for CBSR gradients that do
+# not fit L2: "auto" = when n_src * k * 4 bytes exceed _BWD_TILED_MIN_MB, "0" / "1" force it off / on.
+_BWD_TILED = os.environ.get("MAXK_BWD_TILED", "auto")
+_BWD_TILED_MIN_MB = int(os.environ.get("MAXK_BWD_TILED_MIN_MB", "112"))
+_BWD_TILE_MB = int(os.environ.get("MAXK_BWD_TILE_MB", "64"))     # slice of dXs one column block covers
+_blkptr_cache = {}
+
+
+def set_backward_tiled(mode, tile_mb: Optional[int] = None) -> None:
+    """mode: "auto", True / "1", False / "0"; tile_mb: MB of the CBSR gradient per column block."""
+    global _BWD_TILED, _BWD_TILE_MB
+    _BWD_TILED = mode if isinstance(mode, str) else ("1" if mode else "0")
+    if tile_mb is not None:
+        _BWD_TILE_MB = max(int(tile_mb), 1)
+
+
+def backward_tiles(n_src: int, dim_sparse: int, dim_origin: int) -> int:
+    """Column blocks the tiled backward would use for this shape (0: the plain backward runs)."""
+    if _BWD_TILED == "0" or dim_sparse not in (8, 16, 32, 64) or dim_origin % 4:
+        return 0
+    nbytes = n_src * dim_sparse * 4
+    if _BWD_TILED == "auto" and nbytes <= (_BWD_TILED_MIN_MB << 20):
+        return 0
+    return max(2, min(64, -(-nbytes // (_BWD_TILE_MB << 20))))
+
+
+def _rows_ascending(ptr: torch.Tensor, idx: torch.Tensor, num_nodes: int) -> bool:
+    """Column ids ascending inside every CSR row?  (One pass, one sync; callers cache the answer.)"""
+    e = int(idx.numel())
+    if e < 2:
+        return True
+    bad = idx[1:] < idx[:-1]
+    starts = ptr[1:num_nodes].to(torch.int64)
+    starts = starts[(starts > 0) & (starts < e)]
+    bad[starts - 1] = False
+    return not bool(bad.any())
+
+
+def block_pointers(ptr: torch.Tensor, idx: torch.Tensor, num_nodes: int, n_blocks: int, width: int) -> torch.Tensor:
+    """int32 [(n_blocks+1) * num_nodes]: blk[b*n + r] = first position of CSR row r whose column id is
+    >= b * width (mk_block_ptr).  None when the column ids of some row are not ascending (the
+    caller then stays on the un-blocked kernel).  Cached per graph."""
+    global _launches
+    key = (ptr.device.index, ptr.data_ptr(), idx.data_ptr(), int(num_nodes), int(n_blocks), int(width))
+    hit = _blkptr_cache.get(key)
+    if hit is not None and hit[0]() is ptr and hit[1] == ptr._version:
+        return hit[2]
+    blk = None
+    if _rows_ascending(ptr, idx, num_nodes):
+        blk = torch.empty(((n_blocks + 1) * num_nodes,), dtype=torch.int32, device=ptr.device)
+        with torch.cuda.device(ptr.device):
+            _lib.check(_lib.lib().mk_block_ptr(ptr.data_ptr(), idx.data_ptr(), num_nodes, n_blocks, width,
+                                               blk.data_ptr(), _stream()), "mk_block_ptr")
+        _launches += 1
+    if len(_blkptr_cache) >= 16:
+        del _blkptr_cache[next(iter(_blkptr_cache))]
+    _blkptr_cache[key] = (weakref.ref(ptr), ptr._version, blk)
+    return blk
+
+
 def spgemm_backward(ptr, idx, val, grad_output, sp_index, num_nodes, num_edges, dim_sparse, dim_origin,
                     *, out: Optional[torch.Tensor] = None):
     """dXs[j,t] = sum over stored e=(r<-j) of val[e] * grad_output[r, sp_index[j,t]]; fp32
@@ -513,8 +575,17 @@ def spgemm_backward(ptr, idx, val, grad_output, sp_index, num_nodes, num_edges, 
              "out must be float32 [sp_index.size(0), dim_sparse]")
         dxs = out
     tma = _BWD_TMA if (ib == 1 and dim_sparse == 32 and _BWD_TMA in (1, 2, 4)) else 0
+    tiles = backward_tiles(n_src, dim_sparse, dim_origin) if (nb <= 1 and not tma and num_nodes > 0) else 0
     with torch.cuda.device(grad_output.device):
-        if tma:
+        blk = None
+        if tiles:
+            width = -(-n_src // tiles)
+            blk = block_pointers(ptr, idx, num_nodes, tiles, width)
+        if blk is not None:
+            rc = _lib.lib().mk_sspmm_bwd_tiled(
+                blk.data_ptr(), tiles, idx.data_ptr(), val.data_ptr(), grad_output.data_ptr(),
+                sp_index.data_ptr(), ib, dxs.data_ptr(), num_nodes, n_src, dim_sparse, dim_origin, _stream())
+        elif tma:
             rc = _lib.lib().mk_sspmm_bwd_tma(
                 parts.data_ptr(), part.num_parts, idx.data_ptr(), val.data_ptr(),
                 grad_output.data_ptr(), sp_index.data_ptr(), ib, dxs.data_ptr(), num_nodes, n_src,

@@ -804,3 +804,50 @@ def test_packed_banked_forward_k8_k16(mk, n, deg, d, k):
     assert torch.equal(auto, out)
     plain, _ = mk.spgemm_forward(g.indptr, g.indices, val, sd, si, n, e, k, d, allow_banked=False)
     assert_rel(plain, want, bound, "plain forward")
+
+
+@pytest.mark.parametrize("n,deg,d,k,tile_mb", [(3000, 40, 256, 32, 0), (2500, 60, 256, 16, 0), (2000, 30, 128, 8, 0),
+                                               (1500, 50, 384, 64, 0), (4000, 12, 256, 32, 0)])
+def test_tiled_column_blocked_backward(mk, n, deg, d, k, tile_mb):
+    """mk_sspmm_bwd_tiled (the backward for CBSR gradients larger than L2): forced on with column
+    blocks of a few hundred sources, it meets the oracle at the 1e-5 bar and agrees with the plain
+    kernel -- including empty rows, a row that holds a large share of all stored entries, and a row
+    count that is not a multiple of the 8-row tile."""
+    from oracle import c_oracle
+    from spgemm_gnn_b200 import maxk_kernels as mkk
+    from conftest import small_graph
+    g = small_graph(n - 3, deg, seed=n + k, device="cuda")          # n-3 rows: ragged last tile
+    nn, e = g.num_nodes(), g.num_edges()
+    rng = np.random.default_rng(n + d)
+    x = rng.standard_normal((nn, d)).astype(np.float32)
+    dy = rng.standard_normal((nn, d)).astype(np.float32)
+    val = g.edge_weights("both")
+    sd, si = mk.maxk_forward_cbsr(dev(x), k)
+    ptr, idx, v = g.indptr.cpu().numpy(), g.indices.cpu().numpy(), val.cpu().numpy()
+    wi = _np_index(si, d)
+    want = c_oracle.sspmm_bwd(ptr, idx, v, dy, wi)
+    bound = c_oracle.sspmm_bwd(ptr, idx, np.abs(v), np.abs(dy), wi)
+    plain = mk.spgemm_backward(g.indptr, g.indices, val, dev(dy), si, nn, e, k, d)
+    saved = (mkk._BWD_TILED, mkk._BWD_TILE_MB)
+    try:
+        mkk._BWD_TILED = "1"
+        for blocks in (2, 5, 13):
+            mkk._blkptr_cache.clear()
+            mkk.backward_tiles = lambda *_a, _b=blocks: _b            # this many column blocks
+            tiled = mkk.spgemm_backward(g.indptr, g.indices, val, dev(dy), si, nn, e, k, d)
+            assert_rel(tiled, want, bound, f"tiled backward, {blocks} column blocks")
+            assert float((tiled - plain).abs().max()) <= 2e-5 * float(plain.abs().max())
+    finally:
+        mkk._BWD_TILED, mkk._BWD_TILE_MB = saved
+        mkk.backward_tiles = _ORIG_BACKWARD_TILES
+        mkk._blkptr_cache.clear()
+    # unsorted column ids: the blocked form refuses (falls back to the plain kernel), same result
+    perm_idx = g.indices.clone()
+    lo, hi = int(g.indptr[5]), int(g.indptr[6])
+    perm_idx[lo:hi] = perm_idx[lo:hi].flip(0)
+    if hi - lo > 1:
+        assert mkk.block_pointers(g.indptr, perm_idx, nn, 4, -(-nn // 4)) is None
+
+
+from spgemm_gnn_b200 import maxk_kernels as _mkk_for_tiles  # noqa: E402
+_ORIG_BACKWARD_TILES = _mkk_for_tiles.backward_tiles
