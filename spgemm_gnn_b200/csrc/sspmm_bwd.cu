@@ -60,14 +60,41 @@ sspmm_bwd_body(const mk_part* __restrict__ parts, const int* __restrict__ idx,
     __syncwarp();
 
     const int end = rec.loc + rec.len;
+#ifdef MK_EDGE_CPASYNC
+    // Measured variant (BASELINE.json part 2: "cp.async/TMA to stage ... edge slices"): the next
+    // 32-entry slice of idx / val is copied to shared memory with cp.async (LDGSTS) while the current
+    // one is consumed, and read back with group-uniform LDS instead of SHFL broadcasts.  Slower on
+    // every shape tried (profiles/r2/cpasync_edges.log): the kernel is bound by the L1TEX data pipe
+    // and the SM->L2 request path, LDGSTS adds shared-memory write wavefronts and an LDS per broadcast
+    // to exactly that pipe, and the latency it hides is already hidden by 32 resident warps per SM.
+    __shared__ int s_nz[2][32];
+    __shared__ float s_v[2][32];
+    auto stage = [&](int buf, int base) {
+        if (base + lane < end) {
+            const unsigned dn = static_cast<unsigned>(__cvta_generic_to_shared(&s_nz[buf][lane]));
+            const unsigned dv = static_cast<unsigned>(__cvta_generic_to_shared(&s_v[buf][lane]));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dn), "l"(idx + base + lane) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dv), "l"(val + base + lane) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0, rec.loc);
+    int cur = 0;
+#endif
     for (int base = rec.loc; base < end; base += 32) {
         const int n_here = min(32, end - base);
+#ifdef MK_EDGE_CPASYNC
+        stage(cur ^ 1, base + 32);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+#else
         int my_nz = 0;
         float my_v = 0.f;
         if (lane < n_here) {
             my_nz = ld_stream_i1(idx + base + lane);
             my_v = ld_stream_f1(val + base + lane);
         }
+#endif
         for (int i = 0; i < n_here; i += G * U) {
             int cv[U][4];
             int nzv[U];
@@ -76,8 +103,13 @@ sspmm_bwd_body(const mk_part* __restrict__ parts, const int* __restrict__ idx,
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int e = i + u * G + g;
+#ifdef MK_EDGE_CPASYNC
+                nzv[u] = s_nz[cur][e & 31];
+                vv[u] = s_v[cur][e & 31];
+#else
                 nzv[u] = __shfl_sync(kFull, my_nz, e & 31);
                 vv[u] = __shfl_sync(kFull, my_v, e & 31);
+#endif
                 ok[u] = e < n_here;
                 if (ok[u]) load_cols4<IdxT>(sp_index + static_cast<int64_t>(nzv[u]) * K + 4 * t, cv[u]);
             }
@@ -90,6 +122,10 @@ sspmm_bwd_body(const mk_part* __restrict__ parts, const int* __restrict__ idx,
                 }
             }
         }
+#ifdef MK_EDGE_CPASYNC
+        __syncwarp();
+        cur ^= 1;
+#endif
     }
 }
 

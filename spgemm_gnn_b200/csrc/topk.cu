@@ -14,12 +14,20 @@
 
 namespace mk {
 
+// Order-preserving uint32 key of a float: larger value <=> larger key, every NaN above +inf (the
+// torch.topk convention), -0.0 ties with +0.0.  Three instructions: `v + 0.0f` turns -0.0 into +0.0
+// and every NaN into the canonical 0x7FFFFFFF (an fp32 add never returns another NaN pattern), then
+// positive values get their sign bit set and negative ones are complemented.
 __device__ __forceinline__ uint32_t order_key(float v) {
-    const uint32_t b = __float_as_uint(v);
-    uint32_t key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-    if (b == 0x80000000u) key = 0x80000000u;  // -0.0 ties with +0.0
-    if (v != v) key = 0xFFFFFFFFu;            // every NaN above +inf (torch.topk convention)
-    return key;
+    const int32_t b = __float_as_int(__fadd_rn(v, 0.0f));
+    return static_cast<uint32_t>(b) ^ (static_cast<uint32_t>(b >> 31) | 0x80000000u);
+}
+
+// c += (key >= cand), cand != 0, given ncand = -cand: the carry out of key + (2^32 - cand).  Two integer
+// instructions per element, and ptxas folds two carries into one IADD3.X (the compiler's own
+// `c += key >= cand` is a compare, an add and a predicated move per element).
+__device__ __forceinline__ void count_ge(int& c, uint32_t key, uint32_t ncand) {
+    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, 0;\n\t}" : "+r"(c) : "r"(key), "r"(ncand));
 }
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
@@ -66,9 +74,10 @@ topk_cbsr_reg_kernel(const float* __restrict__ x, int64_t n, int d, int k,
     bool exact = false;
     for (int bit = 31; bit >= 0; --bit) {
         const uint32_t cand = thr | (1u << bit);
+        const uint32_t ncand = 0u - cand;
         int c = 0;
 #pragma unroll
-        for (int e = 0; e < NV4 * 4; ++e) c += (key[e] >= cand) ? 1 : 0;
+        for (int e = 0; e < NV4 * 4; ++e) count_ge(c, key[e], ncand);
         c = __reduce_add_sync(kFull, c);
         if (c >= k) {
             thr = cand;

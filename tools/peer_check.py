@@ -172,24 +172,41 @@ def distributed(bench: bool) -> int:
             out, fi = mdist.sharded_forward(sd, si, ptr, idx, val, n_rows, d)
             return out, fi, mdist.sharded_backward(dy, fi, ptr, idx, val, n_rows, d)
 
+        def timed(fn, reps=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b) / reps], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
         res, times = {}, {}
         for mode in (False, True, True):   # NCCL, peer, peer again (window re-use: epochs 2..)
             peer.set_enabled(mode)
             res[mode] = step()
             if bench:
-                for _ in range(3):
-                    step()
-                torch.cuda.synchronize()
-                dist.barrier()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                for _ in range(20):
-                    step()
-                b.record()
-                torch.cuda.synchronize()
-                t = torch.tensor([a.elapsed_time(b) / 20], device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                times[mode] = float(t.item())
+                times[mode] = timed(step)
+        if bench and "--sweep" in sys.argv:
+            # who moves the rows / how many pusher CTAs, forward and backward timed on their own
+            fi0 = res[True][1]
+            for push, pushers in (("nccl", 0), ("sm", 592), ("sm", 148), ("sm", 296), ("sm", 1184), ("dma", 0)):
+                peer.set_enabled(push != "nccl")
+                if push != "nccl":
+                    peer._PUSH, peer._PUSHERS = push, pushers or peer._PUSHERS
+                tf = timed(lambda: mdist.sharded_forward(sd, si, ptr, idx, val, n_rows, d))
+                tb = timed(lambda: mdist.sharded_backward(dy, fi0, ptr, idx, val, n_rows, d))
+                ts = timed(step)
+                if rank == 0:
+                    print(f"  {name} [{push} {pushers}]: fwd {tf:.3f}  bwd {tb:.3f}  fwd+bwd {ts:.3f} ms", flush=True)
+            peer._PUSH, peer._PUSHERS = "sm", 592
+            peer.set_enabled(True)
         o0, f0, b0 = res[False]
         o1, f1, b1 = res[True]
         fwd_equal = torch.equal(o0, o1) and torch.equal(f0, f1)
