@@ -208,6 +208,29 @@ MK_API int mk_spgemm_fwd_banked_ex(const mk_part* parts, int64_t num_parts, int6
                                    const float* bk_data, const uint16_t* bk_slot, float* out,
                                    float* partial, int64_t n_rows, int k, int d, const int32_t* split,
                                    const mk_fwd_exchange* xchg, void* stream);
+/* One phase of a forward that is cut by SOURCE BLOCK ("chunk the all-gather by
+ * source rank and start on the local block first").  blk_ptr is mk_block_ptr's output for n_blocks
+ * blocks: blk_ptr[b * row_stride + r] = position in idx of row r's first entry of block b
+ * (b = n_blocks: the row's end).  The launch walks the entries of blocks [a0, a1), then [b0, b1) (two
+ * ranges, because "rank, rank+1, ..." wraps around); `accumulate` adds to the rows the earlier phases
+ * wrote instead of overwriting them; `last` keeps the completion contract of mk_fwd_exchange (the kernel
+ * returns when the whole table has arrived) -- earlier phases only wait for the blocks they read.
+ * The phases of one forward must cover every block exactly once; the row sums then differ from the
+ * one-launch forward only by the association of the per-phase partial sums.                         */
+typedef struct mk_fwd_phase {
+    const int32_t* blk_ptr;
+    int64_t row_stride;
+    int32_t n_blocks;
+    int32_t a0, a1, b0, b1;
+    int32_t accumulate;
+    int32_t last;
+} mk_fwd_phase;
+MK_API int mk_spgemm_fwd_banked_phase(const mk_part* parts, int64_t num_parts, int64_t num_slots,
+                                      const mk_part* exec_parts, const int32_t* idx, const float* val,
+                                      const float* bk_data, const uint16_t* bk_slot, float* out,
+                                      float* partial, int64_t n_rows, int k, int d,
+                                      const mk_fwd_exchange* xchg, const mk_fwd_phase* phase,
+                                      void* stream);
 /* Packed banked CBSR for k = 8, 16 (mk_packed_supported): one entry = {float value, uint16 cell,
  * uint16 column} in 8 bytes, bk_pack [n, k] of them, so that a lane fetches value and cell offset with
  * ONE load -- at these widths the forward is bound by L1 wavefronts per gathered row, and the separate

@@ -41,6 +41,8 @@ SIGNATURES = {
     "mk_spgemm_fwd_banked": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "mk_spgemm_fwd_banked_ex": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
                                        _vp, _vp, _vp]),
+    "mk_spgemm_fwd_banked_phase": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
+                                          _vp, _vp, _vp]),
     "mk_packed_supported": (_i32, [_i32, _i32]),
     "mk_cbsr_bank_packed": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, _i32, _vp]),
     "mk_spgemm_fwd_packed_ex": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
@@ -71,6 +73,13 @@ class FwdExchange(ctypes.Structure):
                 ("rows_per_rank", _i64), ("timeout_ms", ctypes.c_int32), ("pushers", ctypes.c_int32),
                 ("h_windows", ctypes.POINTER(_vp)), ("n_seg", ctypes.c_int32),
                 ("h_offsets", ctypes.POINTER(_i64)), ("h_bytes", ctypes.POINTER(_i64))]
+
+
+class FwdPhase(ctypes.Structure):
+    """`mk_fwd_phase` of include/maxk_b200.h."""
+    _fields_ = [("blk_ptr", _vp), ("row_stride", _i64), ("n_blocks", ctypes.c_int32),
+                ("a0", ctypes.c_int32), ("a1", ctypes.c_int32), ("b0", ctypes.c_int32), ("b1", ctypes.c_int32),
+                ("accumulate", ctypes.c_int32), ("last", ctypes.c_int32)]
 
 
 _lib = None

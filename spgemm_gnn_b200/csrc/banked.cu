@@ -162,6 +162,20 @@ struct FwdWait {
     PushDesc push;
 };
 
+// One PHASE of a forward that is cut by source block (mk_fwd_phase): the launch only walks the stored
+// entries whose column lies in the blocks [a0, a1) and then [b0, b1) (blk[b * stride + row] = position
+// in idx of the row's first entry of block b, mk_block_ptr), and either writes the output rows or adds
+// to what the earlier phases wrote.  A row-partitioned forward runs the phases in the order the
+// peers' rows arrive -- own block, the next few senders, the rest -- so that whole launches, not
+// just the CTAs that happen to be resident, overlap the transfer.
+struct FwdPhase {
+    const int* blk;  // null: no phases (the record's whole range, `split` order)
+    int64_t stride;
+    int a0, a1, b0, b1;
+    int accumulate;  // add to the rows already in `out`
+    int last;        // the kernel's completion must mean "the whole table has arrived"
+};
+
 // `split` (nullable): per CSR row, the position in idx of the first stored entry whose column is
 // >= rank*rows_per_rank.  A record then walks [split, end) first and [begin, split) second, i.e.
 // the source blocks in the order rank, rank+1, ..., world-1, 0, ..., rank-1 -- the order in which
@@ -172,7 +186,7 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
                          const float* __restrict__ val, const float* __restrict__ bk_data,
                          const uint16_t* __restrict__ bk_slot, float* __restrict__ out,
                          float* __restrict__ partial, int d, int rows, const int* __restrict__ split,
-                         const FwdWait fw) {
+                         const FwdWait fw, const FwdPhase ph) {
     constexpr int CAP = K / 8;
     extern __shared__ __align__(16) float acc[];  // 32 * rows
     const int lane = lane_id();
@@ -212,12 +226,25 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
     float* __restrict__ my = acc + 8 * g;
     [[maybe_unused]] const unsigned gmask = 0xffu << (8 * g);  // the lanes that share this group's banks
     const int lo = rec.loc, hi = rec.loc + rec.len;
-    int sp = lo;
-    if (split != nullptr) sp = min(max(__ldg(split + rec.row), lo), hi);
+    int r0b, r0e, r1b, r1e;  // the two ranges of idx this launch walks, in this order
+    if (ph.blk != nullptr) {
+        const int* __restrict__ bp = ph.blk + rec.row;
+        r0b = min(max(__ldg(bp + ph.a0 * ph.stride), lo), hi);
+        r0e = min(max(__ldg(bp + ph.a1 * ph.stride), lo), hi);
+        r1b = r1e = lo;
+        if (ph.b1 > ph.b0) {
+            r1b = min(max(__ldg(bp + ph.b0 * ph.stride), lo), hi);
+            r1e = min(max(__ldg(bp + ph.b1 * ph.stride), lo), hi);
+        }
+    } else {
+        int sp = lo;
+        if (split != nullptr) sp = min(max(__ldg(split + rec.row), lo), hi);
+        r0b = sp; r0e = hi; r1b = lo; r1e = sp;
+    }
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-        const int b0 = pass == 0 ? sp : lo;
-        const int end = pass == 0 ? hi : sp;
+        const int b0 = pass == 0 ? r0b : r1b;
+        const int end = pass == 0 ? r0e : r1e;
         for (int base = b0; base < end; base += 32) {
             const int n_here = min(32, end - base);
             int my_nz = 0;
@@ -277,7 +304,7 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
     __syncwarp();
     // the kernel's completion must mean "the whole table has arrived" (the backward reads the
     // gathered column ids after it): one CTA waits for every sender
-    if (WAIT && role == 0 && lane < fw.world)
+    if (WAIT && ph.last && role == 0 && lane < fw.world)
         wait_flag(fw.hdr + kHdrDone + lane, epoch, const_cast<uint32_t*>(fw.hdr) + kHdrError, fw.timeout_ns);
 
     // ---- fold the 4 groups and the 2 copies.  Lane (s, b) sums, for row 4i+s, the cells of bank
@@ -312,6 +339,15 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
     __syncwarp();
     float* __restrict__ o = rec.slot < 0 ? out + static_cast<int64_t>(rec.row) * d
                                          : partial + static_cast<int64_t>(rec.slot) * d;
+    if (ph.accumulate && rec.slot < 0) {  // later phase: on top of what the earlier ones wrote
+        for (int c = lane * 4; c < d; c += 128) {
+            float4 a = *reinterpret_cast<const float4*>(acc + c);
+            const float4 p = *reinterpret_cast<const float4*>(o + c);
+            a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+            st_stream_f4(o + c, a);
+        }
+        return;
+    }
     for (int c = lane * 4; c < d; c += 128)
         st_stream_f4(o + c, *reinterpret_cast<const float4*>(acc + c));
 }
@@ -406,7 +442,7 @@ template <int K, bool PACKED>
 static int launch_fwd_banked(const mk_part* parts, int64_t num_parts, const int* idx,
                              const float* val, const float* bk_data, const uint16_t* bk_slot,
                              float* out, float* partial, int d, int rows, const int* split,
-                             const FwdWait& fw, cudaStream_t st) {
+                             const FwdWait& fw, const FwdPhase& ph, cudaStream_t st) {
 #ifdef MK_FWD_U
     constexpr int U = MK_FWD_U;
 #else
@@ -421,14 +457,14 @@ static int launch_fwd_banked(const mk_part* parts, int64_t num_parts, const int*
         const int64_t grid = num_parts + fw.push.pushers;
         if (grid > 0x7fffffffLL) return MK_EUNSUPPORTED;
         kern<<<static_cast<unsigned>(grid), 32, smem, st>>>(parts, idx, val, bk_data, bk_slot, out,
-                                                            partial, d, rows, split, fw);
+                                                            partial, d, rows, split, fw, ph);
     } else {
         auto kern = spgemm_fwd_banked_kernel<K, U, false, PACKED>;
         if (smem > 48 * 1024)
             MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem)));
         kern<<<static_cast<unsigned>(num_parts), 32, smem, st>>>(parts, idx, val, bk_data, bk_slot, out,
-                                                                 partial, d, rows, split, fw);
+                                                                 partial, d, rows, split, fw, ph);
     }
     MK_LAUNCH_CHECK("spgemm_fwd_banked_kernel");
     return MK_OK;
@@ -451,7 +487,7 @@ static int launch_bwd_banked(const mk_part* parts, int64_t num_parts, const int*
 }
 
 int launch_fold(const mk_part* parts, int64_t num_parts, const float* partial, float* out, int d,
-                cudaStream_t st);  // spgemm_fwd.cu
+                cudaStream_t st, int accumulate = 0);  // spgemm_fwd.cu
 
 }  // namespace mk
 
@@ -463,8 +499,20 @@ static int fwd_banked_any(bool packed, const mk_part* parts, int64_t num_parts, 
                          const mk_part* exec_parts, const int32_t* idx, const float* val,
                          const float* bk_data, const uint16_t* bk_slot, float* out, float* partial,
                          int64_t n_rows, int k, int d, const int32_t* split, const mk_fwd_exchange* x,
-                         void* stream) {
+                         const mk_fwd_phase* phase, void* stream) {
     if (n_rows < 0 || num_parts < 0 || num_slots < 0 || d < 1 || k < 1 || k > d) return MK_EINVAL;
+    mk::FwdPhase ph{};
+    ph.last = 1;
+    if (phase != nullptr && phase->blk_ptr != nullptr) {
+        if (phase->n_blocks < 1 || phase->a0 < 0 || phase->a1 < phase->a0 || phase->a1 > phase->n_blocks ||
+            phase->b0 < 0 || phase->b1 < phase->b0 || phase->b1 > phase->n_blocks || phase->row_stride < n_rows)
+            return MK_EINVAL;
+        ph.blk = phase->blk_ptr;
+        ph.stride = phase->row_stride;
+        ph.a0 = phase->a0; ph.a1 = phase->a1; ph.b0 = phase->b0; ph.b1 = phase->b1;
+        ph.accumulate = phase->accumulate ? 1 : 0;
+        ph.last = phase->last ? 1 : 0;
+    }
     if (!mk_banked_supported(k, d) || (packed && k > 16)) return MK_EUNSUPPORTED;
     const bool waiting = x != nullptr && x->window != nullptr;
     if (waiting) {
@@ -486,7 +534,7 @@ static int fwd_banked_any(bool packed, const mk_part* parts, int64_t num_parts, 
     const bool pushing = waiting && x->h_windows != nullptr && x->world > 1;
     if ((n_rows == 0 || num_parts == 0) && !pushing) {
         // nothing to compute, but the collective's contract stands: return once the table is complete
-        if (waiting) return mk_peer_wait_all(const_cast<void*>(x->window), x->world, x->timeout_ms, stream);
+        if (waiting && ph.last) return mk_peer_wait_all(const_cast<void*>(x->window), x->world, x->timeout_ms, stream);
         return MK_OK;
     }
     if (!parts || !out || !bk_data || (!packed && !bk_slot)) return MK_EINVAL;
@@ -519,18 +567,18 @@ static int fwd_banked_any(bool packed, const mk_part* parts, int64_t num_parts, 
     const int rows = mk_banked_rows(d);
     int rc;
     if (packed) {
-        rc = k == 8 ? mk::launch_fwd_banked<8, true>(ex, num_parts, idx, val, bk_data, nullptr, out, partial, d, rows, split, fw, st)
-                    : mk::launch_fwd_banked<16, true>(ex, num_parts, idx, val, bk_data, nullptr, out, partial, d, rows, split, fw, st);
+        rc = k == 8 ? mk::launch_fwd_banked<8, true>(ex, num_parts, idx, val, bk_data, nullptr, out, partial, d, rows, split, fw, ph, st)
+                    : mk::launch_fwd_banked<16, true>(ex, num_parts, idx, val, bk_data, nullptr, out, partial, d, rows, split, fw, ph, st);
     } else {
         switch (k) {
-            case 8: rc = mk::launch_fwd_banked<8, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, st); break;
-            case 16: rc = mk::launch_fwd_banked<16, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, st); break;
-            case 32: rc = mk::launch_fwd_banked<32, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, st); break;
-            default: rc = mk::launch_fwd_banked<64, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, st); break;
+            case 8: rc = mk::launch_fwd_banked<8, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, ph, st); break;
+            case 16: rc = mk::launch_fwd_banked<16, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, ph, st); break;
+            case 32: rc = mk::launch_fwd_banked<32, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, ph, st); break;
+            default: rc = mk::launch_fwd_banked<64, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, ph, st); break;
         }
     }
     if (rc != MK_OK) return rc;
-    if (num_slots > 0) return mk::launch_fold(parts, num_parts, partial, out, d, st);
+    if (num_slots > 0) return mk::launch_fold(parts, num_parts, partial, out, d, st, ph.accumulate);
     return MK_OK;
 }
 
@@ -540,7 +588,17 @@ extern "C" int mk_spgemm_fwd_banked_ex(const mk_part* parts, int64_t num_parts, 
                                        float* partial, int64_t n_rows, int k, int d,
                                        const int32_t* split, const mk_fwd_exchange* xchg, void* stream) {
     return fwd_banked_any(false, parts, num_parts, num_slots, exec_parts, idx, val, bk_data, bk_slot, out,
-                          partial, n_rows, k, d, split, xchg, stream);
+                          partial, n_rows, k, d, split, xchg, nullptr, stream);
+}
+
+extern "C" int mk_spgemm_fwd_banked_phase(const mk_part* parts, int64_t num_parts, int64_t num_slots,
+                                          const mk_part* exec_parts, const int32_t* idx, const float* val,
+                                          const float* bk_data, const uint16_t* bk_slot, float* out,
+                                          float* partial, int64_t n_rows, int k, int d,
+                                          const mk_fwd_exchange* xchg, const mk_fwd_phase* phase,
+                                          void* stream) {
+    return fwd_banked_any(false, parts, num_parts, num_slots, exec_parts, idx, val, bk_data, bk_slot, out,
+                          partial, n_rows, k, d, nullptr, xchg, phase, stream);
 }
 
 extern "C" int mk_spgemm_fwd_packed_ex(const mk_part* parts, int64_t num_parts, int64_t num_slots,
@@ -550,7 +608,7 @@ extern "C" int mk_spgemm_fwd_packed_ex(const mk_part* parts, int64_t num_parts, 
                                        void* stream) {
     return fwd_banked_any(true, parts, num_parts, num_slots, exec_parts, idx, val,
                           static_cast<const float*>(bk_pack), nullptr, out, partial, n_rows, k, d, split,
-                          xchg, stream);
+                          xchg, nullptr, stream);
 }
 
 extern "C" int mk_spgemm_fwd_banked(const mk_part* parts, int64_t num_parts, int64_t num_slots,

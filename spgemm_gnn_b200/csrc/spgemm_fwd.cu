@@ -290,7 +290,7 @@ spgemm_fwd_generic_kernel(const mk_part* __restrict__ parts, const int* __restri
 // only the first record of such a row does work.
 __global__ void __launch_bounds__(256)
 spgemm_fold_kernel(const mk_part* __restrict__ parts, int64_t num_parts,
-                   const float* __restrict__ partial, float* __restrict__ out, int d) {
+                   const float* __restrict__ partial, float* __restrict__ out, int d, int accumulate) {
     const int64_t p = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (p >= num_parts) return;
     const mk_part rec = parts[p];
@@ -304,14 +304,14 @@ spgemm_fold_kernel(const mk_part* __restrict__ parts, int64_t num_parts,
     for (int c = lane; c < d; c += 32) {
         float s = src[c];
         for (int q = 1; q < cnt; ++q) s += src[static_cast<int64_t>(q) * d + c];
-        o[c] = s;
+        o[c] = accumulate ? o[c] + s : s;
     }
 }
 
 int launch_fold(const mk_part* parts, int64_t num_parts, const float* partial, float* out, int d,
-                cudaStream_t st) {
+                cudaStream_t st, int accumulate) {
     const int64_t blocks = (num_parts * 32 + 255) / 256;
-    spgemm_fold_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(parts, num_parts, partial, out, d);
+    spgemm_fold_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(parts, num_parts, partial, out, d, accumulate);
     MK_LAUNCH_CHECK("spgemm_fold_kernel");
     return MK_OK;
 }
@@ -440,6 +440,6 @@ extern "C" int mk_spgemm_fwd(const mk_part* parts, int64_t num_parts, int64_t nu
                        : mk::launch_fwd<uint16_t>(parts, num_parts, idx, val, sp_data, sp_index,
                                                   out, partial, k, d, st);
     if (rc != MK_OK) return rc;
-    if (num_slots > 0) return mk::launch_fold(parts, num_parts, partial, out, d, st);
+    if (num_slots > 0) return mk::launch_fold(parts, num_parts, partial, out, d, st, 0);
     return MK_OK;
 }

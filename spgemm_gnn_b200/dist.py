@@ -214,6 +214,14 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
     # peer form and the NCCL form (their forwards are bit-equal)
     split = (maxk_kernels.block_split(ptr, idx, num_rows, world, rank, r)
              if (form != "plain" and sp_data.is_cuda) else None)
+    # banked form: one launch per source-block phase (own block, the next senders, the rest), each adding
+    # to the rows of the earlier ones -- same launches, same sums, in the peer form and the NCCL form
+    phases = blk = None
+    if form == "banked" and sp_data.is_cuda and world > 1 and peer.phases():
+        blk = maxk_kernels.block_pointers(ptr, idx, num_rows, world, r)
+        if blk is not None:
+            phases = maxk_kernels.forward_phases(world, rank)
+    pkw = dict(phases=phases, blk=blk, n_blocks=world) if phases is not None else dict(split=split)
     if _peer_path(group, r * k * 4):
         rows = world * r
         per_rank = {"banked": [r * k * 4, r * k * 2, r * k * ib], "packed": [r * k * 8, r * k * ib],
@@ -257,8 +265,11 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
                 if wait is None:
                     peer.wait_all(win)
             if form == "banked":
+                if phases is not None and wait is not None:   # only the first launch carries the pushers
+                    rest = peer.exchange(win, r)
+                    wait = [wait] + [rest] * (len(phases) - 1)
                 out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, full_data, full_slot, num_rows, e, k,
-                                                         dim_origin, split=split, wait=wait)
+                                                         dim_origin, wait=wait, **pkw)
             elif form == "packed":
                 out = maxk_kernels.spgemm_forward_packed(ptr, idx, val, full_pack, num_rows, e, k, dim_origin,
                                                          split=split, wait=wait)
@@ -273,7 +284,7 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
         bk_data, _, bk_slot = maxk_kernels.cbsr_bank(sp_data, sp_index, dim_origin, with_index=False)
         full_data, full_slot, full_index = allgather_many([bk_data, bk_slot, sp_index], group)
         out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, full_data, full_slot, num_rows, e, k,
-                                                 dim_origin, split=split)
+                                                 dim_origin, **pkw)
     elif form == "packed":
         bk_pack = maxk_kernels.cbsr_bank_packed(sp_data, sp_index, dim_origin)
         full_pack, full_index = allgather_many([bk_pack, sp_index], group)

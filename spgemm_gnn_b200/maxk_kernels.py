@@ -30,7 +30,7 @@ from . import _lib
 
 __all__ = [
     "maxk_forward", "maxk_backward", "spgemm_forward", "spgemm_backward",
-    "maxk_forward_cbsr", "cbsr_scatter", "cbsr_gather", "partition",
+    "maxk_forward_cbsr", "cbsr_scatter", "cbsr_gather", "partition", "forward_phases",
     "clear_partition_cache", "install_partition", "set_max_nz", "get_max_nz", "launch_count",
     "banked_supported", "cbsr_bank", "block_split", "packed_supported", "cbsr_bank_packed",
     "spgemm_forward_packed", "use_packed", "ForwardExchange", "set_backward_tiled", "backward_tiles",
@@ -674,12 +674,36 @@ def maxk_forward_banked(input: torch.Tensor, k: int):
     return cbsr_bank(sp_data, sp_index, input.shape[1])
 
 
+def forward_phases(world: int, rank: int):
+    """Source-block phases of a row-partitioned forward, in arrival order: own block, the next
+    ~3/7 of the senders, the rest -- as block ranges `(a0, a1, b0, b1)` for `mk_fwd_phase` ("rank,
+    rank+1, ..." wraps around, hence two ranges).  8 ranks: {r}, {r+1..r+3}, {r+4..r+7}."""
+    world, rank = int(world), int(rank)
+    if world <= 1:
+        return [(0, 1, 0, 0)]
+    cuts = sorted({0, 1, min(world, 1 + max(1, round((world - 1) * 3 / 7))), world})
+    out = []
+    for s0, s1 in zip(cuts[:-1], cuts[1:]):
+        lo, hi = rank + s0, rank + s1
+        if hi <= world:
+            out.append((lo, hi, 0, 0))
+        elif lo >= world:
+            out.append((lo - world, hi - world, 0, 0))
+        else:
+            out.append((lo, world, 0, hi - world))
+    return out
+
+
 def spgemm_forward_banked(ptr, idx, val, bk_data, bk_slot, num_nodes, num_edges, dim_sparse, dim_origin,
-                          *, split: Optional[torch.Tensor] = None, wait=None):
+                          *, split: Optional[torch.Tensor] = None, wait=None, phases=None, blk=None,
+                          n_blocks: int = 0):
     """`spgemm_forward` on a banked table: same result, no shared-memory bank conflicts.
     Row-partitioned form (dist.py): `split` int32 [num_nodes] makes every record walk the source
     blocks in arrival order, `wait` (a `ForwardExchange`) lets the kernel run while the peers' rows are
-    still arriving and, with pushers, makes it the all-gather itself (peer.py)."""
+    still arriving and, with pushers, makes it the all-gather itself (peer.py).
+    `phases` (from `forward_phases`) + `blk` (`block_pointers` over `n_blocks` source blocks): one launch
+    per phase, each restricted to its blocks and adding to the rows of the earlier ones, so that whole
+    launches overlap the transfer; `wait` may then be a list with one exchange per phase."""
     global _launches
     _check_graph(ptr, idx, val)
     _cuda_contig(bk_data, "sp_data")
@@ -695,8 +719,28 @@ def spgemm_forward_banked(ptr, idx, val, bk_data, bk_slot, num_nodes, num_edges,
     out = torch.empty((num_nodes, dim_origin), dtype=torch.float32, device=bk_data.device)
     partial = part.partial_for(dim_origin, bk_data.device)
     ex = part.exec_parts()
+    L = _lib.lib()
+    if phases is not None:
+        _chk(blk is not None and blk.dtype == torch.int32 and blk.numel() >= (n_blocks + 1) * num_nodes,
+             "phases need the block pointers of the graph")
+        waits = wait if isinstance(wait, (list, tuple)) else [wait] * len(phases)
+        _chk(len(waits) == len(phases), "one exchange per phase")
+        with torch.cuda.device(bk_data.device):
+            for i, (a0, a1, b0, b1) in enumerate(phases):
+                ph = _lib.FwdPhase(blk.data_ptr(), num_nodes, int(n_blocks), a0, a1, b0, b1,
+                                   1 if i > 0 else 0, 1 if i == len(phases) - 1 else 0)
+                w = waits[i]
+                rc = L.mk_spgemm_fwd_banked_phase(
+                    part.parts.data_ptr(), part.num_parts, part.num_slots,
+                    ex.data_ptr() if ex is not part.parts else None, idx.data_ptr(), val.data_ptr(),
+                    bk_data.data_ptr(), bk_slot.data_ptr(), out.data_ptr(),
+                    partial.data_ptr() if partial is not None else None, num_nodes, dim_sparse, dim_origin,
+                    w.ref() if w is not None else None, ctypes.byref(ph), _stream())
+                _lib.check(rc, "mk_spgemm_fwd_banked_phase")
+                _launches += 1 + (1 if part.num_slots else 0)
+        return out
     with torch.cuda.device(bk_data.device):
-        rc = _lib.lib().mk_spgemm_fwd_banked_ex(
+        rc = L.mk_spgemm_fwd_banked_ex(
             part.parts.data_ptr(), part.num_parts, part.num_slots,
             ex.data_ptr() if ex is not part.parts else None, idx.data_ptr(), val.data_ptr(),
             bk_data.data_ptr(), bk_slot.data_ptr(), out.data_ptr(),

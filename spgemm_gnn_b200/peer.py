@@ -56,6 +56,9 @@ _OVERLAP = os.environ.get("MAXK_PEER_OVERLAP", "1") != "0"
 # pay ~4 us each and concurrent flows interfere -- profiles/r2/push_probe_call6.log, exchange_forms8_call7.log)
 _PUSH = os.environ.get("MAXK_PEER_PUSH", "sm")
 _PUSHERS = int(os.environ.get("MAXK_PEER_PUSHERS", "592"))   # pusher CTAs (32 threads each)
+# forward cut into source-block phases (own block, the next senders, the rest: one launch each), so
+# that whole launches overlap the transfer instead of the CTAs that happen to be resident
+_PHASES = os.environ.get("MAXK_PEER_PHASES", "1") != "0"
 _launches = 0
 
 
@@ -82,6 +85,10 @@ def timeout_ms() -> int:
 
 def overlap() -> bool:
     return _OVERLAP
+
+
+def phases() -> bool:
+    return _PHASES and _OVERLAP
 
 
 def push_mode() -> str:

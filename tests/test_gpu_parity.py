@@ -770,6 +770,48 @@ def test_forward_arrival_order_walk_and_sorted_records(mk, k):
         mk.clear_partition_cache()
 
 
+@pytest.mark.parametrize("world,rank,k,max_nz", [(8, 5, 32, 64), (4, 0, 32, 1024), (2, 1, 64, 64), (3, 2, 32, 16)])
+def test_forward_in_source_block_phases(mk, world, rank, k, max_nz):
+    """The forward cut into source-block phases (mk_spgemm_fwd_banked_phase: own block, the next
+    senders, the rest; one launch each, later ones adding to the rows of the earlier ones) covers every
+    stored entry exactly once: float64 oracle at the 1e-5 bar, rows of several records included, and
+    repeatable bit for bit."""
+    from oracle import c_oracle
+    from conftest import small_graph
+    g = small_graph(2600, 90, seed=21, device="cuda")
+    n, e, d = g.num_nodes(), g.num_edges(), 256
+    rng = np.random.default_rng(world * 10 + rank)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    val = g.edge_weights("mean")
+    sd, si = mk.maxk_forward_cbsr(dev(x), k)
+    bd, _, bs = mk.cbsr_bank(sd, si, d, with_index=False)
+    mk.set_max_nz(max_nz)
+    try:
+        mk.clear_partition_cache()
+        r = -(-n // world)
+        blk = mk.block_pointers(g.indptr, g.indices, n, world, r)
+        phases = mk.forward_phases(world, rank)
+        got = mk.spgemm_forward_banked(g.indptr, g.indices, val, bd, bs, n, e, k, d, phases=phases, blk=blk,
+                                       n_blocks=world)
+        again = mk.spgemm_forward_banked(g.indptr, g.indices, val, bd, bs, n, e, k, d, phases=phases, blk=blk,
+                                         n_blocks=world)
+        ptr, idx = g.indptr.cpu().numpy(), g.indices.cpu().numpy()
+        want = c_oracle.spgemm_fwd(ptr, idx, val.cpu().numpy(), sd.cpu().numpy(), si.cpu().numpy(), d)
+        bound = c_oracle.spgemm_fwd(ptr, idx, np.abs(val.cpu().numpy()), np.abs(sd.cpu().numpy()), si.cpu().numpy(), d)
+        assert_rel(got, want, bound, f"phased forward, {len(phases)} phases")
+        assert torch.equal(got, again)
+        # a single phase over all blocks is the one-launch forward in the `split` order, bit for bit
+        whole = [(rank, world, 0, rank)]
+        split = mk.block_split(g.indptr, g.indices, n, world, rank, r)
+        one = mk.spgemm_forward_banked(g.indptr, g.indices, val, bd, bs, n, e, k, d, phases=whole, blk=blk,
+                                       n_blocks=world)
+        ref = mk.spgemm_forward_banked(g.indptr, g.indices, val, bd, bs, n, e, k, d, split=split)
+        assert torch.equal(one, ref)
+    finally:
+        mk.set_max_nz(1024)
+        mk.clear_partition_cache()
+
+
 @pytest.mark.parametrize("n,deg,d,k", [(1500, 150, 256, 8), (1500, 150, 256, 16), (800, 200, 128, 8),
                                        (600, 180, 384, 16), (700, 120, 64, 16)])
 def test_packed_banked_forward_k8_k16(mk, n, deg, d, k):

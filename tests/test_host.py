@@ -162,3 +162,17 @@ def test_tools_and_drivers_compile():
     assert len(files) >= 8
     for f in files:
         py_compile.compile(f, doraise=True)
+
+
+def test_forward_phases_cover_every_block_once_in_arrival_order():
+    """`forward_phases`: the rotated order rank, rank+1, ... cut into contiguous phases; every block in
+    exactly one phase, own block first."""
+    from spgemm_gnn_b200.maxk_kernels import forward_phases
+    for world in (1, 2, 3, 4, 5, 8, 16):
+        for rank in range(world):
+            seen = []
+            for a0, a1, b0, b1 in forward_phases(world, rank):
+                assert 0 <= a0 <= a1 <= world and 0 <= b0 <= b1 <= world
+                seen += list(range(a0, a1)) + list(range(b0, b1))
+            assert seen == [(rank + s) % world for s in range(world)], (world, rank, seen)
+    assert forward_phases(8, 5) == [(5, 6, 0, 0), (6, 8, 0, 1), (1, 5, 0, 0)]

@@ -91,8 +91,14 @@ def virtual(world: int) -> int:
                 # round 2: the forward kernel carries pusher CTAs as well (they re-send rows that are
                 # already there -- on one device the real overlap cannot be staged, the code path can)
                 x = peer.exchange(w, r, o, per_rank) if rnd == 2 else peer.exchange(w, r)
-                out = mk.spgemm_forward_banked(local.indptr, local.indices, vals[q], fd, fs, r, local.num_edges(),
-                                               kk, d, split=split, wait=x)
+                if rnd % 2 == 1:   # rounds 1, 3: the forward in source-block phases (one launch each)
+                    blk = mk.block_pointers(local.indptr, local.indices, r, world, r)
+                    out = mk.spgemm_forward_banked(local.indptr, local.indices, vals[q], fd, fs, r, local.num_edges(),
+                                                   kk, d, phases=mk.forward_phases(world, q), blk=blk,
+                                                   n_blocks=world, wait=x)
+                else:
+                    out = mk.spgemm_forward_banked(local.indptr, local.indices, vals[q], fd, fs, r, local.num_edges(),
+                                                   kk, d, split=split, wait=x)
                 peer.join_push(w)
                 outs.append((out, fd.clone(), fs.clone(), fi.clone()))
                 peer.release(w)
@@ -101,8 +107,14 @@ def virtual(world: int) -> int:
                 out, fd, fs, fi = outs[q]
                 local = shards[q][0]
                 split = mk.block_split(local.indptr, local.indices, r, world, q, r)
-                out_ref = mk.spgemm_forward_banked(local.indptr, local.indices, vals[q], want[0], want[1], r,
-                                                   local.num_edges(), kk, d, split=split)
+                if rnd % 2 == 1:
+                    blk = mk.block_pointers(local.indptr, local.indices, r, world, r)
+                    out_ref = mk.spgemm_forward_banked(local.indptr, local.indices, vals[q], want[0], want[1], r,
+                                                       local.num_edges(), kk, d, phases=mk.forward_phases(world, q),
+                                                       blk=blk, n_blocks=world)
+                else:
+                    out_ref = mk.spgemm_forward_banked(local.indptr, local.indices, vals[q], want[0], want[1], r,
+                                                       local.num_edges(), kk, d, split=split)
                 good = (torch.equal(fd, want[0]) and torch.equal(fs, want[1]) and torch.equal(fi, want[2])
                         and torch.equal(out, out_ref))
                 ep, err = wins[q].epoch()
