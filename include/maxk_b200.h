@@ -73,6 +73,14 @@ MK_API int mk_device_ok(void);
  * the LOWER column.  Values are bit copies of the inputs.  1 <= k <= d.                  */
 MK_API int mk_topk_cbsr(const float* x, int64_t n, int d, int k, float* sp_data, void* sp_index,
                         int index_bytes, void* stream);
+/* f-3: mk_topk_cbsr and mk_cbsr_bank (below) in ONE kernel -- the row is read once, the sorted column
+ * ids (what the backward and the autograd scatter need) and the banked values + cell offsets (what the
+ * forward SpGEMM reads) are written once, the sorted values only if sp_data is not NULL.  Results are
+ * bit-identical to the two calls.  bk_pack != NULL: the packed 8-byte form (k = 8, 16) instead of
+ * bk_data / bk_slot.  Supported where mk_banked_supported(k, d) holds.                             */
+MK_API int mk_topk_cbsr_bank(const float* x, int64_t n, int d, int k, float* sp_data, void* sp_index,
+                             int index_bytes, float* bk_data, uint16_t* bk_slot, void* bk_pack,
+                             void* stream);
 
 /* ---- a-2  CBSR gradient -> dense ----------------------------------------------------
  * Replaces `maxk_backward` -> `maxk_backward_cuda` (maxk_cuda_kernels.o@0x4d0: an N*k host

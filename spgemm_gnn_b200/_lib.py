@@ -22,6 +22,7 @@ SIGNATURES = {
     "mk_last_cuda_error": (ctypes.c_char_p, []),
     "mk_device_ok": (_i32, []),
     "mk_topk_cbsr": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "mk_topk_cbsr_bank": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "mk_cbsr_scatter": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, _i32, _vp]),
     "mk_cbsr_gather": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, _i32, _vp]),
     "mk_partition": (_i32, [_vp, _i64, _i32, _vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp]),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libmaxk_b200.so")
-SOURCES = ["api.cu", "topk.cu", "cbsr.cu", "partition.cu", "spgemm_fwd.cu", "sspmm_bwd.cu", "bank.cu", "banked.cu", "layernorm.cu", "peer.cu"]
+SOURCES = ["api.cu", "topk.cu", "topk_tile.cu", "cbsr.cu", "partition.cu", "spgemm_fwd.cu", "sspmm_bwd.cu", "bank.cu", "banked.cu", "layernorm.cu", "peer.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

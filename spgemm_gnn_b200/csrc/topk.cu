@@ -10,34 +10,12 @@
 // Replaces: maxk_kernel (so@0x21110) -- one thread per row, 8 bisection steps, approximate --
 // and torch.topk + zeros_like + scatter_ + mul (utils/models.py:14-20).
 // HBM traffic: reads N*D*4 once, writes N*k*(4+w).
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "topk.cuh"
 
 namespace mk {
-
-// Order-preserving uint32 key of a float: larger value <=> larger key, every NaN above +inf (the
-// torch.topk convention), -0.0 ties with +0.0.  Three instructions: `v + 0.0f` turns -0.0 into +0.0
-// and every NaN into the canonical 0x7FFFFFFF (an fp32 add never returns another NaN pattern), then
-// positive values get their sign bit set and negative ones are complemented.
-__device__ __forceinline__ uint32_t order_key(float v) {
-    const int32_t b = __float_as_int(__fadd_rn(v, 0.0f));
-    return static_cast<uint32_t>(b) ^ (static_cast<uint32_t>(b >> 31) | 0x80000000u);
-}
-
-// c += (key >= cand), cand != 0, given ncand = -cand: the carry out of key + (2^32 - cand).  Two integer
-// instructions per element, and ptxas folds two carries into one IADD3.X (the compiler's own
-// `c += key >= cand` is a compare, an add and a predicated move per element).
-__device__ __forceinline__ void count_ge(int& c, uint32_t key, uint32_t ncand) {
-    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, 0;\n\t}" : "+r"(c) : "r"(key), "r"(ncand));
-}
-
-__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(kFull, v, o);
-        if (lane >= o) v += t;
-    }
-    return v;
-}
 
 // Column of element (j, i) held by `lane`: j*128 + lane*4 + i.
 template <int NV4, typename IdxT, bool VEC>
@@ -236,6 +214,9 @@ static int launch_topk(const float* x, int64_t n, int d, int k, float* sp_data, 
     return MK_OK;
 }
 
+int launch_topk_tile(const float* x, int64_t n, int d, int k, float* sp_data, void* sp_index, int index_bytes,
+                     cudaStream_t st);  // topk_tile.cu
+
 }  // namespace mk
 
 extern "C" int mk_topk_cbsr(const float* x, int64_t n, int d, int k, float* sp_data,
@@ -246,6 +227,13 @@ extern "C" int mk_topk_cbsr(const float* x, int64_t n, int d, int k, float* sp_d
     if (n == 0) return MK_OK;
     if (!x || !sp_data || !sp_index) return MK_EINVAL;
     cudaStream_t st = mk::as_stream(stream);
+    // second-generation kernel (topk_tile.cu: interpolation search, coalesced output) for rows that fit
+    // the registers; MAXK_TOPK_V1=1 keeps the first one (A/B measurements)
+    static const bool v1 = [] { const char* e = getenv("MAXK_TOPK_V1"); return e && e[0] == '1'; }();
+    if (!v1 && d <= 1024) {
+        const int rc = mk::launch_topk_tile(x, n, d, k, sp_data, sp_index, index_bytes, st);
+        if (rc != MK_EUNSUPPORTED) return rc;
+    }
     return index_bytes == 1 ? mk::launch_topk<uint8_t>(x, n, d, k, sp_data, sp_index, st)
                             : mk::launch_topk<uint16_t>(x, n, d, k, sp_data, sp_index, st);
 }
