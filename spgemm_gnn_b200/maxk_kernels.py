@@ -30,7 +30,7 @@ from . import _lib
 
 __all__ = [
     "maxk_forward", "maxk_backward", "spgemm_forward", "spgemm_backward",
-    "maxk_forward_cbsr", "cbsr_scatter", "cbsr_gather", "partition", "forward_phases",
+    "maxk_forward_cbsr", "maxk_forward_cbsr_banked", "cbsr_scatter", "cbsr_gather", "partition", "forward_phases",
     "clear_partition_cache", "install_partition", "set_max_nz", "get_max_nz", "launch_count",
     "banked_supported", "cbsr_bank", "block_split", "packed_supported", "cbsr_bank_packed",
     "spgemm_forward_packed", "use_packed", "ForwardExchange", "set_backward_tiled", "backward_tiles",
@@ -158,6 +158,51 @@ def maxk_forward_cbsr(input: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.
     _lib.check(rc, "mk_topk_cbsr")
     _launches += 1
     return sp_data, sp_index
+
+
+def maxk_forward_cbsr_banked(input: torch.Tensor, k: int, *, want_data: bool = False, packed: bool = False,
+                             out=None):
+    """Top-k and banking in ONE kernel (mk_topk_cbsr_bank, f-3): the dense row is read once and leaves
+    as the sorted column ids (for the backward) plus the banked table the forward SpGEMM reads.
+    Returns `(sp_data | None, sp_index, bk_data, bk_slot)`, or with `packed` (k = 8, 16)
+    `(sp_data | None, sp_index, bk_pack, None)`.  Bit-identical to `maxk_forward_cbsr` + `cbsr_bank` /
+    `cbsr_bank_packed`.  `out = (bk_data, bk_slot)` or `(bk_pack,)`: write the banked rows there (a
+    rank's rows of a peer window)."""
+    global _launches
+    _cuda_contig(input, "input")
+    _chk(input.dim() == 2, "Input must be 2D tensor")
+    _chk(input.dtype == torch.float32, "input must be float32")
+    n, d = input.shape
+    _chk(1 <= k <= d, "k must be between 1 and input dimension")
+    _chk(banked_supported(k, d), "banked CBSR needs k in {8,16,32,64}, dim % 8 == 0, dim <= 512")
+    _chk(not packed or packed_supported(k, d), "packed CBSR needs k in {8,16}")
+    dev = input.device
+    sp_data = torch.empty((n, k), dtype=torch.float32, device=dev) if want_data else None
+    sp_index = torch.empty((n, k), dtype=_index_dtype(d), device=dev)
+    bk_data = bk_slot = bk_pack = None
+    if packed:
+        bk_pack = out[0] if out is not None else torch.empty((n, k, 2), dtype=torch.int32, device=dev)
+        _cuda_contig(bk_pack, "out")
+        _chk(bk_pack.dtype == torch.int32 and tuple(bk_pack.shape) == (n, k, 2), "out must be int32 [n, k, 2]")
+    else:
+        if out is not None:
+            bk_data, bk_slot = out
+        else:
+            bk_data = torch.empty((n, k), dtype=torch.float32, device=dev)
+            bk_slot = torch.empty((n, k), dtype=torch.int16, device=dev)
+        _cuda_contig(bk_data, "out")
+        _cuda_contig(bk_slot, "out")
+        _chk(bk_data.dtype == torch.float32 and bk_slot.dtype in (torch.int16, torch.uint16)
+             and tuple(bk_data.shape) == (n, k) and tuple(bk_slot.shape) == (n, k),
+             "out must be (float32 [n,k], int16 [n,k])")
+    with torch.cuda.device(dev):
+        rc = _lib.lib().mk_topk_cbsr_bank(
+            input.data_ptr(), n, d, k, sp_data.data_ptr() if want_data else None, sp_index.data_ptr(),
+            sp_index.element_size(), None if packed else bk_data.data_ptr(),
+            None if packed else bk_slot.data_ptr(), bk_pack.data_ptr() if packed else None, _stream())
+    _lib.check(rc, "mk_topk_cbsr_bank")
+    _launches += 1
+    return sp_data, sp_index, (bk_pack if packed else bk_data), bk_slot
 
 
 def maxk_forward(input: torch.Tensor, k: int) -> torch.Tensor:

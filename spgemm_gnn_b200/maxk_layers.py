@@ -102,6 +102,35 @@ class SpGEMMFunction(Function):
         return dxs, None, None, None, None, None, None
 
 
+class MaxKAggregateFunction(Function):
+    """feat [N,D] -> A x MaxK(feat) in two launches (f-3): `mk_topk_cbsr_bank` reads the dense row once
+    and emits the sorted column ids + the banked table, the banked / packed forward SpGEMM consumes it.
+    backward: `spgemm_backward` at the kept positions, then the CBSR gradient scattered to dense.
+    Same values as MaxKCBSRFunction + SpGEMMFunction, bit for bit (the two kernels it fuses are)."""
+
+    @staticmethod
+    def forward(ctx, feat, k, ptr, idx, val, num_nodes, packed):
+        x = feat.contiguous()
+        d = x.shape[1]
+        e = idx.numel()
+        _, sp_index, table, bk_slot = maxk_kernels.maxk_forward_cbsr_banked(x, k, packed=packed)
+        if packed:
+            out = maxk_kernels.spgemm_forward_packed(ptr, idx, val, table, num_nodes, e, k, d)
+        else:
+            out = maxk_kernels.spgemm_forward_banked(ptr, idx, val, table, bk_slot, num_nodes, e, k, d)
+        ctx.save_for_backward(sp_index, ptr, idx, val)
+        ctx.meta = (num_nodes, k, d)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        sp_index, ptr, idx, val = ctx.saved_tensors
+        num_nodes, k, d = ctx.meta
+        dxs = maxk_kernels.spgemm_backward(ptr, idx, val, grad_out.contiguous(), sp_index, num_nodes,
+                                           idx.numel(), k, d)
+        return maxk_kernels.cbsr_scatter(dxs, sp_index, d), None, None, None, None, None, None
+
+
 class AddLayerNormFunction(Function):
     """y = LayerNorm(a + b + bias) * gamma + beta in one pass (f-3: the epilogue of the
     aggregation, utils/maxk_layers.py:174-182).  b and bias may be None."""
@@ -152,6 +181,14 @@ def aggregate_cbsr(graph: CSRGraph, sp_data, sp_index, weight_kind: str, dim_ori
 
 def maxk_aggregate(graph: CSRGraph, feat: torch.Tensor, k: int, weight_kind: str) -> torch.Tensor:
     """MaxK -> CBSR -> SpGEMM in one go: sum_j w(i<-j) * maxk(feat)[j].  The hot path."""
+    if getattr(graph, "world", 1) == 1 and feat.is_cuda and feat.dim() == 2 and feat.dtype == torch.float32:
+        n, e, d = graph.num_nodes(), graph.num_edges(), feat.shape[1]
+        if feat.shape[0] == graph.num_src and maxk_kernels.banked_supported(k, d):
+            part = maxk_kernels.partition(graph.indptr, n)
+            banked = maxk_kernels.use_banked(part.num_parts, e, k, d)
+            if banked or maxk_kernels.use_packed(part.num_parts, e, k, d):   # top-k + banking fused
+                return MaxKAggregateFunction.apply(feat, k, graph.indptr, graph.indices,
+                                                   graph.edge_weights(weight_kind), n, not banked)
     sp_data, sp_index = MaxKCBSRFunction.apply(feat, k)
     return aggregate_cbsr(graph, sp_data, sp_index, weight_kind, feat.shape[1])
 

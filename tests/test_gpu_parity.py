@@ -88,6 +88,88 @@ def test_topk_ties_nan_signed_zero(mk):
         assert np.array_equal(data.cpu().numpy().view(np.uint32), wd.view(np.uint32)), (d, k)
 
 
+def _tie_heavy_rows(rng, n, d):
+    """Row families that stress the interpolation search of topk_tile.cu: thresholds inside big tie
+    groups (ReLU-like zeros, clipped maxima, integers, constants), extreme scales, infinities."""
+    base = rng.standard_normal((n, d)).astype(np.float32)
+    fam = [
+        base, np.maximum(base, 0), np.maximum(base - 1.5, 0), np.minimum(base, 0.5),
+        rng.integers(-3, 4, (n, d)).astype(np.float32), np.ones((n, d), np.float32),
+        (base * 1e-30).astype(np.float32), (base * np.exp(rng.standard_normal((n, d)) * 5)).astype(np.float32),
+        -np.abs(base), np.where(base > 1.0, np.inf, base).astype(np.float32),
+        np.where(base < -1.0, -np.inf, np.float32(-0.0) * base).astype(np.float32),
+        rng.standard_cauchy((n, d)).astype(np.float32), np.float32(1e-42) * rng.integers(0, 5, (n, d)).astype(np.float32),
+    ]
+    return np.concatenate(fam, axis=0)
+
+
+@pytest.mark.parametrize("d,k", [(256, 32), (256, 8), (256, 64), (128, 32), (100, 7), (384, 16), (512, 64),
+                                 (1024, 40), (64, 64), (32, 1)])
+def test_topk_tile_kernel_on_tie_heavy_rows(mk, d, k):
+    """Second-generation top-k kernel (interpolation search, tie short cuts, NaN fallback) against the
+    oracle, bit for bit, on rows built to break a value-space search."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(d * 100 + k)
+    x = _tie_heavy_rows(rng, 40, d)
+    x[7, : d // 2] = np.nan
+    x[11, 3] = np.nan
+    data, idx = mk.maxk_forward_cbsr(dev(x), k)
+    wd, wi = c_oracle.maxk_cbsr(x, k)
+    gi = idx.cpu().numpy() if d <= 256 else idx.view(torch.int16).cpu().numpy().view(np.uint16)
+    assert np.array_equal(gi, wi)
+    assert np.array_equal(data.cpu().numpy().view(np.uint32), wd.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,d,k", [(1000, 256, 32), (999, 256, 64), (4097, 256, 16), (333, 128, 8), (257, 384, 32),
+                                   (100, 512, 64), (200_000, 256, 32), (31, 64, 8)])
+def test_fused_topk_and_banking_is_bit_identical_to_the_two_kernels(mk, n, d, k):
+    """mk_topk_cbsr_bank (f-3) == mk_topk_cbsr followed by mk_cbsr_bank / mk_cbsr_bank_packed, bit for
+    bit: sorted column ids, sorted values, banked values, cell offsets -- 200,000 rows make every warp
+    walk more than one 32-row tile."""
+    rng = np.random.default_rng(n + d + k)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    if n < 5000:
+        x[: n // 3] = np.maximum(x[: n // 3] - 1.0, 0)          # ties inside the tile
+    xt = dev(x)
+    sd, si = mk.maxk_forward_cbsr(xt, k)
+    bd, _, bs = mk.cbsr_bank(sd, si, d, with_index=False)
+    fd, fi, fbd, fbs = mk.maxk_forward_cbsr_banked(xt, k, want_data=True)
+    assert torch.equal(fi.view(torch.uint8), si.view(torch.uint8))
+    assert torch.equal(fd.view(torch.int32), sd.view(torch.int32))
+    assert torch.equal(fbd.view(torch.int32), bd.view(torch.int32))
+    assert torch.equal(fbs, bs)
+    nd, ni, _, _ = mk.maxk_forward_cbsr_banked(xt, k)           # sorted values not requested
+    assert nd is None and torch.equal(ni.view(torch.uint8), si.view(torch.uint8))
+    if mk.packed_supported(k, d):
+        want = mk.cbsr_bank_packed(sd, si, d)
+        _, pi, pk, none = mk.maxk_forward_cbsr_banked(xt, k, packed=True)
+        assert none is None and torch.equal(pk, want) and torch.equal(pi.view(torch.uint8), si.view(torch.uint8))
+
+
+@pytest.mark.parametrize("k", [32, 16])
+def test_fused_aggregate_function_equals_the_unfused_path(mk, k):
+    """`maxk_aggregate` through MaxKAggregateFunction (top-k + banking fused) gives the forward and the
+    input gradient of MaxKCBSRFunction + SpGEMMFunction."""
+    from conftest import small_graph
+    from spgemm_gnn_b200 import maxk_layers as ml
+    g = small_graph(3000, 120, seed=4, device="cuda")
+    rng = np.random.default_rng(k)
+    x = dev(rng.standard_normal((g.num_nodes(), 256)).astype(np.float32))
+    dy = dev(rng.standard_normal((g.num_nodes(), 256)).astype(np.float32))
+    a = x.clone().requires_grad_(True)
+    ya = ml.maxk_aggregate(g, a, k, "mean")
+    assert type(ya.grad_fn).__name__.startswith("MaxKAggregateFunction")
+    ya.backward(dy)
+    b = x.clone().requires_grad_(True)
+    sd, si = ml.MaxKCBSRFunction.apply(b, k)
+    yb = ml.aggregate_cbsr(g, sd, si, "mean", 256)
+    yb.backward(dy)
+    assert torch.equal(ya, yb)
+    scale = b.grad.abs().max()
+    assert float((a.grad - b.grad).abs().max() / scale) < 1e-5   # REDG order is free in both
+    assert torch.equal(a.grad != 0, b.grad != 0)
+
+
 def test_golden_vectors_through_the_cuda_path(mk, golden):
     """Outputs of the reference's own Python (tests/golden/make_golden.py)."""
     from spgemm_gnn_b200.maxk_layers import MaxKFunction

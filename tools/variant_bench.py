@@ -66,5 +66,8 @@ for mz in ([int(v) for v in a.max_nz.split(",")] if a.max_nz else [mk.get_max_nz
             extra = f" (banked kernel alone {fb:.3f})"
         if a.topk:
             extra += f" topk {t(lambda: mk.maxk_forward_cbsr(x, k)):.4f}"
+            if mk.banked_supported(k, a.dim):
+                extra += f" bank {t(lambda: mk.cbsr_bank(sd, si, a.dim, with_index=False)):.4f}"
+                extra += f" topk+bank fused {t(lambda: mk.maxk_forward_cbsr_banked(x, k)):.4f}"
         print(f"[{a.tag}] {a.workload} shard 1/{a.shard} rows {n_rows} E {e} k {k} max_nz {mz} records {part.num_parts}: "
               f"fwd {f:.3f} ms{extra}  bwd {b:.3f} ms", flush=True)
