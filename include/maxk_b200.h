@@ -239,6 +239,29 @@ MK_API int mk_spgemm_fwd_banked_phase(const mk_part* parts, int64_t num_parts, i
                                       float* partial, int64_t n_rows, int k, int d,
                                       const mk_fwd_exchange* xchg, const mk_fwd_phase* phase,
                                       void* stream);
+/* f-3: the forward SpGEMM with the layer's epilogue applied to every row as it is finished:
+ *     y[r] = LayerNorm(h_self[r] + (A x Xs)[r] + bias) * gamma + beta
+ * -- `output = h_self + aggregated_feat; output = self.norm(output)` (utils/maxk_layers.py:174-182)
+ * without writing the aggregated row and reading it back.  h_self and bias may be NULL; z (the
+ * pre-normalisation sum), mean, rstd are what mk_layernorm_bwd needs and may be NULL for inference.
+ * Bit-identical to mk_spgemm_fwd_banked / _packed followed by mk_add_layernorm_fwd.  `table` is
+ * bk_data with bk_slot, or the packed table with bk_slot == NULL.  d % 4 == 0, d <= 512; 16-byte
+ * aligned pointers.                                                                                 */
+typedef struct mk_fwd_epilogue {
+    const float* h_self;
+    const float* bias;
+    const float* gamma;
+    const float* beta;
+    float* z;
+    float* mean;
+    float* rstd;
+    float eps;
+} mk_fwd_epilogue;
+MK_API int mk_spgemm_fwd_banked_ln(const mk_part* parts, int64_t num_parts, int64_t num_slots,
+                                   const mk_part* exec_parts, const int32_t* idx, const float* val,
+                                   const void* table, const uint16_t* bk_slot, float* y, float* partial,
+                                   int64_t n_rows, int k, int d, const mk_fwd_epilogue* epilogue,
+                                   void* stream);
 /* Packed banked CBSR for k = 8, 16 (mk_packed_supported): one entry = {float value, uint16 cell,
  * uint16 column} in 8 bytes, bk_pack [n, k] of them, so that a lane fetches value and cell offset with
  * ONE load -- at these widths the forward is bound by L1 wavefronts per gathered row, and the separate

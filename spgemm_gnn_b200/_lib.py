@@ -44,6 +44,8 @@ SIGNATURES = {
                                        _vp, _vp, _vp]),
     "mk_spgemm_fwd_banked_phase": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
                                           _vp, _vp, _vp]),
+    "mk_spgemm_fwd_banked_ln": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
+                                       _vp, _vp]),
     "mk_packed_supported": (_i32, [_i32, _i32]),
     "mk_cbsr_bank_packed": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, _i32, _vp]),
     "mk_spgemm_fwd_packed_ex": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
@@ -81,6 +83,12 @@ class FwdPhase(ctypes.Structure):
     _fields_ = [("blk_ptr", _vp), ("row_stride", _i64), ("n_blocks", ctypes.c_int32),
                 ("a0", ctypes.c_int32), ("a1", ctypes.c_int32), ("b0", ctypes.c_int32), ("b1", ctypes.c_int32),
                 ("accumulate", ctypes.c_int32), ("last", ctypes.c_int32)]
+
+
+class FwdEpilogue(ctypes.Structure):
+    """`mk_fwd_epilogue` of include/maxk_b200.h."""
+    _fields_ = [("h_self", _vp), ("bias", _vp), ("gamma", _vp), ("beta", _vp), ("z", _vp), ("mean", _vp),
+                ("rstd", _vp), ("eps", ctypes.c_float)]
 
 
 _lib = None

@@ -13,6 +13,7 @@
 // over the 4 groups and the 2 copies when the row is written.  Backward: the cells are replicas
 // of dY[r, :], built once per record.
 #include "common.cuh"
+#include "epilogue.cuh"
 #include "peer.cuh"
 
 namespace mk {
@@ -186,7 +187,7 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
                          const float* __restrict__ val, const float* __restrict__ bk_data,
                          const uint16_t* __restrict__ bk_slot, float* __restrict__ out,
                          float* __restrict__ partial, int d, int rows, const int* __restrict__ split,
-                         const FwdWait fw, const FwdPhase ph) {
+                         const FwdWait fw, const FwdPhase ph, const FwdEpilogue ep) {
     constexpr int CAP = K / 8;
     extern __shared__ __align__(16) float acc[];  // 32 * rows
     const int lane = lane_id();
@@ -339,6 +340,13 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
     __syncwarp();
     float* __restrict__ o = rec.slot < 0 ? out + static_cast<int64_t>(rec.row) * d
                                          : partial + static_cast<int64_t>(rec.slot) * d;
+    if (ep.gamma != nullptr && rec.slot < 0) {
+        // f-3: the finished row goes straight into y = LayerNorm(h_self + row + bias) * gamma + beta
+        // (and z, mean, rstd for the backward) -- no dense round trip of the aggregated row
+        fwd_epilogue_row(ep, [&](int c) { return *reinterpret_cast<const float4*>(acc + c); }, out, rec.row, d,
+                         lane);
+        return;
+    }
     if (ph.accumulate && rec.slot < 0) {  // later phase: on top of what the earlier ones wrote
         for (int c = lane * 4; c < d; c += 128) {
             float4 a = *reinterpret_cast<const float4*>(acc + c);
@@ -442,7 +450,7 @@ template <int K, bool PACKED>
 static int launch_fwd_banked(const mk_part* parts, int64_t num_parts, const int* idx,
                              const float* val, const float* bk_data, const uint16_t* bk_slot,
                              float* out, float* partial, int d, int rows, const int* split,
-                             const FwdWait& fw, const FwdPhase& ph, cudaStream_t st) {
+                             const FwdWait& fw, const FwdPhase& ph, const FwdEpilogue& ep, cudaStream_t st) {
 #ifdef MK_FWD_U
     constexpr int U = MK_FWD_U;
 #else
@@ -457,14 +465,14 @@ static int launch_fwd_banked(const mk_part* parts, int64_t num_parts, const int*
         const int64_t grid = num_parts + fw.push.pushers;
         if (grid > 0x7fffffffLL) return MK_EUNSUPPORTED;
         kern<<<static_cast<unsigned>(grid), 32, smem, st>>>(parts, idx, val, bk_data, bk_slot, out,
-                                                            partial, d, rows, split, fw, ph);
+                                                            partial, d, rows, split, fw, ph, ep);
     } else {
         auto kern = spgemm_fwd_banked_kernel<K, U, false, PACKED>;
         if (smem > 48 * 1024)
             MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem)));
         kern<<<static_cast<unsigned>(num_parts), 32, smem, st>>>(parts, idx, val, bk_data, bk_slot, out,
-                                                                 partial, d, rows, split, fw, ph);
+                                                                 partial, d, rows, split, fw, ph, ep);
     }
     MK_LAUNCH_CHECK("spgemm_fwd_banked_kernel");
     return MK_OK;
@@ -487,7 +495,7 @@ static int launch_bwd_banked(const mk_part* parts, int64_t num_parts, const int*
 }
 
 int launch_fold(const mk_part* parts, int64_t num_parts, const float* partial, float* out, int d,
-                cudaStream_t st, int accumulate = 0);  // spgemm_fwd.cu
+                cudaStream_t st, int accumulate = 0, const FwdEpilogue* ep = nullptr);  // spgemm_fwd.cu
 
 }  // namespace mk
 
@@ -499,8 +507,18 @@ static int fwd_banked_any(bool packed, const mk_part* parts, int64_t num_parts, 
                          const mk_part* exec_parts, const int32_t* idx, const float* val,
                          const float* bk_data, const uint16_t* bk_slot, float* out, float* partial,
                          int64_t n_rows, int k, int d, const int32_t* split, const mk_fwd_exchange* x,
-                         const mk_fwd_phase* phase, void* stream) {
+                         const mk_fwd_phase* phase, const mk_fwd_epilogue* epi, void* stream) {
     if (n_rows < 0 || num_parts < 0 || num_slots < 0 || d < 1 || k < 1 || k > d) return MK_EINVAL;
+    mk::FwdEpilogue ep{};
+    if (epi != nullptr && epi->gamma != nullptr) {
+        if (phase != nullptr || x != nullptr || !epi->beta || d % 4 != 0 || d > 512) return MK_EUNSUPPORTED;
+        const uintptr_t al = reinterpret_cast<uintptr_t>(epi->h_self) | reinterpret_cast<uintptr_t>(epi->bias) |
+                             reinterpret_cast<uintptr_t>(epi->gamma) | reinterpret_cast<uintptr_t>(epi->beta) |
+                             reinterpret_cast<uintptr_t>(epi->z);
+        if (al & 15) return MK_EINVAL;
+        ep.h_self = epi->h_self; ep.bias = epi->bias; ep.gamma = epi->gamma; ep.beta = epi->beta;
+        ep.z = epi->z; ep.mean = epi->mean; ep.rstd = epi->rstd; ep.eps = epi->eps;
+    }
     mk::FwdPhase ph{};
     ph.last = 1;
     if (phase != nullptr && phase->blk_ptr != nullptr) {
@@ -567,18 +585,18 @@ static int fwd_banked_any(bool packed, const mk_part* parts, int64_t num_parts, 
     const int rows = mk_banked_rows(d);
     int rc;
     if (packed) {
-        rc = k == 8 ? mk::launch_fwd_banked<8, true>(ex, num_parts, idx, val, bk_data, nullptr, out, partial, d, rows, split, fw, ph, st)
-                    : mk::launch_fwd_banked<16, true>(ex, num_parts, idx, val, bk_data, nullptr, out, partial, d, rows, split, fw, ph, st);
+        rc = k == 8 ? mk::launch_fwd_banked<8, true>(ex, num_parts, idx, val, bk_data, nullptr, out, partial, d, rows, split, fw, ph, ep, st)
+                    : mk::launch_fwd_banked<16, true>(ex, num_parts, idx, val, bk_data, nullptr, out, partial, d, rows, split, fw, ph, ep, st);
     } else {
         switch (k) {
-            case 8: rc = mk::launch_fwd_banked<8, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, ph, st); break;
-            case 16: rc = mk::launch_fwd_banked<16, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, ph, st); break;
-            case 32: rc = mk::launch_fwd_banked<32, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, ph, st); break;
-            default: rc = mk::launch_fwd_banked<64, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, ph, st); break;
+            case 8: rc = mk::launch_fwd_banked<8, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, ph, ep, st); break;
+            case 16: rc = mk::launch_fwd_banked<16, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, ph, ep, st); break;
+            case 32: rc = mk::launch_fwd_banked<32, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, ph, ep, st); break;
+            default: rc = mk::launch_fwd_banked<64, false>(ex, num_parts, idx, val, bk_data, bk_slot, out, partial, d, rows, split, fw, ph, ep, st); break;
         }
     }
     if (rc != MK_OK) return rc;
-    if (num_slots > 0) return mk::launch_fold(parts, num_parts, partial, out, d, st, ph.accumulate);
+    if (num_slots > 0) return mk::launch_fold(parts, num_parts, partial, out, d, st, ph.accumulate, ep.gamma ? &ep : nullptr);
     return MK_OK;
 }
 
@@ -588,7 +606,7 @@ extern "C" int mk_spgemm_fwd_banked_ex(const mk_part* parts, int64_t num_parts, 
                                        float* partial, int64_t n_rows, int k, int d,
                                        const int32_t* split, const mk_fwd_exchange* xchg, void* stream) {
     return fwd_banked_any(false, parts, num_parts, num_slots, exec_parts, idx, val, bk_data, bk_slot, out,
-                          partial, n_rows, k, d, split, xchg, nullptr, stream);
+                          partial, n_rows, k, d, split, xchg, nullptr, nullptr, stream);
 }
 
 extern "C" int mk_spgemm_fwd_banked_phase(const mk_part* parts, int64_t num_parts, int64_t num_slots,
@@ -598,7 +616,7 @@ extern "C" int mk_spgemm_fwd_banked_phase(const mk_part* parts, int64_t num_part
                                           const mk_fwd_exchange* xchg, const mk_fwd_phase* phase,
                                           void* stream) {
     return fwd_banked_any(false, parts, num_parts, num_slots, exec_parts, idx, val, bk_data, bk_slot, out,
-                          partial, n_rows, k, d, nullptr, xchg, phase, stream);
+                          partial, n_rows, k, d, nullptr, xchg, phase, nullptr, stream);
 }
 
 extern "C" int mk_spgemm_fwd_packed_ex(const mk_part* parts, int64_t num_parts, int64_t num_slots,
@@ -608,7 +626,18 @@ extern "C" int mk_spgemm_fwd_packed_ex(const mk_part* parts, int64_t num_parts, 
                                        void* stream) {
     return fwd_banked_any(true, parts, num_parts, num_slots, exec_parts, idx, val,
                           static_cast<const float*>(bk_pack), nullptr, out, partial, n_rows, k, d, split,
-                          xchg, nullptr, stream);
+                          xchg, nullptr, nullptr, stream);
+}
+
+extern "C" int mk_spgemm_fwd_banked_ln(const mk_part* parts, int64_t num_parts, int64_t num_slots,
+                                       const mk_part* exec_parts, const int32_t* idx, const float* val,
+                                       const void* table, const uint16_t* bk_slot, float* y, float* partial,
+                                       int64_t n_rows, int k, int d, const mk_fwd_epilogue* epilogue,
+                                       void* stream) {
+    if (epilogue == nullptr || epilogue->gamma == nullptr) return MK_EINVAL;
+    return fwd_banked_any(bk_slot == nullptr, parts, num_parts, num_slots, exec_parts, idx, val,
+                          static_cast<const float*>(table), bk_slot, y, partial, n_rows, k, d, nullptr, nullptr,
+                          nullptr, epilogue, stream);
 }
 
 extern "C" int mk_spgemm_fwd_banked(const mk_part* parts, int64_t num_parts, int64_t num_slots,

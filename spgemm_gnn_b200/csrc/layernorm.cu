@@ -10,16 +10,11 @@
 //   backward: reads gy, z, writes gz (= d loss / d z, which is also d/da and d/db), and per-CTA
 //             partial sums of d gamma / d beta that a second tiny kernel folds in fixed order.
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace mk {
 
 constexpr int kLNMaxV4 = 8;  // float4 per lane -> D <= 1024
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-    return v;
-}
 
 template <int NV4>
 __global__ void __launch_bounds__(256)
@@ -31,59 +26,16 @@ add_layernorm_fwd_kernel(const float* __restrict__ a, const float* __restrict__ 
     const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (row >= n) return;
     const int lane = lane_id();
-    float v[NV4 * 4];
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < NV4; ++j) {
-        const int c = j * 128 + lane * 4;
-        if (c < d) {
-            float4 x = ld_stream_f4(a + row * d + c);
-            if (b) {
-                const float4 r = ld_stream_f4(b + row * d + c);
-                x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
-            }
-            if (bias) {
-                const float4 r = *reinterpret_cast<const float4*>(bias + c);
-                x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
-            }
-            v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
-            s += (x.x + x.y) + (x.z + x.w);
-            if (z) *reinterpret_cast<float4*>(z + row * d + c) = x;
-        } else {
-            v[4 * j] = v[4 * j + 1] = v[4 * j + 2] = v[4 * j + 3] = 0.f;
-        }
-    }
-    const float mu = warp_sum(s) / d;
-    float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < NV4; ++j) {
-        const int c = j * 128 + lane * 4;
-        if (c < d) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float t = v[4 * j + i] - mu;
-                q += t * t;
-            }
-        }
-    }
-    const float rs = rsqrtf(warp_sum(q) / d + eps);
-    if (lane == 0) {
-        mean[row] = mu;
-        rstd[row] = rs;
-    }
-#pragma unroll
-    for (int j = 0; j < NV4; ++j) {
-        const int c = j * 128 + lane * 4;
-        if (c < d) {
-            const float4 g = *reinterpret_cast<const float4*>(gamma + c);
-            const float4 bt = *reinterpret_cast<const float4*>(beta + c);
-            float4 o;
-            o.x = (v[4 * j] - mu) * rs * g.x + bt.x;
-            o.y = (v[4 * j + 1] - mu) * rs * g.y + bt.y;
-            o.z = (v[4 * j + 2] - mu) * rs * g.z + bt.z;
-            o.w = (v[4 * j + 3] - mu) * rs * g.w + bt.w;
-            st_stream_f4(y + row * d + c, o);
-        }
+    const float* __restrict__ ar = a + row * d;
+    float* z_row = z ? z + row * d : nullptr;
+    auto fa = [&](int c) { return ld_stream_f4(ar + c); };
+    if (b) {
+        const float* __restrict__ br = b + row * d;
+        add_layernorm_row<NV4, true>(fa, [&](int c) { return ld_stream_f4(br + c); }, bias, gamma, beta, z_row,
+                                     y + row * d, mean + row, rstd + row, d, eps, lane);
+    } else {
+        add_layernorm_row<NV4, false>(fa, fa, bias, gamma, beta, z_row, y + row * d, mean + row, rstd + row, d,
+                                      eps, lane);
     }
 }
 

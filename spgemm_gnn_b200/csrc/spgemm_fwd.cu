@@ -24,6 +24,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace mk {
 
@@ -308,8 +309,38 @@ spgemm_fold_kernel(const mk_part* __restrict__ parts, int64_t num_parts,
     }
 }
 
+// The fold of a multi-record row followed by the f-3 epilogue (same sums as the plain fold, then
+// epilogue.cuh): the rows the forward kernel could not finish by itself.
+__global__ void __launch_bounds__(256)
+spgemm_fold_ln_kernel(const mk_part* __restrict__ parts, int64_t num_parts,
+                      const float* __restrict__ partial, float* __restrict__ y, int d, const FwdEpilogue ep) {
+    const int64_t p = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (p >= num_parts) return;
+    const mk_part rec = parts[p];
+    if (rec.slot < 0) return;
+    if (p > 0 && parts[p - 1].row == rec.row) return;
+    int cnt = 1;
+    while (p + cnt < num_parts && parts[p + cnt].row == rec.row) ++cnt;
+    const float* __restrict__ src = partial + static_cast<int64_t>(rec.slot) * d;
+    auto agg = [&](int c) {
+        float4 s = *reinterpret_cast<const float4*>(src + c);
+        for (int q = 1; q < cnt; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(src + static_cast<int64_t>(q) * d + c);
+            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        return s;
+    };
+    fwd_epilogue_row(ep, agg, y, rec.row, d, lane_id());
+}
+
 int launch_fold(const mk_part* parts, int64_t num_parts, const float* partial, float* out, int d,
-                cudaStream_t st, int accumulate) {
+                cudaStream_t st, int accumulate, const FwdEpilogue* ep) {
+    if (ep != nullptr) {
+        const int64_t blocks = (num_parts * 32 + 255) / 256;
+        spgemm_fold_ln_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(parts, num_parts, partial, out, d, *ep);
+        MK_LAUNCH_CHECK("spgemm_fold_ln_kernel");
+        return MK_OK;
+    }
     const int64_t blocks = (num_parts * 32 + 255) / 256;
     spgemm_fold_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(parts, num_parts, partial, out, d, accumulate);
     MK_LAUNCH_CHECK("spgemm_fold_kernel");
@@ -440,6 +471,6 @@ extern "C" int mk_spgemm_fwd(const mk_part* parts, int64_t num_parts, int64_t nu
                        : mk::launch_fwd<uint16_t>(parts, num_parts, idx, val, sp_data, sp_index,
                                                   out, partial, k, d, st);
     if (rc != MK_OK) return rc;
-    if (num_slots > 0) return mk::launch_fold(parts, num_parts, partial, out, d, st, 0);
+    if (num_slots > 0) return mk::launch_fold(parts, num_parts, partial, out, d, st, 0, nullptr);
     return MK_OK;
 }

@@ -227,10 +227,12 @@ extern "C" int mk_topk_cbsr(const float* x, int64_t n, int d, int k, float* sp_d
     if (n == 0) return MK_OK;
     if (!x || !sp_data || !sp_index) return MK_EINVAL;
     cudaStream_t st = mk::as_stream(stream);
-    // second-generation kernel (topk_tile.cu: interpolation search, coalesced output) for rows that fit
-    // the registers; MAXK_TOPK_V1=1 keeps the first one (A/B measurements)
-    static const bool v1 = [] { const char* e = getenv("MAXK_TOPK_V1"); return e && e[0] == '1'; }();
-    if (!v1 && d <= 1024) {
+    // MAXK_TOPK_TILE=1: the second-generation kernel (topk_tile.cu: interpolation search, shared-memory
+    // compaction, row prefetch).  Measured SLOWER than the kernel below on a B200 (profiles/r2/topk_tile.log:
+    // 0.197 vs 0.164 ms on the Reddit shape): its ~5.5 counting steps carry ~45 warp-uniform
+    // instructions of bracket arithmetic each, against 13.7 steps of 20 instructions here.
+    static const bool tile = [] { const char* e = getenv("MAXK_TOPK_TILE"); return e && e[0] == '1'; }();
+    if (tile && d <= 1024) {
         const int rc = mk::launch_topk_tile(x, n, d, k, sp_data, sp_index, index_bytes, st);
         if (rc != MK_EUNSUPPORTED) return rc;
     }

@@ -48,7 +48,11 @@ __device__ __forceinline__ void kth_largest_key(const uint32_t (&key)[E], int k,
     for (int e = 1; e < E; ++e) lm = max(lm, key[e]);
     const uint32_t gmax = __reduce_max_sync(kFull, lm);
     exact = false;
+#ifdef MK_TILE_BITWISE
+    if (true) {  // measurement variant: topk.cu's bitwise search inside this kernel
+#else
     if (gmax == 0xFFFFFFFFu) {  // a NaN in the row: hi = gmax + 1 would wrap; plain bitwise search
+#endif
         thr = 0;
         for (int bit = 31; bit >= 0; --bit) {
             const uint32_t cand = thr | (1u << bit);

@@ -34,7 +34,7 @@ __all__ = [
     "clear_partition_cache", "install_partition", "set_max_nz", "get_max_nz", "launch_count",
     "banked_supported", "cbsr_bank", "block_split", "packed_supported", "cbsr_bank_packed",
     "spgemm_forward_packed", "use_packed", "ForwardExchange", "set_backward_tiled", "backward_tiles",
-    "block_pointers", "maxk_forward_banked", "spgemm_forward_banked",
+    "block_pointers", "maxk_forward_banked", "spgemm_forward_banked", "spgemm_forward_ln",
     "spgemm_backward_banked", "set_banked", "set_backward_tma", "use_banked", "forward_variant", "partition_blocked", "backward_blocks",
     "set_backward_block_mb", "add_layernorm_supported", "add_layernorm_forward", "layernorm_backward",
 ]
@@ -795,6 +795,47 @@ def spgemm_forward_banked(ptr, idx, val, bk_data, bk_slot, num_nodes, num_edges,
     _lib.check(rc, "mk_spgemm_fwd_banked_ex")
     _launches += 1 + (1 if part.num_slots else 0)
     return out
+
+
+def spgemm_forward_ln(ptr, idx, val, table, bk_slot, num_nodes, num_edges, dim_sparse, dim_origin,
+                      h_self, bias, gamma, beta, eps: float, *, keep_stats: bool = True):
+    """Forward SpGEMM on a banked (`bk_slot` given) or packed (`bk_slot=None`) table with the layer's
+    epilogue applied to every finished row (mk_spgemm_fwd_banked_ln, f-3):
+        y = LayerNorm(h_self + A x Xs + bias) * gamma + beta
+    Returns `(y, z, mean, rstd)`; z / mean / rstd (what `layernorm_backward` needs) are None with
+    `keep_stats=False`.  Bit-identical to `spgemm_forward_banked` + `add_layernorm_forward`."""
+    global _launches
+    _check_graph(ptr, idx, val)
+    _cuda_contig(table, "sp_data")
+    _chk(dim_origin % 4 == 0 and dim_origin <= 512, "fused epilogue needs dim % 4 == 0, dim <= 512")
+    for t, name in ((h_self, "h_self"), (bias, "bias"), (gamma, "gamma"), (beta, "beta")):
+        if t is not None:
+            _cuda_contig(t, name)
+            _chk(t.dtype == torch.float32, f"{name} must be float32")
+    _chk(h_self is None or tuple(h_self.shape) == (num_nodes, dim_origin), "h_self must be [num_nodes, dim]")
+    _chk(gamma.numel() == dim_origin and beta.numel() == dim_origin, "gamma / beta must have dim entries")
+    dev = table.device
+    part = partition(ptr, num_nodes)
+    y = torch.empty((num_nodes, dim_origin), dtype=torch.float32, device=dev)
+    z = torch.empty_like(y) if keep_stats else None
+    mean = torch.empty((num_nodes,), dtype=torch.float32, device=dev) if keep_stats else None
+    rstd = torch.empty((num_nodes,), dtype=torch.float32, device=dev) if keep_stats else None
+    partial = part.partial_for(dim_origin, dev)
+    ex = part.exec_parts()
+    ep = _lib.FwdEpilogue(h_self.data_ptr() if h_self is not None else None,
+                          bias.data_ptr() if bias is not None else None, gamma.data_ptr(), beta.data_ptr(),
+                          z.data_ptr() if keep_stats else None, mean.data_ptr() if keep_stats else None,
+                          rstd.data_ptr() if keep_stats else None, float(eps))
+    with torch.cuda.device(dev):
+        rc = _lib.lib().mk_spgemm_fwd_banked_ln(
+            part.parts.data_ptr(), part.num_parts, part.num_slots,
+            ex.data_ptr() if ex is not part.parts else None, idx.data_ptr(), val.data_ptr(),
+            table.data_ptr(), bk_slot.data_ptr() if bk_slot is not None else None, y.data_ptr(),
+            partial.data_ptr() if partial is not None else None, num_nodes, dim_sparse, dim_origin,
+            ctypes.byref(ep), _stream())
+    _lib.check(rc, "mk_spgemm_fwd_banked_ln")
+    _launches += 1 + (1 if part.num_slots else 0)
+    return y, z, mean, rstd
 
 
 def packed_supported(k: int, dim_origin: int) -> bool:

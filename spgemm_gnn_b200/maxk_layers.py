@@ -13,6 +13,8 @@ What changed underneath:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 from torch.autograd import Function
@@ -21,6 +23,14 @@ from . import maxk_kernels
 from .graph import CSRGraph
 
 KERNELS_AVAILABLE = True  # kept for callers that test it (maxk_gnn_integrated.py:24-31)
+
+# f-3: top-k and banking as ONE kernel (mk_topk_cbsr_bank) on the single-GPU hot path.  Built, bit-identical
+# to the two kernels, and measured slower on a B200 (profiles/r2/topk_tile.log: 0.272 ms against
+# 0.164 + 0.064 ms on the Reddit shape -- both halves are bound by integer instruction issue, not by the
+# 37 MB round trip the fusion removes), so it is opt-in.
+FUSED_TOPK_BANK = os.environ.get("MAXK_FUSED_TOPK_BANK", "0") != "0"
+# f-3: `h_self + aggregated -> LayerNorm` applied by the forward SpGEMM to the row it has just finished
+FUSED_LN_EPILOGUE = os.environ.get("MAXK_FUSED_LN", "1") != "0"
 
 
 # ---------------------------------------------------------------------------------------
@@ -131,6 +141,69 @@ class MaxKAggregateFunction(Function):
         return maxk_kernels.cbsr_scatter(dxs, sp_index, d), None, None, None, None, None, None
 
 
+class MaxKAggregateLNFunction(Function):
+    """y = LayerNorm(h_self + A x MaxK(h_neigh) + bias) * gamma + beta with the epilogue INSIDE the
+    forward SpGEMM (mk_spgemm_fwd_banked_ln, f-3): the aggregated row never makes the round trip
+    through memory (utils/maxk_layers.py:161-184 is top-k, SpGEMM, add, LayerNorm as separate passes).
+    backward: fused LayerNorm backward -> gz (the gradient of h_self), SSpMM of gz at the kept
+    positions -> gradient of h_neigh.  Same values as the unfused chain, bit for bit in the forward."""
+
+    @staticmethod
+    def forward(ctx, h_neigh, h_self, bias, gamma, beta, eps, k, ptr, idx, val, num_nodes):
+        x = h_neigh.contiguous()
+        d = x.shape[1]
+        e = idx.numel()
+        part = maxk_kernels.partition(ptr, num_nodes)
+        packed = not maxk_kernels.use_banked(part.num_parts, e, k, d)
+        sp_data, sp_index = maxk_kernels.maxk_forward_cbsr(x, k)
+        if packed:
+            table, slot = maxk_kernels.cbsr_bank_packed(sp_data, sp_index, d), None
+        else:
+            table, _, slot = maxk_kernels.cbsr_bank(sp_data, sp_index, d, with_index=False)
+        keep = any(ctx.needs_input_grad[:5])
+        y, z, mean, rstd = maxk_kernels.spgemm_forward_ln(
+            ptr, idx, val, table, slot, num_nodes, e, k, d, None if h_self is None else h_self.contiguous(),
+            None if bias is None else bias.contiguous(), gamma.contiguous(), beta.contiguous(), eps,
+            keep_stats=keep)
+        if keep:
+            ctx.save_for_backward(z, gamma, mean, rstd, sp_index, ptr, idx, val)
+        ctx.meta = (num_nodes, k, d, h_self is not None, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        z, gamma, mean, rstd, sp_index, ptr, idx, val = ctx.saved_tensors
+        num_nodes, k, d, has_self, has_bias = ctx.meta
+        gz, dgamma, dbeta, dbias = maxk_kernels.layernorm_backward(grad_y.contiguous(), z, gamma, mean, rstd,
+                                                                   want_dbias=has_bias)
+        d_neigh = None
+        if ctx.needs_input_grad[0]:
+            dxs = maxk_kernels.spgemm_backward(ptr, idx, val, gz, sp_index, num_nodes, idx.numel(), k, d)
+            d_neigh = maxk_kernels.cbsr_scatter(dxs, sp_index, d)
+        return (d_neigh, gz if has_self else None, dbias, dgamma, dbeta, None, None, None, None, None, None)
+
+
+def maxk_aggregate_add_norm(graph: CSRGraph, h_neigh: torch.Tensor, h_self, bias, norm, k: int,
+                            weight_kind: str) -> torch.Tensor:
+    """`norm(h_self + aggregate(MaxK(h_neigh)) + bias)` -- with the epilogue inside the forward SpGEMM
+    where that exists (single GPU, banked or packed forward, affine LayerNorm over <= 512 columns),
+    the separate kernels otherwise."""
+    d = h_neigh.shape[1]
+    if (FUSED_LN_EPILOGUE and getattr(graph, "world", 1) == 1 and h_neigh.is_cuda and h_neigh.dim() == 2
+            and h_neigh.dtype == torch.float32 and isinstance(norm, nn.LayerNorm) and norm.elementwise_affine
+            and norm.bias is not None and len(norm.normalized_shape) == 1 and d % 4 == 0 and d <= 512
+            and h_neigh.shape[0] == graph.num_src == graph.num_nodes() and maxk_kernels.banked_supported(k, d)):
+        n, e = graph.num_nodes(), graph.num_edges()
+        part = maxk_kernels.partition(graph.indptr, n)
+        if maxk_kernels.use_banked(part.num_parts, e, k, d) or maxk_kernels.use_packed(part.num_parts, e, k, d):
+            return MaxKAggregateLNFunction.apply(h_neigh, h_self, bias, norm.weight, norm.bias, norm.eps, k,
+                                                 graph.indptr, graph.indices, graph.edge_weights(weight_kind), n)
+    agg = maxk_aggregate(graph, h_neigh, k, weight_kind)
+    if h_self is None:
+        return add_layer_norm(agg, None, bias, norm)
+    return add_layer_norm(h_self, agg, bias, norm)
+
+
 class AddLayerNormFunction(Function):
     """y = LayerNorm(a + b + bias) * gamma + beta in one pass (f-3: the epilogue of the
     aggregation, utils/maxk_layers.py:174-182).  b and bias may be None."""
@@ -181,7 +254,8 @@ def aggregate_cbsr(graph: CSRGraph, sp_data, sp_index, weight_kind: str, dim_ori
 
 def maxk_aggregate(graph: CSRGraph, feat: torch.Tensor, k: int, weight_kind: str) -> torch.Tensor:
     """MaxK -> CBSR -> SpGEMM in one go: sum_j w(i<-j) * maxk(feat)[j].  The hot path."""
-    if getattr(graph, "world", 1) == 1 and feat.is_cuda and feat.dim() == 2 and feat.dtype == torch.float32:
+    if (FUSED_TOPK_BANK and getattr(graph, "world", 1) == 1 and feat.is_cuda and feat.dim() == 2
+            and feat.dtype == torch.float32):
         n, e, d = graph.num_nodes(), graph.num_edges(), feat.shape[1]
         if feat.shape[0] == graph.num_src and maxk_kernels.banked_supported(k, d):
             part = maxk_kernels.partition(graph.indptr, n)
@@ -263,8 +337,8 @@ class MaxKSAGEConv(nn.Module):
     def forward(self, graph, feat):
         h_self = self.fc_self(feat)
         h_neigh = self.fc_neigh(feat)
-        agg = maxk_aggregate(graph, h_neigh, self.maxk, self.aggregator_type)
-        output = add_layer_norm(h_self, agg, None, self.norm)
+        output = maxk_aggregate_add_norm(graph, h_neigh, h_self, None, self.norm, self.maxk,
+                                         self.aggregator_type)
         return self.feat_drop(output)
 
 

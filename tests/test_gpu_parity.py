@@ -113,11 +113,14 @@ def test_topk_tile_kernel_on_tie_heavy_rows(mk, d, k):
     x = _tie_heavy_rows(rng, 40, d)
     x[7, : d // 2] = np.nan
     x[11, 3] = np.nan
-    data, idx = mk.maxk_forward_cbsr(dev(x), k)
     wd, wi = c_oracle.maxk_cbsr(x, k)
-    gi = idx.cpu().numpy() if d <= 256 else idx.view(torch.int16).cpu().numpy().view(np.uint16)
-    assert np.array_equal(gi, wi)
-    assert np.array_equal(data.cpu().numpy().view(np.uint32), wd.view(np.uint32))
+    outs = [mk.maxk_forward_cbsr(dev(x), k)]                         # topk.cu (bitwise search)
+    if mk.banked_supported(k, d):                                    # topk_tile.cu (interpolation search)
+        outs.append(mk.maxk_forward_cbsr_banked(dev(x), k, want_data=True)[:2])
+    for data, idx in outs:
+        gi = idx.cpu().numpy() if d <= 256 else idx.view(torch.int16).cpu().numpy().view(np.uint16)
+        assert np.array_equal(gi, wi)
+        assert np.array_equal(data.cpu().numpy().view(np.uint32), wd.view(np.uint32))
 
 
 @pytest.mark.parametrize("n,d,k", [(1000, 256, 32), (999, 256, 64), (4097, 256, 16), (333, 128, 8), (257, 384, 32),
@@ -146,6 +149,76 @@ def test_fused_topk_and_banking_is_bit_identical_to_the_two_kernels(mk, n, d, k)
         assert none is None and torch.equal(pk, want) and torch.equal(pi.view(torch.uint8), si.view(torch.uint8))
 
 
+@pytest.mark.parametrize("n,deg,d,k,max_nz,with_self,with_bias", [
+    (2500, 120, 256, 32, 1024, True, False), (2500, 120, 256, 32, 64, True, True), (1500, 150, 256, 16, 1024, True, False),
+    (1500, 150, 128, 8, 32, False, True), (900, 200, 512, 64, 1024, True, True), (700, 90, 384, 32, 1024, False, False)])
+def test_forward_with_layernorm_epilogue_is_bit_identical(mk, n, deg, d, k, max_nz, with_self, with_bias):
+    """mk_spgemm_fwd_banked_ln (f-3: y = LayerNorm(h_self + A x Xs + bias) inside the forward SpGEMM) ==
+    the banked / packed forward followed by mk_add_layernorm_fwd, bit for bit -- y, z, mean, rstd --
+    rows of several records (fold + epilogue kernel) included; inference form without z."""
+    from conftest import small_graph
+    g = small_graph(n, deg, seed=n + k, device="cuda")
+    e = g.num_edges()
+    rng = np.random.default_rng(d + k)
+    x = dev(rng.standard_normal((n, d)).astype(np.float32))
+    hs = dev(rng.standard_normal((n, d)).astype(np.float32)) if with_self else None
+    bias = dev(rng.standard_normal(d).astype(np.float32)) if with_bias else None
+    gamma = dev(rng.standard_normal(d).astype(np.float32))
+    beta = dev(rng.standard_normal(d).astype(np.float32))
+    val = g.edge_weights("mean")
+    sd, si = mk.maxk_forward_cbsr(x, k)
+    mk.set_max_nz(max_nz)
+    try:
+        mk.clear_partition_cache()
+        if k >= 32:
+            table, _, slot = mk.cbsr_bank(sd, si, d, with_index=False)
+            agg = mk.spgemm_forward_banked(g.indptr, g.indices, val, table, slot, n, e, k, d)
+        else:
+            table, slot = mk.cbsr_bank_packed(sd, si, d), None
+            agg = mk.spgemm_forward_packed(g.indptr, g.indices, val, table, n, e, k, d)
+        if with_self:
+            wy, wz, wm, wr = mk.add_layernorm_forward(hs, agg, bias, gamma, beta, 1e-5)
+        else:
+            wy, wz, wm, wr = mk.add_layernorm_forward(agg, None, bias, gamma, beta, 1e-5)
+        y, z, m, r = mk.spgemm_forward_ln(g.indptr, g.indices, val, table, slot, n, e, k, d, hs, bias, gamma, beta, 1e-5)
+        assert torch.equal(z, wz) and torch.equal(m, wm) and torch.equal(r, wr) and torch.equal(y, wy)
+        y2, z2, m2, r2 = mk.spgemm_forward_ln(g.indptr, g.indices, val, table, slot, n, e, k, d, hs, bias, gamma,
+                                              beta, 1e-5, keep_stats=False)
+        assert z2 is None and m2 is None and r2 is None and torch.equal(y2, wy)
+    finally:
+        mk.set_max_nz(1024)
+        mk.clear_partition_cache()
+
+
+def test_sage_layer_with_the_fused_epilogue_equals_the_separate_kernels(mk):
+    """MaxKSAGEConv through MaxKAggregateLNFunction (epilogue inside the SpGEMM) against the same layer
+    on the separate kernels: forward bit-equal, parameter and input gradients to summation order."""
+    from conftest import small_graph
+    from spgemm_gnn_b200 import maxk_layers as ml
+    g = small_graph(3000, 110, seed=12, device="cuda")
+    torch.manual_seed(5)
+    layer = ml.MaxKSAGEConv(256, 256, "mean", feat_drop=0.0, norm=torch.nn.LayerNorm(256), maxk=32).cuda()
+    x0 = torch.randn(g.num_nodes(), 256, device="cuda")
+    dy = torch.randn(g.num_nodes(), 256, device="cuda")
+    res = {}
+    for fused in (True, False):
+        was = ml.FUSED_LN_EPILOGUE
+        ml.FUSED_LN_EPILOGUE = fused
+        try:
+            layer.zero_grad()
+            x = x0.clone().requires_grad_(True)
+            y = layer(g, x)
+            y.backward(dy)
+            res[fused] = (y.detach(), x.grad.clone(), [p.grad.clone() for p in layer.parameters()],
+                          type(y.grad_fn).__name__)
+        finally:
+            ml.FUSED_LN_EPILOGUE = was
+    assert res[True][3].startswith("MaxKAggregateLNFunction") and not res[False][3].startswith("MaxKAggregateLN")
+    assert torch.equal(res[True][0], res[False][0])
+    for a, b in [(res[True][1], res[False][1])] + list(zip(res[True][2], res[False][2])):
+        assert float((a - b).abs().max() / b.abs().max().clamp_min(1e-20)) < 2e-5
+
+
 @pytest.mark.parametrize("k", [32, 16])
 def test_fused_aggregate_function_equals_the_unfused_path(mk, k):
     """`maxk_aggregate` through MaxKAggregateFunction (top-k + banking fused) gives the forward and the
@@ -157,7 +230,12 @@ def test_fused_aggregate_function_equals_the_unfused_path(mk, k):
     x = dev(rng.standard_normal((g.num_nodes(), 256)).astype(np.float32))
     dy = dev(rng.standard_normal((g.num_nodes(), 256)).astype(np.float32))
     a = x.clone().requires_grad_(True)
-    ya = ml.maxk_aggregate(g, a, k, "mean")
+    was = ml.FUSED_TOPK_BANK
+    ml.FUSED_TOPK_BANK = True
+    try:
+        ya = ml.maxk_aggregate(g, a, k, "mean")
+    finally:
+        ml.FUSED_TOPK_BANK = was
     assert type(ya.grad_fn).__name__.startswith("MaxKAggregateFunction")
     ya.backward(dy)
     b = x.clone().requires_grad_(True)
