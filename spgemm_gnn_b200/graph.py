@@ -215,6 +215,36 @@ def from_edges(dst: torch.Tensor, src: torch.Tensor, num_nodes: int, *, symmetri
     return g
 
 
+def from_dgl(g) -> CSRGraph:
+    """A DGLGraph (anything with DGL's `edges()` / `num_nodes()` surface) as a `CSRGraph`, so that the
+    layers take the object the reference's layers take (utils/maxk_layers.py:82 `forward(graph, feat)`;
+    maxk_gnn_integrated.py:77-135 attaches `_sparse_format` the same way).  Rows are DESTINATIONS and
+    list their in-neighbours ascending -- what `update_all(copy_u, sum|mean)` sums over, i.e. DGL's
+    'csc' form; the reference extracts 'csr' (utils/maxk_layers.py:106), which is the same matrix
+    only on the bidirected graphs it trains on.  Parallel edges are kept (DGL counts them).  The
+    result is cached on the graph object."""
+    if isinstance(g, CSRGraph):
+        return g
+    hit = getattr(g, "_maxk_csr", None)
+    if hit is not None:
+        return hit
+    src, dst = g.edges()
+    n = int(g.num_nodes())
+    src, dst = torch.as_tensor(src), torch.as_tensor(dst)
+    if src.numel() >= 2**31:
+        raise ValueError("edge count does not fit int32")
+    key, _ = torch.sort(dst.to(torch.int64) * n + src.to(torch.int64))
+    d = torch.div(key, n, rounding_mode="floor")
+    ptr = torch.zeros(n + 1, dtype=torch.int64, device=key.device)
+    ptr[1:] = torch.cumsum(torch.bincount(d, minlength=n), 0)
+    out = CSRGraph(ptr.to(torch.int32), (key - d * n).to(torch.int32).contiguous())
+    try:
+        g._maxk_csr = out
+    except AttributeError:
+        pass
+    return out
+
+
 def synthetic_graph(
     num_nodes: int,
     num_edges: int,

@@ -9,7 +9,8 @@ What changed underneath:
     never calls it: its SpGEMM output is detached from autograd, utils/maxk_layers.py:166-171);
   * there is no DGL fallback and no CPU fallback: without the CUDA library every call raises.
 
-`graph` is a `spgemm_gnn_b200.graph.CSRGraph` (destination-indexed CSR); DGL is not needed.
+`graph` is a `spgemm_gnn_b200.graph.CSRGraph` (destination-indexed CSR) or a DGLGraph, which
+`graph.from_dgl` converts once and caches on the object; DGL itself is not needed.
 """
 from __future__ import annotations
 
@@ -20,7 +21,7 @@ import torch.nn as nn
 from torch.autograd import Function
 
 from . import maxk_kernels
-from .graph import CSRGraph
+from .graph import CSRGraph, from_dgl
 
 KERNELS_AVAILABLE = True  # kept for callers that test it (maxk_gnn_integrated.py:24-31)
 
@@ -335,6 +336,7 @@ class MaxKSAGEConv(nn.Module):
         return extract_sparse_format(sparse_tensor, self.maxk)
 
     def forward(self, graph, feat):
+        graph = from_dgl(graph)       # CSRGraph passes through; a DGLGraph is converted once and cached
         h_self = self.fc_self(feat)
         h_neigh = self.fc_neigh(feat)
         output = maxk_aggregate_add_norm(graph, h_neigh, h_self, None, self.norm, self.maxk,
@@ -377,6 +379,7 @@ class MaxKGCNConv(nn.Module):
         return extract_sparse_format(sparse_tensor, self.maxk)
 
     def forward(self, graph, feat):
+        graph = from_dgl(graph)
         if not self.allow_zero_in_degree:
             zero = graph._cache.get("has_zero_in")
             if zero is None:
@@ -416,6 +419,7 @@ class MaxKGINConv(nn.Module):
                 nn.init.xavier_uniform_(layer.weight)
 
     def forward(self, graph, feat):
+        graph = from_dgl(graph)
         neigh = maxk_aggregate(graph, feat, self.maxk, "sum")
         output = (1 + self.eps) * feat + neigh
         return self.mlp(output)

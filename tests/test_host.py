@@ -176,3 +176,28 @@ def test_forward_phases_cover_every_block_once_in_arrival_order():
                 seen += list(range(a0, a1)) + list(range(b0, b1))
             assert seen == [(rank + s) % world for s in range(world)], (world, rank, seen)
     assert forward_phases(8, 5) == [(5, 6, 0, 0), (6, 8, 0, 1), (1, 5, 0, 0)]
+
+
+def test_from_dgl_builds_the_in_edge_csr_and_caches_it():
+    """`graph.from_dgl` on a stand-in with DGL's surface (DGL is not in the image): rows are destinations,
+    in-neighbours ascending, parallel edges kept, result cached on the object."""
+    import torch
+    from spgemm_gnn_b200.graph import CSRGraph, from_dgl
+
+    class FakeDGL:
+        def __init__(self, src, dst, n):
+            self._s, self._d, self._n = torch.tensor(src), torch.tensor(dst), n
+
+        def edges(self):
+            return self._s, self._d
+
+        def num_nodes(self):
+            return self._n
+
+    g = FakeDGL([2, 0, 1, 2, 2, 3], [0, 0, 0, 1, 1, 3], 5)       # 2->1 twice
+    c = from_dgl(g)
+    assert c.indptr.tolist() == [0, 3, 5, 5, 6, 6]
+    assert c.indices.tolist() == [0, 1, 2, 2, 2, 3]
+    assert from_dgl(g) is c and from_dgl(c) is c
+    assert c.in_degrees().tolist() == [3, 2, 0, 1, 0]
+    assert isinstance(c, CSRGraph)

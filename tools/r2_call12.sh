@@ -9,5 +9,5 @@ MAXK_TOPK_TILE=1 MAXK_LIB=$PWD/spgemm_gnn_b200/libmaxk_tilebw.so timeout 300 pyt
 } > $OUT/topk_tile_bitwise.log 2>&1
 cat $OUT/topk_tile_bitwise.log
 for f in 1 0; do
-  MAXK_FUSED_LN=$f timeout 600 python tools/epoch_profile.py > $OUT/epoch_ln$f.txt 2>&1; echo "epoch_profile fused_ln=$f rc=$?"; grep -i "ms per epoch\|epoch" $OUT/epoch_ln$f.txt | head -5
+  MAXK_FUSED_LN=$f timeout 600 python tools/epoch_profile.py --model maxk-sage --tf32 > $OUT/epoch_ln$f.txt 2>&1; echo "epoch_profile fused_ln=$f rc=$?"; grep "epoch ms" $OUT/epoch_ln$f.txt
 done
