@@ -20,7 +20,7 @@ cbsr_scatter_kernel(const float* __restrict__ g, const IdxT* __restrict__ sp_ind
     const int w = threadIdx.x >> 5;
     const int lane = lane_id();
     float* __restrict__ buf = srow + w * dpad;
-    const int64_t row = static_cast<int64_t>(blockIdx.x) * kRowsPerBlock + w;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + w;  // rows per CTA = warps
     if (row >= n) return;
     for (int c = lane * 4; c < dpad; c += 128)
         *reinterpret_cast<float4*>(buf + c) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -66,9 +66,13 @@ extern "C" int mk_cbsr_scatter(const float* g, const void* sp_index, int index_b
     if (n == 0) return MK_OK;
     if (!g || !sp_index || !dense) return MK_EINVAL;
     const int dpad = (d + 3) & ~3;
-    const size_t smem = static_cast<size_t>(mk::kRowsPerBlock) * dpad * 4;
+    // rows (= warps) per CTA: 8 while their staging rows fit shared memory, fewer for very wide rows --
+    // every D the top-k accepts (<= 49,152) can be scattered back
+    int rpb = mk::kRowsPerBlock;
+    while (rpb > 1 && static_cast<size_t>(rpb) * dpad * 4 > 200 * 1024) rpb >>= 1;
+    const size_t smem = static_cast<size_t>(rpb) * dpad * 4;
     if (smem > 200 * 1024) return MK_EUNSUPPORTED;
-    const int64_t blocks = (n + mk::kRowsPerBlock - 1) / mk::kRowsPerBlock;
+    const int64_t blocks = (n + rpb - 1) / rpb;
     if (blocks > 0x7fffffffLL) return MK_EUNSUPPORTED;
     cudaStream_t st = mk::as_stream(stream);
     if (index_bytes == 1) {
@@ -76,7 +80,7 @@ extern "C" int mk_cbsr_scatter(const float* g, const void* sp_index, int index_b
             MK_CUDA_TRY(cudaFuncSetAttribute(mk::cbsr_scatter_kernel<uint8_t>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem)));
-        mk::cbsr_scatter_kernel<uint8_t><<<static_cast<unsigned>(blocks), mk::kRowsPerBlock * 32,
+        mk::cbsr_scatter_kernel<uint8_t><<<static_cast<unsigned>(blocks), rpb * 32,
                                            smem, st>>>(
             g, static_cast<const uint8_t*>(sp_index), dense, n, k, d);
     } else {
@@ -84,7 +88,7 @@ extern "C" int mk_cbsr_scatter(const float* g, const void* sp_index, int index_b
             MK_CUDA_TRY(cudaFuncSetAttribute(mk::cbsr_scatter_kernel<uint16_t>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem)));
-        mk::cbsr_scatter_kernel<uint16_t><<<static_cast<unsigned>(blocks), mk::kRowsPerBlock * 32,
+        mk::cbsr_scatter_kernel<uint16_t><<<static_cast<unsigned>(blocks), rpb * 32,
                                             smem, st>>>(
             g, static_cast<const uint16_t*>(sp_index), dense, n, k, d);
     }

@@ -461,7 +461,7 @@ extern "C" int mk_spgemm_fwd(const mk_part* parts, int64_t num_parts, int64_t nu
     if (index_bytes != 1 && index_bytes != 2) return MK_EINVAL;
     if ((index_bytes == 1 && d > 256) || d > 65536) return MK_EINVAL;
     if (n_rows == 0 || num_parts == 0) return MK_OK;
-    if (!parts || !out || !sp_data || !sp_index) return MK_EINVAL;
+    if (!parts || !out || !sp_data || !sp_index || !idx || !val) return MK_EINVAL;
     if (num_slots > 0 && !partial) return MK_EINVAL;
     if (num_parts > 0x7fffffffLL) return MK_EUNSUPPORTED;
     cudaStream_t st = mk::as_stream(stream);

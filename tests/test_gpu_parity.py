@@ -265,7 +265,8 @@ def test_golden_vectors_through_the_cuda_path(mk, golden):
             assert np.array_equal(data.cpu().numpy(), golden[pre + "sp_data"])
 
 
-@pytest.mark.parametrize("n,d,k", [(100, 256, 32), (33, 100, 7), (20, 384, 16), (7, 1500, 40)])
+@pytest.mark.parametrize("n,d,k", [(100, 256, 32), (33, 100, 7), (20, 384, 16), (7, 1500, 40), (5, 9000, 33),
+                                   (3, 49152, 64)])
 def test_scatter_and_gather(mk, n, d, k):
     from oracle import maxk_oracle as mo
     rng = np.random.default_rng(d)

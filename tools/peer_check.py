@@ -208,16 +208,18 @@ def distributed(bench: bool) -> int:
         if bench and "--sweep" in sys.argv:
             # who moves the rows / how many pusher CTAs, forward and backward timed on their own
             fi0 = res[True][1]
-            for push, pushers in (("nccl", 0), ("sm", 592), ("sm", 148), ("sm", 296), ("sm", 1184), ("dma", 0)):
+            for push, pushers, ph in (("nccl", 0, 1), ("nccl", 0, 0), ("sm", 592, 1), ("sm", 592, 0), ("dma", 0, 1),
+                                      ("dma", 0, 0), ("sm", 148, 1), ("sm", 1184, 1)):
                 peer.set_enabled(push != "nccl")
+                peer._PHASES = bool(ph)
                 if push != "nccl":
                     peer._PUSH, peer._PUSHERS = push, pushers or peer._PUSHERS
                 tf = timed(lambda: mdist.sharded_forward(sd, si, ptr, idx, val, n_rows, d))
                 tb = timed(lambda: mdist.sharded_backward(dy, fi0, ptr, idx, val, n_rows, d))
                 ts = timed(step)
                 if rank == 0:
-                    print(f"  {name} [{push} {pushers}]: fwd {tf:.3f}  bwd {tb:.3f}  fwd+bwd {ts:.3f} ms", flush=True)
-            peer._PUSH, peer._PUSHERS = "sm", 592
+                    print(f"  {name} [{push} {pushers} phases={ph}]: fwd {tf:.3f}  bwd {tb:.3f}  fwd+bwd {ts:.3f} ms", flush=True)
+            peer._PUSH, peer._PUSHERS, peer._PHASES = "sm", 592, True
             peer.set_enabled(True)
         o0, f0, b0 = res[False]
         o1, f1, b1 = res[True]
