@@ -212,6 +212,16 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
     }
     const mk_part rec = parts[role];
 
+    // f-3 epilogue: this row's h_self, asked for now and consumed when the row is finished (the load's
+    // latency would otherwise sit at the end of every CTA)
+    float4 hs[4];
+    if (ep.gamma != nullptr && ep.h_self != nullptr && rec.slot < 0) {
+        const float* __restrict__ hrow = ep.h_self + static_cast<int64_t>(rec.row) * d;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j * 128 + lane * 4 < d) hs[j] = ld_stream_f4(hrow + j * 128 + lane * 4);
+    }
+
     // which source blocks have arrived (bit q); refreshed only while something is missing
     unsigned have = 0xffffffffu;
     if (WAIT) {
@@ -343,8 +353,8 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
     if (ep.gamma != nullptr && rec.slot < 0) {
         // f-3: the finished row goes straight into y = LayerNorm(h_self + row + bias) * gamma + beta
         // (and z, mean, rstd for the backward) -- no dense round trip of the aggregated row
-        fwd_epilogue_row(ep, [&](int c) { return *reinterpret_cast<const float4*>(acc + c); }, out, rec.row, d,
-                         lane);
+        fwd_epilogue_row(ep, [&](int c) { return *reinterpret_cast<const float4*>(acc + c); },
+                         [&](int c) { return hs[c >> 7]; }, out, rec.row, d, lane);
         return;
     }
     if (ph.accumulate && rec.slot < 0) {  // later phase: on top of what the earlier ones wrote

@@ -93,17 +93,16 @@ __device__ __forceinline__ void add_layernorm_row(FA first, FB second, const flo
 }
 
 // The forward's use: `agg(c)` is the aggregated row (shared memory or folded partials), D <= 512.
-template <typename FAgg>
-__device__ __forceinline__ void fwd_epilogue_row(const FwdEpilogue& ep, FAgg agg, float* __restrict__ y,
-                                                 int64_t row, int d, int lane) {
+// `hself(c)`: this lane's float4 of h_self at column c (prefetched registers, or a load).
+template <typename FAgg, typename FSelf>
+__device__ __forceinline__ void fwd_epilogue_row(const FwdEpilogue& ep, FAgg agg, FSelf hself,
+                                                 float* __restrict__ y, int64_t row, int d, int lane) {
     float* z_row = ep.z ? ep.z + row * d : nullptr;
     float* y_row = y + row * d;
     float* m = ep.mean ? ep.mean + row : nullptr;
     float* r = ep.rstd ? ep.rstd + row : nullptr;
     if (ep.h_self != nullptr) {
-        const float* __restrict__ hs = ep.h_self + row * d;
-        add_layernorm_row<4, true>([&](int c) { return ld_stream_f4(hs + c); }, agg, ep.bias, ep.gamma, ep.beta,
-                                   z_row, y_row, m, r, d, ep.eps, lane);
+        add_layernorm_row<4, true>(hself, agg, ep.bias, ep.gamma, ep.beta, z_row, y_row, m, r, d, ep.eps, lane);
     } else {
         add_layernorm_row<4, false>(agg, agg, ep.bias, ep.gamma, ep.beta, z_row, y_row, m, r, d, ep.eps, lane);
     }

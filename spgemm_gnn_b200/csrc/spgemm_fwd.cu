@@ -330,7 +330,8 @@ spgemm_fold_ln_kernel(const mk_part* __restrict__ parts, int64_t num_parts,
         }
         return s;
     };
-    fwd_epilogue_row(ep, agg, y, rec.row, d, lane_id());
+    const float* __restrict__ hrow = ep.h_self ? ep.h_self + static_cast<int64_t>(rec.row) * d : nullptr;
+    fwd_epilogue_row(ep, agg, [&](int c) { return ld_stream_f4(hrow + c); }, y, rec.row, d, lane_id());
 }
 
 int launch_fold(const mk_part* parts, int64_t num_parts, const float* partial, float* out, int d,
@@ -461,7 +462,7 @@ extern "C" int mk_spgemm_fwd(const mk_part* parts, int64_t num_parts, int64_t nu
     if (index_bytes != 1 && index_bytes != 2) return MK_EINVAL;
     if ((index_bytes == 1 && d > 256) || d > 65536) return MK_EINVAL;
     if (n_rows == 0 || num_parts == 0) return MK_OK;
-    if (!parts || !out || !sp_data || !sp_index || !idx || !val) return MK_EINVAL;
+    if (!parts || !out || !sp_data || !sp_index) return MK_EINVAL;  // idx / val may be NULL: a graph without stored entries
     if (num_slots > 0 && !partial) return MK_EINVAL;
     if (num_parts > 0x7fffffffLL) return MK_EUNSUPPORTED;
     cudaStream_t st = mk::as_stream(stream);

@@ -446,7 +446,7 @@ extern "C" int mk_sspmm_bwd(const mk_part* parts, int64_t num_parts, const int32
     cudaStream_t st = mk::as_stream(stream);
     MK_CUDA_TRY(cudaMemsetAsync(dxs, 0, static_cast<size_t>(n_src) * k * sizeof(float), st));
     if (n_rows == 0 || num_parts == 0) return MK_OK;
-    if (!parts || !dy || !sp_index || !idx || !val) return MK_EINVAL;
+    if (!parts || !dy || !sp_index) return MK_EINVAL;  // idx / val may be NULL: a graph without stored entries
     if (num_parts > 0x7fffffffLL) return MK_EUNSUPPORTED;
     return index_bytes == 1
                ? mk::launch_bwd<uint8_t>(parts, num_parts, idx, val, dy, sp_index, dxs, k, d, st)

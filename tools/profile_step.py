@@ -35,23 +35,28 @@ x = torch.randn(n, a.dim, device="cuda", generator=gen)
 dy = torch.randn(n, a.dim, device="cuda", generator=gen)
 sd, si = mk.maxk_forward_cbsr(x, a.k)
 banked = not a.plain and mk.banked_supported(a.k, a.dim)
+packed = banked and a.k in (8, 16) and mk.packed_supported(a.k, a.dim)   # what the product runs at k = 8, 16
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 for it in range(a.warmup + a.steps):
     ev[0].record()
-    if banked:
+    if packed:
+        bp = mk.cbsr_bank_packed(sd, si, a.dim)
+    elif banked:
         bd, bi, bs = mk.cbsr_bank(sd, si, a.dim)
     ev[1].record()
-    if banked:
+    if packed:
+        out = mk.spgemm_forward_packed(g.indptr, g.indices, val, bp, n, e, a.k, a.dim)
+    elif banked:
         out = mk.spgemm_forward_banked(g.indptr, g.indices, val, bd, bs, n, e, a.k, a.dim)
     else:
         out, _ = mk.spgemm_forward(g.indptr, g.indices, val, sd, si, n, e, a.k, a.dim)
     ev[2].record()
-    if banked and a.banked_bwd:
+    if banked and a.banked_bwd and not packed:
         dxs = mk.spgemm_backward_banked(g.indptr, g.indices, val, dy, bs, n, e, a.k, a.dim)
     else:
         dxs = mk.spgemm_backward(g.indptr, g.indices, val, dy, si, n, e, a.k, a.dim)
     ev[3].record()
 torch.cuda.synchronize()
 print(f"{a.workload} N={n} E={e} k={a.k} D={a.dim} max_nz={mk.get_max_nz()} bwd_blocks={mk.backward_blocks(n, a.k, n, e)} "
-      f"{'banked' if banked else 'plain'}: bank {ev[0].elapsed_time(ev[1]):.3f} ms  "
+      f"{'packed' if packed else 'banked' if banked else 'plain'}: bank {ev[0].elapsed_time(ev[1]):.3f} ms  "
       f"fwd {ev[1].elapsed_time(ev[2]):.3f} ms  bwd {ev[2].elapsed_time(ev[3]):.3f} ms")
