@@ -41,7 +41,7 @@ def _aggregate_cbsr(g, sp_data, sp_index, kind, dim):
 # padded ONCE with zero columns (`pad_features`) and the two weights are padded on the fly inside
 # the call -- same parameters, same state dict, same result up to summation order.  Off by default
 # until measured.
-_ALIGN_GEMM = os.environ.get("MAXK_ALIGN_GEMM", "0") != "0"
+_ALIGN_GEMM = os.environ.get("MAXK_ALIGN_GEMM", "1") != "0"
 _ALIGN = 8
 
 
