@@ -172,8 +172,8 @@ def workload_config(args, world, n, e):
             "scale": args.scale,
             "parallelism": "1 GPU" if world == 1 else f"1-D row partition over {world} GPUs, "
                            "CBSR all-gather fwd + CBSR-grad reduce-scatter bwd "
-                           + ("(own NVLink kernels over CUDA-IPC peer windows)"
-                              if _peer_on() else "(NCCL)"),
+                           + ("(own NVLink kernels over CUDA-IPC peer windows; NCCL above 32 MB at >= 8 ranks "
+                              "-- see parity.exchange)" if _peer_on() else "(NCCL)"),
             "l2": "no explicit flush: every step streams inputs larger than L2 "
                   "(edge arrays 8 B/entry + dense rows); the CBSR table is re-used inside one "
                   "launch by construction"}
@@ -285,29 +285,46 @@ def parity_record(mk, mdist, g, rank, world, ptr, idx, val, val_full, x_local, d
     rec = {"fwd_max_rel": rel(out, out_1), "bwd_max_rel": rel(dxs, dxs_1),
            "index_equal": bool(torch.equal(fi.view(torch.uint8), si_f.view(torch.uint8)))}
     was = mpeer.enabled()
-    if was:  # same layer with the exchanges as NCCL calls
+    fwd_peer = mpeer.wanted(world, world * n_rows * k * 7)
+    bwd_peer = mpeer.wanted(world, world * n_rows * k * 4)
+    if was:
+        # both forms of the two exchanges, whichever the timed step uses at this size: the library's own
+        # kernels over peer windows (size limit lifted) and the NCCL calls, each against the one-GPU rows
+        # and against each other
+        lim = mpeer.set_max_mb(0)
+        out_p, fi_p = mdist.sharded_forward(sd, si, ptr, idx, val, n_rows, d)
+        dxs_p = mdist.sharded_backward(dy, fi_p, ptr, idx, val, n_rows, d)
+        out_p, dxs_p = out_p.clone(), dxs_p.clone()
+        mpeer.set_max_mb(lim)
         mpeer.set_enabled(False)
         out_n, fi_n = mdist.sharded_forward(sd, si, ptr, idx, val, n_rows, d)
         dxs_n = mdist.sharded_backward(dy, fi_n, ptr, idx, val, n_rows, d)
         mpeer.set_enabled(True)
-        rec["fwd_bit_equal_nccl_form"] = bool(torch.equal(out, out_n))
-        rec["bwd_max_rel_nccl_form"] = rel(dxs, dxs_n)
-    for key in ("fwd_max_rel", "bwd_max_rel", "bwd_max_rel_nccl_form"):
-        if key in rec:
-            rec[key] = _max_over_ranks(rec[key], device, world)
-    flags = torch.tensor([int(rec["index_equal"]), int(rec.get("fwd_bit_equal_nccl_form", True))],
+        rec["fwd_max_rel_peer_form"] = rel(out_p, out_1)
+        rec["bwd_max_rel_peer_form"] = rel(dxs_p, dxs_1)
+        rec["fwd_max_rel_nccl_form"] = rel(out_n, out_1)
+        rec["bwd_max_rel_nccl_form"] = rel(dxs_n, dxs_1)
+        rec["fwd_bit_equal_peer_vs_nccl"] = bool(torch.equal(out_p, out_n))
+        rec["bwd_max_rel_peer_vs_nccl"] = rel(dxs_p, dxs_n)
+    rel_keys = [key for key in rec if "max_rel" in key]
+    for key in rel_keys:
+        rec[key] = _max_over_ranks(rec[key], device, world)
+    flags = torch.tensor([int(rec["index_equal"]), int(rec.get("fwd_bit_equal_peer_vs_nccl", True))],
                          device=device, dtype=torch.int32)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     rec["index_equal"] = bool(flags[0].item())
-    if "fwd_bit_equal_nccl_form" in rec:
-        rec["fwd_bit_equal_nccl_form"] = bool(flags[1].item())
-    rec["ok"] = bool(rec["fwd_max_rel"] <= 1e-6 and rec["bwd_max_rel"] <= 1e-5 and rec["index_equal"]
-                     and rec.get("fwd_bit_equal_nccl_form", True)
-                     and rec.get("bwd_max_rel_nccl_form", 0.0) <= 1e-5)
+    if "fwd_bit_equal_peer_vs_nccl" in rec:
+        rec["fwd_bit_equal_peer_vs_nccl"] = bool(flags[1].item())
+    rec["ok"] = bool(all(rec[key] <= (1e-6 if key.startswith("fwd") else 1e-5) for key in rel_keys)
+                     and rec["index_equal"] and rec.get("fwd_bit_equal_peer_vs_nccl", True))
     rec["against"] = ("rows of this rank recomputed on one GPU from NCCL-gathered dense inputs (forward: same "
                       "kernel without the exchange; backward: whole-graph SSpMM, rank's slice)"
-                      + ("; and the NCCL form of both exchanges" if was else ""))
-    rec["exchange"] = "peer windows" if was else "NCCL"
+                      + ("; the peer-window form and the NCCL form of both exchanges, each against those rows "
+                         "and against each other" if was else ""))
+    rec["exchange"] = {"forward": "peer windows" if (was and fwd_peer) else "NCCL",
+                       "backward": "peer windows" if (was and bwd_peer) else "NCCL",
+                       "rule": "own NVLink kernels unless the group has >= 8 ranks and the table / gradient exceeds "
+                               "MAXK_PEER_MAX_MB (32): measured faster there (profiles/r2/peer_phases8_call13.log)"}
     return rec
 
 

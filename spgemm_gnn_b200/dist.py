@@ -222,7 +222,7 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
         if blk is not None:
             phases = maxk_kernels.forward_phases(world, rank)
     pkw = dict(phases=phases, blk=blk, n_blocks=world) if phases is not None else dict(split=split)
-    if _peer_path(group, r * k * 4):
+    if _peer_path(group, r * k * 4) and peer.wanted(world, world * r * k * (6 + ib if form == "banked" else 4 + ib)):
         rows = world * r
         per_rank = {"banked": [r * k * 4, r * k * 2, r * k * ib], "packed": [r * k * 8, r * k * ib],
                     "plain": [r * k * 4, r * k * ib]}[form]
@@ -304,7 +304,7 @@ def sharded_backward(grad_out, full_index, ptr, idx, val, num_rows, dim_origin, 
     n_src, k = full_index.shape
     world = dist.get_world_size(group)
     r = n_src // world
-    if _peer_path(group, r * k * 4):
+    if _peer_path(group, r * k * 4) and peer.wanted(world, n_src * k * 4):
         offs, total = peer.layout([n_src * k * 4])
         win = peer.window("dxs", total, group)
         if win is not None:

@@ -57,8 +57,18 @@ _OVERLAP = os.environ.get("MAXK_PEER_OVERLAP", "1") != "0"
 _PUSH = os.environ.get("MAXK_PEER_PUSH", "sm")
 _PUSHERS = int(os.environ.get("MAXK_PEER_PUSHERS", "592"))   # pusher CTAs (32 threads each)
 # forward cut into source-block phases (own block, the next senders, the rest: one launch each), so
-# that whole launches overlap the transfer instead of the CTAs that happen to be resident
-_PHASES = os.environ.get("MAXK_PEER_PHASES", "1") != "0"
+# that whole launches overlap the transfer instead of the CTAs that happen to be resident.  Measured at
+# 8 GPUs on the Reddit shape (profiles/r2/peer_phases8_call13.log): the three launches cost 0.13 ms more
+# than one (every record zeroes, folds and writes its 8 KB of accumulators three times, and the rows
+# are read back twice) and hide less than that of the ~0.12 ms all-gather -- 0.683 ms against 0.638 ms
+# with the copy engines, 0.713 against 0.600 with pusher CTAs.  Off by default.
+_PHASES = os.environ.get("MAXK_PEER_PHASES", "0") != "0"
+# Above this table size, groups of 8 or more ranks use NCCL's all-gather / reduce-scatter instead of the
+# peer kernels: the own kernels win where the exchange is latency-bound (20 k-node graph at 8 GPUs:
+# 0.30 ms per layer against 0.69 ms) and lose a few per cent where it is bandwidth-bound (Reddit shape,
+# 52 MB table: 1.014 against 0.953 ms per layer; products shape 2.75 against 2.68 ms -- NCCL's NVLS
+# all-gather sends every row once, the push sends it seven times).  MAXK_PEER_MAX_MB=0: no limit.
+_MAX_BYTES = int(os.environ.get("MAXK_PEER_MAX_MB", "32")) << 20
 _launches = 0
 
 
@@ -85,6 +95,20 @@ def timeout_ms() -> int:
 
 def overlap() -> bool:
     return _OVERLAP
+
+
+def wanted(world: int, exchange_bytes: int) -> bool:
+    """Peer kernels or NCCL for an exchange of `exchange_bytes` (whole table / whole gradient) over
+    `world` ranks -- same answer on every rank (same shapes)."""
+    return _ENABLED and (_MAX_BYTES == 0 or world < 8 or exchange_bytes <= _MAX_BYTES)
+
+
+def set_max_mb(mb: int) -> int:
+    """Size limit of `wanted` in MB (0: none); returns the previous one."""
+    global _MAX_BYTES
+    was = _MAX_BYTES >> 20
+    _MAX_BYTES = max(int(mb), 0) << 20
+    return was
 
 
 def phases() -> bool:

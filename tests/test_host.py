@@ -135,15 +135,16 @@ def test_aligned_linear_is_the_same_layer():
     lin.zero_grad()
     xp = models.pad_features(x)
     assert xp.shape == (50, 608) and not xp[:, 602:].any() and models.pad_features(xp) is xp
-    assert not models.align_gemm()
-    assert torch.equal(models.aligned_linear(lin, x), y0)             # no padding asked for, none needed
-    models.set_align_gemm(True)
+    was = models.align_gemm()
+    models.set_align_gemm(False)
     try:
+        assert torch.equal(models.aligned_linear(lin, x), y0)         # no padding asked for, none needed
+        models.set_align_gemm(True)
         y1 = models.aligned_linear(lin, xp)
         assert y1.shape == (50, 41)
         y1.backward(gy)
     finally:
-        models.set_align_gemm(False)
+        models.set_align_gemm(was)
     torch.testing.assert_close(y1, y0, rtol=1e-12, atol=1e-12)
     torch.testing.assert_close(lin.weight.grad, g0[0], rtol=1e-12, atol=1e-12)
     torch.testing.assert_close(lin.bias.grad, g0[1], rtol=1e-12, atol=1e-12)
