@@ -33,8 +33,12 @@ extern "C" {
 #define MK_API __attribute__((visibility("default")))
 #endif
 
-#define MK_VERSION 200 /* major*100 + minor; 2.00: overlapped copy-engine all-gather (mk_peer_push & co. replace
-                          * mk_peer_allgather / mk_peer_bank_push), mk_spgemm_fwd_banked_ex, soft peer time-outs */
+#define MK_VERSION 201 /* major*100 + minor; 2.00: overlapped copy-engine all-gather (mk_peer_push & co. replace
+                          * mk_peer_allgather / mk_peer_bank_push), mk_spgemm_fwd_banked_ex, soft peer time-outs;
+                          * 2.01: mk_topk_cbsr_bank, mk_spgemm_fwd_banked_phase, mk_spgemm_fwd_banked_ln,
+                          * mk_sspmm_bwd_tiled, packed tables.  Experimental entry points -- measured dead ends
+                          * kept as the record of the experiment, off in every product path, free to go in 3.x:
+                          * mk_sspmm_bwd_tma, mk_sspmm_bwd_banked, mk_spgemm_fwd_banked_phase, mk_topk_cbsr_bank. */
 
 enum {
     MK_OK = 0,
