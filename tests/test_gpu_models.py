@@ -131,6 +131,51 @@ def test_fifty_epoch_loss_curve(name):
     assert rel.max() <= LOSS_CAP
 
 
+def test_fifty_epoch_loss_curve_on_the_flickr_shape():
+    """BASELINE.json config 1 at full size: Flickr-shaped graph (89,250 nodes, ~0.99 M stored entries,
+    500 input features, 7 classes), SAGE 3 x 256, k = 32, LayerNorm, 50 Adam steps -- the CUDA path
+    against the reference formulation in float64, yardstick = the reference's own float32 run."""
+    import copy
+    import torch.nn.functional as F
+    from oracle import ref_torch
+    from spgemm_gnn_b200.graph import FEATS, shaped_graph
+    from spgemm_gnn_b200.train import train_epochs
+    g = shaped_graph("flickr")
+    n = g.num_nodes()
+    in_f, classes = FEATS["flickr"]
+    gen = torch.Generator().manual_seed(97)
+    x = torch.randn(n, in_f, generator=gen)
+    y = torch.randint(0, classes, (n,), generator=gen)
+    mask = torch.rand(n, generator=gen) < 0.66
+    ref, ours = _pair("sage", in_f, 256, 3, classes, 32, norm=True)
+    adj = ref_torch.csr_matrix(g.indptr, g.indices, g.edge_weights("mean").double(), g.num_src)
+    ref32 = copy.deepcopy(ref).float()
+
+    def run_ref(model, a, xin):
+        opt = torch.optim.Adam(model.parameters(), lr=0.01)
+        out = []
+        for _ in range(50):
+            loss = F.cross_entropy(model(a, xin)[mask], y[mask])
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            out.append(float(loss))
+        return np.array(out)
+
+    ref_l = run_ref(ref, adj, x.double())
+    ref32_l = run_ref(ref32, adj.float(), x)
+    losses, _ = train_epochs(ours, g.to("cuda"), x.cuda(), y.cuda(), mask.cuda(), 50, lr=0.01)
+    our_l = np.array(losses)
+    rel = np.abs(our_l - ref_l) / np.abs(ref_l)
+    drift = np.abs(ref32_l - ref_l) / np.abs(ref_l)
+    print(f"flickr shape: loss {ref_l[0]:.4f} -> {ref_l[-1]:.4f}; max rel deviation ours {rel.max():.2e} "
+          f"(epoch {rel.argmax()}), reference fp32-vs-fp64 drift {drift.max():.2e}")
+    assert ref_l[-1] < 0.95 * ref_l[0]
+    assert rel[:3].max() <= 1e-4
+    assert rel.max() <= max(LOSS_FACTOR * drift.max(), LOSS_FLOOR), (rel.max(), drift.max())
+    assert rel.max() <= LOSS_CAP
+
+
 def test_integrated_models_train(name="maxk-sage"):
     """utils/integrated_models.py family: runs, gradients reach every parameter, loss falls."""
     from spgemm_gnn_b200 import models
