@@ -20,6 +20,14 @@
 //   E*(4 + 4 + k*w + k*4) + N*D*4 + N*k*4 + (N+1)*4 + P*16.
 #include "common.cuh"
 
+// Records per CTA of the plain backward (measurement knob, VERDICT r1 "occupancy ceiling": one 32-thread
+// CTA per record caps residency at 32 CTAs = 32 warps per SM).  W warps per CTA, one record each, lift
+// the cap to 64 warps.  Measured on a B200 (profiles/r2/bwd_warps_per_cta.log): no gain -- the kernel is
+// bound by the SM->L2 request path (93 %), not by latency; the default stays 1.
+#ifndef MK_BWD_WARPS
+#define MK_BWD_WARPS 1
+#endif
+
 namespace mk {
 
 template <typename IdxT>
@@ -37,17 +45,25 @@ __device__ __forceinline__ void load_cols4<uint16_t>(const uint16_t* p, int (&c)
 
 template <int K, typename IdxT, int U>
 __device__ __forceinline__ void
-sspmm_bwd_body(const mk_part* __restrict__ parts, const int* __restrict__ idx,
+sspmm_bwd_body(const mk_part* __restrict__ parts, [[maybe_unused]] int64_t num_parts, const int* __restrict__ idx,
                const float* __restrict__ val, const float* __restrict__ dy,
                const IdxT* __restrict__ sp_index, float* __restrict__ dxs, int d, int vec_dy) {
     constexpr int LPN = K / 4;     // lanes per neighbour
     constexpr int G = 32 / LPN;    // neighbours per warp step
     static_assert(K % 4 == 0 && (32 % LPN) == 0, "K must be 4, 8, 16, 32, 64 or 128");
-    extern __shared__ __align__(16) float dys[];
+    extern __shared__ __align__(16) float dys_all[];
     const int lane = lane_id();
     const int g = lane / LPN;
     const int t = lane % LPN;
+#if MK_BWD_WARPS > 1
+    const int64_t rid = static_cast<int64_t>(blockIdx.x) * MK_BWD_WARPS + (threadIdx.x >> 5);
+    if (rid >= num_parts) return;
+    float* __restrict__ dys = dys_all + (threadIdx.x >> 5) * ((d + 3) & ~3);
+    const mk_part rec = parts[rid];
+#else
+    float* __restrict__ dys = dys_all;
     const mk_part rec = parts[blockIdx.x];
+#endif
     if (rec.len == 0) return;
 
     const float* __restrict__ dyr = dy + static_cast<int64_t>(rec.row) * d;
@@ -133,18 +149,18 @@ sspmm_bwd_body(const mk_part* __restrict__ parts, const int* __restrict__ idx,
 // 2.60 ms against 2.63 ms at 28 CTAs (72 registers) on the Reddit shape; at k = 64 any register cap
 // spills and loses (4.90-4.96 vs 4.78 ms), so the wide variants keep the compiler's own choice.
 template <int K, typename IdxT, int U>
-__global__ void __launch_bounds__(32, 32)
-sspmm_bwd_kernel_occ32(const mk_part* __restrict__ parts, const int* __restrict__ idx,
+__global__ void __launch_bounds__(32 * MK_BWD_WARPS, 32 / MK_BWD_WARPS)
+sspmm_bwd_kernel_occ32(const mk_part* __restrict__ parts, int64_t num_parts, const int* __restrict__ idx,
                        const float* __restrict__ val, const float* __restrict__ dy,
                        const IdxT* __restrict__ sp_index, float* __restrict__ dxs, int d, int vec_dy) {
-    sspmm_bwd_body<K, IdxT, U>(parts, idx, val, dy, sp_index, dxs, d, vec_dy);
+    sspmm_bwd_body<K, IdxT, U>(parts, num_parts, idx, val, dy, sp_index, dxs, d, vec_dy);
 }
 template <int K, typename IdxT, int U>
-__global__ void __launch_bounds__(32)
-sspmm_bwd_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
+__global__ void __launch_bounds__(32 * MK_BWD_WARPS)
+sspmm_bwd_kernel(const mk_part* __restrict__ parts, int64_t num_parts, const int* __restrict__ idx,
                  const float* __restrict__ val, const float* __restrict__ dy,
                  const IdxT* __restrict__ sp_index, float* __restrict__ dxs, int d, int vec_dy) {
-    sspmm_bwd_body<K, IdxT, U>(parts, idx, val, dy, sp_index, dxs, d, vec_dy);
+    sspmm_bwd_body<K, IdxT, U>(parts, num_parts, idx, val, dy, sp_index, dxs, d, vec_dy);
 }
 
 // ---- column-blocked, row-tiled form for CBSR gradients that do not fit L2 -------------------------
@@ -390,15 +406,15 @@ static int launch_bwd_k(const mk_part* parts, int64_t num_parts, const int* idx,
     constexpr int U = (K / 4 >= 8) ? 8 : (K / 4);
 #endif
     const int dpad = (d + 3) & ~3;
-    const size_t smem = static_cast<size_t>(dpad) * 4;
+    const size_t smem = static_cast<size_t>(dpad) * 4 * MK_BWD_WARPS;
     if (smem > 200 * 1024) return MK_EUNSUPPORTED;
     auto kern = K <= 32 ? sspmm_bwd_kernel_occ32<K, IdxT, U> : sspmm_bwd_kernel<K, IdxT, U>;
     if (smem > 48 * 1024)
         MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
     const int vec_dy = (d % 4 == 0) && (reinterpret_cast<uintptr_t>(dy) % 16 == 0);
-    kern<<<static_cast<unsigned>(num_parts), 32, smem, st>>>(
-        parts, idx, val, dy, static_cast<const IdxT*>(sp_index), dxs, d, vec_dy);
+    kern<<<static_cast<unsigned>((num_parts + MK_BWD_WARPS - 1) / MK_BWD_WARPS), 32 * MK_BWD_WARPS, smem, st>>>(
+        parts, num_parts, idx, val, dy, static_cast<const IdxT*>(sp_index), dxs, d, vec_dy);
     MK_LAUNCH_CHECK("sspmm_bwd_kernel");
     return MK_OK;
 }

@@ -48,12 +48,20 @@ def _task(n=3000, avg_deg=25, in_f=64, classes=7, seed=97):
 
 @pytest.fixture(autouse=True)
 def _no_tf32():
+    """fp32 GEMMs with the reference's own extents: TF32 and the zero-padded first / last Linear
+    (MAXK_ALIGN_GEMM, on by default for speed) change cuBLAS's summation order, and MaxK turns any
+    rounding difference into a top-k flip a few epochs later -- the curve comparisons below isolate the
+    hot path from that.  `test_aligned_gemm_path_matches_the_plain_one` covers the padded path."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    from spgemm_gnn_b200 import models
     old = torch.backends.cuda.matmul.allow_tf32
+    was = models.align_gemm()
     torch.backends.cuda.matmul.allow_tf32 = False
+    models.set_align_gemm(False)
     yield
     torch.backends.cuda.matmul.allow_tf32 = old
+    models.set_align_gemm(was)
 
 
 KIND = {"sage": "mean", "gcn": "both", "gin": "sum"}
@@ -129,6 +137,34 @@ def test_fifty_epoch_loss_curve(name):
     assert rel[:3].max() <= 1e-4                       # before any top-k flip: plain fp32 error
     assert rel.max() <= max(LOSS_FACTOR * drift.max(), LOSS_FLOOR), (rel.max(), drift.max())
     assert rel.max() <= LOSS_CAP
+
+
+def test_aligned_gemm_path_matches_the_plain_one():
+    """MAXK_ALIGN_GEMM (features padded once, first / last weights padded inside the call): same logits
+    and the same gradients as the plain Linear layers, to fp32 GEMM rounding, on extents that are not
+    multiples of 8 (Reddit's 602 inputs / 41 classes)."""
+    import torch.nn.functional as F
+    from spgemm_gnn_b200 import models
+    from spgemm_gnn_b200.graph import synthetic_graph
+    g = synthetic_graph(2500, 2500 * 30, seed=5).to("cuda")
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(2500, 602, device="cuda", generator=gen)
+    y = torch.randint(0, 41, (2500,), device="cuda", generator=gen)
+    torch.manual_seed(11)
+    model = models.MaxKSAGE(602, 256, 3, 41, maxk=32, feat_drop=0.0, norm=True).cuda()
+    res = {}
+    for on in (False, True):
+        models.set_align_gemm(on)
+        model.zero_grad()
+        logits = model(g, models.pad_features(x) if on else x)
+        F.cross_entropy(logits, y).backward()
+        res[on] = (logits.detach().clone(), [p.grad.clone() for p in model.parameters()])
+    models.set_align_gemm(False)
+    assert res[True][0].shape == res[False][0].shape == (2500, 41)
+    scale = float(res[False][0].abs().max())
+    assert float((res[True][0] - res[False][0]).abs().max()) <= 2e-5 * scale
+    for a, b in zip(res[True][1], res[False][1]):
+        assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max()) + 1e-9
 
 
 def test_fifty_epoch_loss_curve_on_the_flickr_shape():
