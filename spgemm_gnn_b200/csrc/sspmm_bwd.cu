@@ -22,8 +22,10 @@
 
 // Records per CTA of the plain backward (measurement knob, VERDICT r1 "occupancy ceiling": one 32-thread
 // CTA per record caps residency at 32 CTAs = 32 warps per SM).  W warps per CTA, one record each, lift
-// the cap to 64 warps.  Measured on a B200 (profiles/r2/bwd_warps_per_cta.log): no gain -- the kernel is
-// bound by the SM->L2 request path (93 %), not by latency; the default stays 1.
+// the cap to 64 warps.  Measured on a B200 (profiles/r2/bwd_warps_per_cta_call17.log): SLOWER -- Reddit shape
+// k = 32: 2.559 ms at 1, 2.862 at 2, 2.867 at 4 warps per CTA; k = 64: 4.744 / 5.276 / 5.291; products shape
+// (plain kernel) 6.46 -> 7.27 ms.  The kernel is bound by the SM->L2 request path (93 %), not by latency;
+// more warps in flight only add contention for it.  The default stays 1.
 #ifndef MK_BWD_WARPS
 #define MK_BWD_WARPS 1
 #endif
