@@ -33,10 +33,11 @@ extern "C" {
 #define MK_API __attribute__((visibility("default")))
 #endif
 
-#define MK_VERSION 201 /* major*100 + minor; 2.00: overlapped copy-engine all-gather (mk_peer_push & co. replace
+#define MK_VERSION 202 /* major*100 + minor; 2.00: overlapped copy-engine all-gather (mk_peer_push & co. replace
                           * mk_peer_allgather / mk_peer_bank_push), mk_spgemm_fwd_banked_ex, soft peer time-outs;
                           * 2.01: mk_topk_cbsr_bank, mk_spgemm_fwd_banked_phase, mk_spgemm_fwd_banked_ln,
-                          * mk_sspmm_bwd_tiled, packed tables.  Experimental entry points -- measured dead ends
+                          * mk_sspmm_bwd_tiled, packed tables; 2.02: NVLink multicast forms mk_peer_push_mc /
+                          * mk_peer_reduce_scatter_mc.  Experimental entry points -- measured dead ends
                           * kept as the record of the experiment, off in every product path, free to go in 3.x:
                           * mk_sspmm_bwd_tma, mk_sspmm_bwd_banked, mk_spgemm_fwd_banked_phase, mk_topk_cbsr_bank. */
 
@@ -361,6 +362,20 @@ MK_API int mk_peer_release(void* const* h_windows, int world, int rank, void* st
 MK_API int mk_peer_reduce_scatter(void* const* h_windows, int world, int rank, int64_t offset,
                                   int64_t block_bytes, float* out, int grid, int timeout_ms,
                                   void* stream);
+/* NVLink multicast (NVLS) forms of the two exchanges, for windows that are symmetric memory bound to a
+ * multicast object (peer.py allocates them through torch's symmetric-memory allocator): `mc_window` is
+ * the multicast address of the window -- a store to it lands at the same offset of every rank's
+ * window, a multimem.ld_reduce from it returns the sum over all of them.
+ *   mk_peer_push_mc            the all-gather of mk_peer_push_sm with every row sent ONCE (after
+ *                              mk_peer_publish; raises done[rank] in every peer's header at the end);
+ *   mk_peer_reduce_scatter_mc  mk_peer_reduce_scatter with the sum formed by the switch (one reduced
+ *                              16-byte load per element instead of `world` loads; the order of the sum
+ *                              is the switch's, as with NCCL).                                        */
+MK_API int mk_peer_push_mc(void* const* h_windows, void* mc_window, int world, int rank, int n_seg,
+                           const int64_t* h_offsets, const int64_t* h_bytes, int grid, void* stream);
+MK_API int mk_peer_reduce_scatter_mc(void* const* h_windows, const void* mc_window, int world, int rank,
+                                     int64_t offset, int64_t block_bytes, float* out, int grid,
+                                     int timeout_ms, void* stream);
 MK_API int mk_peer_reduce_scatter_virtual(void* const* h_windows, int world, int64_t offset,
                                           int64_t block_bytes, float* const* h_outs, int grid,
                                           int timeout_ms, void* stream);

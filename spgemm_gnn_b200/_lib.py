@@ -67,6 +67,9 @@ SIGNATURES = {
     "mk_peer_wait_all": (_i32, [_vp, _i32, _i32, _vp]),
     "mk_peer_release": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _vp]),
     "mk_peer_reduce_scatter": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _i64, _i64, _vp, _i32, _i32, _vp]),
+    "mk_peer_push_mc": (_i32, [ctypes.POINTER(_vp), _vp, _i32, _i32, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i64),
+                               _i32, _vp]),
+    "mk_peer_reduce_scatter_mc": (_i32, [ctypes.POINTER(_vp), _vp, _i32, _i32, _i64, _i64, _vp, _i32, _i32, _vp]),
     "mk_peer_reduce_scatter_virtual": (_i32, [ctypes.POINTER(_vp), _i32, _i64, _i64, ctypes.POINTER(_vp), _i32, _i32, _vp]),
 }
 

@@ -123,6 +123,84 @@ peer_reduce_scatter_kernel(const PeerSet ps, const int world_rt, const int rank_
     peer_end(ps, world, c, e, timeout_ns);
 }
 
+// ---- NVLink multicast (NVLS) forms ----------------------------------------------------------------
+// With the windows allocated as symmetric memory bound to a multicast object (peer.py: torch's
+// symmetric-memory allocator does the driver plumbing), one address reaches the same offset of EVERY
+// rank's window: a store to it is replicated by the NVSwitch, a `multimem.ld_reduce` is summed by it.
+// The all-gather then sends every row once instead of P-1 times, the reduce-scatter receives one
+// reduced row instead of P.
+__device__ __forceinline__ void mc_store_16(void* p, uint4 v) {  // SASS: STG.E.128.STRONG.SYS on the multicast VA
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+}
+__device__ __forceinline__ float4 mc_load_reduce_f4(const float* p) {  // SASS: LDGMC.E.ADD.F32x4
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p)
+                 : "memory");
+    return r;
+}
+
+// All-gather through the multicast address: the rank's rows of every segment are stored ONCE, the
+// switch delivers them to all windows (the own one included: same bytes).  The block that finishes
+// last raises done[rank] = epoch in every peer's header with ordinary release stores.
+__global__ void __launch_bounds__(256)
+peer_push_mc_kernel(const PushDesc pd, unsigned char* __restrict__ mc) {
+    uint32_t* hdr = peer_hdr(pd.ps, pd.rank);
+    const uint32_t e = *reinterpret_cast<volatile uint32_t*>(hdr + kHdrEpoch);
+    const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int g = 0; g < pd.nseg; ++g) {
+        const int64_t base = pd.off[g] + pd.rank * pd.bytes[g];
+        const int64_t n16 = pd.bytes[g] >> 4;
+        const uint4* __restrict__ src = reinterpret_cast<const uint4*>(pd.ps.win[pd.rank] + base);
+        uint4* __restrict__ dst = reinterpret_cast<uint4*>(mc + base);
+        int64_t i = tid;
+        for (; i + 3 * nthr < n16; i += 4 * nthr) {  // four loads in flight per thread
+            const uint4 a = ld_cg_16(src + i), b = ld_cg_16(src + i + nthr);
+            const uint4 c = ld_cg_16(src + i + 2 * nthr), d = ld_cg_16(src + i + 3 * nthr);
+            mc_store_16(dst + i, a);
+            mc_store_16(dst + i + nthr, b);
+            mc_store_16(dst + i + 2 * nthr, c);
+            mc_store_16(dst + i + 3 * nthr, d);
+        }
+        for (; i < n16; i += nthr) mc_store_16(dst + i, ld_cg_16(src + i));
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        const uint32_t t = atomicAdd(hdr + kHdrStep + 1, 1u);
+        s_last = (t == gridDim.x - 1u) ? 1 : 0;
+        if (s_last) hdr[kHdrStep + 1] = 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();  // the other blocks' stores (fenced before their tickets) first
+    if (threadIdx.x < pd.world && static_cast<int>(threadIdx.x) != pd.rank)
+        st_release_sys(peer_hdr(pd.ps, threadIdx.x) + kHdrDone + pd.rank, e);
+}
+
+// out[i] = sum over all ranks of window_q[off + rank*n4 + i], summed by the switch.
+__global__ void __launch_bounds__(256)
+peer_reduce_scatter_mc_kernel(const PeerSet ps, const int world, const int rank, const unsigned char* __restrict__ mc,
+                              const int64_t off, const int64_t n4, float4* __restrict__ out,
+                              const uint64_t timeout_ns) {
+    PeerCtx c;
+    c.rank = rank;
+    c.bid = static_cast<int>(blockIdx.x);
+    c.nblk = static_cast<int>(gridDim.x);
+    const uint32_t e = peer_begin(ps, world, c);
+    peer_wait_all_ready(ps, world, c, e, timeout_ns);
+    const float* __restrict__ src = reinterpret_cast<const float*>(mc + off) + 4 * (rank * n4);
+    const int64_t tid = static_cast<int64_t>(c.bid) * blockDim.x + threadIdx.x;
+    const int64_t nthr = static_cast<int64_t>(c.nblk) * blockDim.x;
+    for (int64_t i = tid; i < n4; i += nthr) out[i] = mc_load_reduce_f4(src + 4 * i);
+    peer_end(ps, world, c, e, timeout_ns);
+}
+
 static int fill_peers(PeerSet& ps, void* const* h_windows, int world, int rank) {
     if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !h_windows) return MK_EINVAL;
     memset(&ps, 0, sizeof(ps));
@@ -342,4 +420,58 @@ extern "C" int mk_peer_reduce_scatter_virtual(void* const* h_windows, int world,
                                               int64_t block_bytes, float* const* h_outs, int grid,
                                               int timeout_ms, void* stream) {
     return mk::reduce_scatter_any(h_windows, world, 0, 1, offset, block_bytes, h_outs, grid, timeout_ms, stream);
+}
+
+extern "C" int mk_peer_push_mc(void* const* h_windows, void* mc_window, int world, int rank, int n_seg,
+                               const int64_t* h_offsets, const int64_t* h_bytes, int grid, void* stream) {
+    mk::PeerSet ps;
+    const int rc = mk::fill_peers(ps, h_windows, world, rank);
+    if (rc != MK_OK) return rc;
+    if (!mc_window || (reinterpret_cast<uintptr_t>(mc_window) & 15)) return MK_EINVAL;
+    if (n_seg < 1 || n_seg > 3 || !h_offsets || !h_bytes) return MK_EINVAL;
+    mk::PushDesc pd{};
+    pd.ps = ps;
+    pd.world = world;
+    pd.rank = rank;
+    pd.nseg = n_seg;
+    int64_t total16 = 0;
+    for (int g = 0; g < n_seg; ++g) {
+        if (h_bytes[g] < 0 || (h_bytes[g] & 15) || h_offsets[g] < MK_PEER_HEADER_BYTES || (h_offsets[g] & 15))
+            return MK_EINVAL;
+        pd.off[g] = h_offsets[g];
+        pd.bytes[g] = h_bytes[g];
+        total16 += h_bytes[g] >> 4;
+    }
+    if (world == 1) return MK_OK;
+    int want = grid > 0 ? grid : 296;  // 2 CTAs per SM saturate the NVLink stores
+    const int64_t need = (total16 + 255) / 256;
+    if (need < want) want = static_cast<int>(need > 0 ? need : 1);
+    mk::peer_push_mc_kernel<<<static_cast<unsigned>(want), 256, 0, mk::as_stream(stream)>>>(
+        pd, static_cast<unsigned char*>(mc_window));
+    MK_LAUNCH_CHECK("peer_push_mc_kernel");
+    return MK_OK;
+}
+
+extern "C" int mk_peer_reduce_scatter_mc(void* const* h_windows, const void* mc_window, int world, int rank,
+                                         int64_t offset, int64_t block_bytes, float* out, int grid,
+                                         int timeout_ms, void* stream) {
+    mk::PeerSet ps;
+    const int rc = mk::fill_peers(ps, h_windows, world, rank);
+    if (rc != MK_OK) return rc;
+    if (!mc_window || (reinterpret_cast<uintptr_t>(mc_window) & 15)) return MK_EINVAL;
+    if (offset < MK_PEER_HEADER_BYTES || (offset & 15) || block_bytes < 0 || (block_bytes & 15)) return MK_EINVAL;
+    if (block_bytes > 0 && (!out || (reinterpret_cast<uintptr_t>(out) & 15))) return MK_EINVAL;
+    const int64_t n4 = block_bytes / 16;
+    const uint64_t tmo = static_cast<uint64_t>(timeout_ms > 0 ? timeout_ms : 30000) * 1000000ull;
+    // every block may wait for a flag that block 0 of a peer's grid writes: the grid must be resident
+    int cap = mk::coresident_blocks(mk::peer_reduce_scatter_mc_kernel, 256, 0);
+    if (cap < 1) return MK_EUNSUPPORTED;
+    int64_t want = grid > 0 ? grid : (n4 + 255) / 256;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    mk::peer_reduce_scatter_mc_kernel<<<static_cast<unsigned>(want), 256, 0, mk::as_stream(stream)>>>(
+        ps, world, rank, static_cast<const unsigned char*>(mc_window), offset, n4, reinterpret_cast<float4*>(out),
+        tmo);
+    MK_LAUNCH_CHECK("peer_reduce_scatter_mc_kernel");
+    return MK_OK;
 }

@@ -222,7 +222,8 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
         if blk is not None:
             phases = maxk_kernels.forward_phases(world, rank)
     pkw = dict(phases=phases, blk=blk, n_blocks=world) if phases is not None else dict(split=split)
-    if _peer_path(group, r * k * 4) and peer.wanted(world, world * r * k * (6 + ib if form == "banked" else 4 + ib)):
+    if _peer_path(group, r * k * 4) and peer.wanted(world, world * r * k * (6 + ib if form == "banked" else 4 + ib),
+                                                   group):
         rows = world * r
         per_rank = {"banked": [r * k * 4, r * k * 2, r * k * ib], "packed": [r * k * 8, r * k * ib],
                     "plain": [r * k * 4, r * k * ib]}[form]
@@ -234,9 +235,13 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
             mine = slice(rank * r, (rank + 1) * r)
             # who moves the rows: pusher CTAs inside the forward kernel ("sm": needs 16-byte multiples),
             # or the copy engines on side streams ("dma"), with or without per-block waiting
-            fused = (form != "plain" and peer.push_mode() == "sm" and all(b % 16 == 0 for b in per_rank))
+            aligned = all(b % 16 == 0 for b in per_rank)
+            mcast = bool(win.mc) and peer._MULTICAST and aligned and world > 1   # every row stored once (NVLS)
+            fused = (not mcast and form != "plain" and peer.push_mode() == "sm" and aligned)
             wait = None
-            if fused:
+            if mcast:
+                pass
+            elif fused:
                 wait = peer.exchange(win, r, o, per_rank)
             elif peer.overlap() and form != "plain":
                 wait = peer.exchange(win, r)
@@ -254,7 +259,11 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
             else:
                 full_data = win.view(o[0], (rows, k), torch.float32)
                 full_data[mine].copy_(sp_data)
-            if fused:
+            if mcast:
+                peer.publish(win, buf)
+                peer.push_mc(win, o, per_rank)
+                peer.wait_all(win)
+            elif fused:
                 peer.publish(win, buf)
             elif peer.push_mode() == "sm" and all(b % 16 == 0 for b in per_rank):
                 peer.publish(win, buf)           # un-banked table: the same stores as a kernel of its own
@@ -304,7 +313,7 @@ def sharded_backward(grad_out, full_index, ptr, idx, val, num_rows, dim_origin, 
     n_src, k = full_index.shape
     world = dist.get_world_size(group)
     r = n_src // world
-    if _peer_path(group, r * k * 4) and peer.wanted(world, n_src * k * 4):
+    if _peer_path(group, r * k * 4) and peer.wanted(world, n_src * k * 4, group):
         offs, total = peer.layout([n_src * k * 4])
         win = peer.window("dxs", total, group)
         if win is not None:

@@ -69,6 +69,12 @@ _PHASES = os.environ.get("MAXK_PEER_PHASES", "0") != "0"
 # 52 MB table: 1.014 against 0.953 ms per layer; products shape 2.75 against 2.68 ms -- NCCL's NVLS
 # all-gather sends every row once, the push sends it seven times).  MAXK_PEER_MAX_MB=0: no limit.
 _MAX_BYTES = int(os.environ.get("MAXK_PEER_MAX_MB", "32")) << 20
+# NVLink multicast (NVLS): windows allocated as symmetric memory bound to a multicast object (torch's
+# symmetric-memory allocator does the driver plumbing: cuMemCreate, handle exchange, cuMulticastBindMem).
+# The all-gather then stores every row once (mk_peer_push_mc), the reduce-scatter loads one row reduced
+# by the switch (mk_peer_reduce_scatter_mc).  "1": use it where the box offers it, fall back to CUDA-IPC
+# windows otherwise; "0": CUDA-IPC windows only.
+_MULTICAST = os.environ.get("MAXK_PEER_MULTICAST", "1") != "0"
 _launches = 0
 
 
@@ -97,10 +103,40 @@ def overlap() -> bool:
     return _OVERLAP
 
 
-def wanted(world: int, exchange_bytes: int) -> bool:
+_mc_state = {"probed": False, "ok": False}
+
+
+def set_multicast(on: bool) -> bool:
+    """Use the multicast forms of the exchanges where the windows have a multicast address (returns the
+    previous setting).  Windows that exist stay what they are; only the kernels change."""
+    global _MULTICAST
+    was, _MULTICAST = _MULTICAST, bool(on)
+    return was
+
+
+def multicast(group=None) -> bool:
+    """Do the windows of this process group come with a multicast address?  Probed once with a small
+    symmetric allocation (a collective: every rank calls it at the same point) and agreed on by all ranks."""
+    if not (_MULTICAST and available(group)):
+        return False
+    if not _mc_state["probed"]:
+        _mc_state["probed"] = True
+        w = PeerWindow._create_symm(1 << 20, group, None)
+        _mc_state["ok"] = w is not None and w.mc != 0
+        if w is not None:
+            w.close()
+    return _mc_state["ok"]
+
+
+def wanted(world: int, exchange_bytes: int, group=None) -> bool:
     """Peer kernels or NCCL for an exchange of `exchange_bytes` (whole table / whole gradient) over
-    `world` ranks -- same answer on every rank (same shapes)."""
-    return _ENABLED and (_MAX_BYTES == 0 or world < 8 or exchange_bytes <= _MAX_BYTES)
+    `world` ranks -- same answer on every rank (same shapes).  With multicast windows the own kernels
+    move no more bytes than NCCL's NVLS collectives, so the size limit only applies without them."""
+    if not _ENABLED:
+        return False
+    if _MAX_BYTES == 0 or world < 8 or exchange_bytes <= _MAX_BYTES:
+        return True
+    return multicast(group)
 
 
 def set_max_mb(mb: int) -> int:
@@ -137,6 +173,19 @@ def push_sm(win: "PeerWindow", offsets: Sequence[int], bytes_per_rank: Sequence[
     with torch.cuda.device(win.device):
         rc = _lib.lib().mk_peer_push_sm(win.ptrs, win.world, win.rank, n, offs, nbytes, _PUSHERS, _stream())
     _lib.check(rc, "mk_peer_push_sm")
+    _launches += 1
+
+
+def push_mc(win: "PeerWindow", offsets: Sequence[int], bytes_per_rank: Sequence[int]) -> None:
+    """The all-gather through the window's multicast address: every row stored once, the switch
+    replicates it (after `publish`, current stream)."""
+    global _launches
+    n = len(offsets)
+    offs = (ctypes.c_int64 * n)(*[int(o) for o in offsets])
+    nbytes = (ctypes.c_int64 * n)(*[int(b) for b in bytes_per_rank])
+    with torch.cuda.device(win.device):
+        rc = _lib.lib().mk_peer_push_mc(win.ptrs, win.mc, win.world, win.rank, n, offs, nbytes, 0, _stream())
+    _lib.check(rc, "mk_peer_push_mc")
     _launches += 1
 
 
@@ -189,6 +238,8 @@ class PeerWindow:
         self._side = None          # stream of the copy-engine pushes
         self._pushed = None        # event behind the last push
         self._buf = 1              # table buffer of the last forward (alternates 0, 1, 0, ...)
+        self.mc = 0                # multicast address of the window (symmetric-memory windows), 0 = none
+        self._symm = None          # (tensor, handle) that own a symmetric-memory window
 
     # ---- construction -------------------------------------------------------------------
     @classmethod
@@ -206,10 +257,45 @@ class PeerWindow:
         return w
 
     @classmethod
+    def _create_symm(cls, nbytes: int, group, device) -> Optional["PeerWindow"]:
+        """Window in symmetric memory (torch.distributed._symmetric_memory): every peer's copy mapped
+        here plus, on NVSwitch boxes, one multicast address for all of them.  Collective; None on every
+        rank if any rank fails."""
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        w, why = None, ""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty(int(nbytes), dtype=torch.uint8, device=device)
+            h = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+            t.zero_()
+            w = cls(nbytes, world, rank, device)
+            ptrs = list(h.buffer_ptrs)
+            w.local = int(ptrs[rank])
+            for q in range(world):
+                w.ptrs[q] = int(ptrs[q])
+            w.mc = int(h.multicast_ptr or 0)
+            w._symm = (t, h)
+        except Exception as exc:  # noqa: BLE001 -- agreed on below
+            w, why = None, f"rank {rank}: {type(exc).__name__}: {exc}"
+        flag = torch.tensor([1 if w is not None else 0], device=device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)   # also: every rank's header is zero
+        if int(flag.item()) == 0:
+            if w is not None:
+                w.close()
+            return None
+        return w
+
+    @classmethod
     def create(cls, nbytes: int, group=None, device=None) -> Optional["PeerWindow"]:
         """Collective over `group`: allocate, export, exchange handles, map every peer.  A failure
         on any rank (no IPC in this sandbox, out of memory, ...) is agreed on by all ranks, which
-        then all return None -- nobody is left waiting in a collective."""
+        then all return None -- nobody is left waiting in a collective.  Symmetric memory with a
+        multicast address first (where the box has it), CUDA-IPC windows otherwise."""
+        if _MULTICAST and _mc_state.get("ok", False):
+            w = cls._create_symm(nbytes, group, device)
+            if w is not None:
+                return w
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if world > MAX_RANKS:
             raise RuntimeError(f"peer windows support at most {MAX_RANKS} ranks")
@@ -298,6 +384,12 @@ class PeerWindow:
         return int(e.value), int(err.value)
 
     def close(self) -> None:
+        if self._symm is not None:     # symmetric memory: torch owns it
+            self._bytes = None
+            self._symm = None
+            self.local = None
+            self.mc = 0
+            return
         L = _lib.lib()
         with torch.cuda.device(self.device):
             for p in self.opened:
@@ -325,6 +417,7 @@ def window(kind: str, nbytes: int, group=None) -> Optional[PeerWindow]:
     if w is None:
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("peer windows must exist before CUDA graph capture (run one eager step first)")
+        multicast(group)          # one collective probe per process: symmetric memory + multicast or CUDA IPC
         w = PeerWindow.create(nbytes, group)
         if w is None:
             set_enabled(False)
@@ -427,8 +520,12 @@ def reduce_scatter(win: PeerWindow, offset: int, rows: int, k: int, grid: int = 
         raise RuntimeError("peer reduce-scatter blocks must be multiples of 16 bytes")
     out = torch.empty((rows, k), dtype=torch.float32, device=win.device)
     with torch.cuda.device(win.device):
-        rc = _lib.lib().mk_peer_reduce_scatter(win.ptrs, win.world, win.rank, int(offset), block,
-                                               out.data_ptr(), grid, _TIMEOUT_MS, _stream())
+        if win.mc and _MULTICAST:    # summed by the switch: one reduced load per element
+            rc = _lib.lib().mk_peer_reduce_scatter_mc(win.ptrs, win.mc, win.world, win.rank, int(offset), block,
+                                                      out.data_ptr(), grid, _TIMEOUT_MS, _stream())
+        else:
+            rc = _lib.lib().mk_peer_reduce_scatter(win.ptrs, win.world, win.rank, int(offset), block,
+                                                   out.data_ptr(), grid, _TIMEOUT_MS, _stream())
     _lib.check(rc, "mk_peer_reduce_scatter")
     _launches += 1
     return out

@@ -38,7 +38,7 @@ def test_header_is_plain_c_and_links(built_lib, tmp_path):
                            os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe,
                            "-L", libdir, "-lmaxk_b200", "-Wl,-rpath," + libdir])
     out = subprocess.check_output([exe]).decode()
-    assert "c abi ok: version 201" in out
+    assert "c abi ok: version 202" in out
 
 
 def test_library_is_sm100a_and_has_no_torch_dependency(built_lib):
@@ -51,7 +51,7 @@ def test_library_is_sm100a_and_has_no_torch_dependency(built_lib):
 
 def test_version_and_error_strings(built_lib):
     L = _lib.lib()
-    assert L.mk_version() == 201
+    assert L.mk_version() == 202
     assert L.mk_error_string(0) == b"ok"
     assert L.mk_error_string(-1) == b"invalid argument"
     assert b"CUDA" in L.mk_error_string(-3)
