@@ -323,8 +323,10 @@ def parity_record(mk, mdist, g, rank, world, ptr, idx, val, val_full, x_local, d
                          "and against each other" if was else ""))
     rec["exchange"] = {"forward": "peer windows" if (was and fwd_peer) else "NCCL",
                        "backward": "peer windows" if (was and bwd_peer) else "NCCL",
-                       "rule": "own NVLink kernels unless the group has >= 8 ranks and the table / gradient exceeds "
-                               "MAXK_PEER_MAX_MB (32): measured faster there (profiles/r2/peer_phases8_call13.log)"}
+                       "multicast": bool(was and mpeer.multicast()),
+                       "rule": "own NVLink kernels; through the NVSwitch multicast address where the box has one (every "
+                               "row stored once, reduce-scatter summed by the switch); without multicast, groups of >= 8 "
+                               "ranks use NCCL above MAXK_PEER_MAX_MB (32)"}
     return rec
 
 
