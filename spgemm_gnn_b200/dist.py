@@ -236,14 +236,14 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
             # who moves the rows: pusher CTAs inside the forward kernel ("sm": needs 16-byte multiples),
             # or the copy engines on side streams ("dma"), with or without per-block waiting
             aligned = all(b % 16 == 0 for b in per_rank)
-            mcast = bool(win.mc) and peer._MULTICAST and aligned and world > 1   # every row stored once (NVLS)
+            mcast = aligned and world > 1 and peer.use_multicast(win)          # every row stored once (NVLS)
             fused = (not mcast and form != "plain" and peer.push_mode() == "sm" and aligned)
             wait = None
             if mcast:
                 pass
             elif fused:
                 wait = peer.exchange(win, r, o, per_rank)
-            elif peer.overlap() and form != "plain":
+            elif peer.overlap() and form != "plain" and peer.push_mode() == "dma":
                 wait = peer.exchange(win, r)
             peer.begin_push(win, buf)
             full_index = win.view(o[-1], (rows, k), sp_index.dtype)
@@ -265,8 +265,8 @@ def sharded_forward(sp_data, sp_index, ptr, idx, val, num_rows, dim_origin, grou
                 peer.wait_all(win)
             elif fused:
                 peer.publish(win, buf)
-            elif peer.push_mode() == "sm" and all(b % 16 == 0 for b in per_rank):
-                peer.publish(win, buf)           # un-banked table: the same stores as a kernel of its own
+            elif peer.push_mode() in ("sm", "sm_seq", "auto", "mc") and aligned:
+                peer.publish(win, buf)           # NVLink stores to every peer as a kernel of its own
                 peer.push_sm(win, o, per_rank)
                 peer.wait_all(win)
             else:

@@ -51,10 +51,15 @@ _PUSH_STREAMS = max(1, int(os.environ.get("MAXK_PEER_STREAMS", "2")))
 # 1: the forward SpGEMM starts with the pushes and waits per source block; 0: it starts when the whole
 # table has arrived (mk_peer_wait_all)
 _OVERLAP = os.environ.get("MAXK_PEER_OVERLAP", "1") != "0"
-# who moves the rows to the peers: "sm" = pusher CTAs inside the forward SpGEMM kernel (default; NVLink
-# stores, progressive arrival), "dma" = copy engines on side streams (measured slower: small transfers
-# pay ~4 us each and concurrent flows interfere -- profiles/r2/push_probe_call6.log, exchange_forms8_call7.log)
-_PUSH = os.environ.get("MAXK_PEER_PUSH", "sm")
+# who moves the rows to the peers:
+#   "auto"   (default) through the window's multicast address where there is one and more than two ranks
+#            (mk_peer_push_mc: every row stored once, then the forward on the complete table), else "sm_seq";
+#   "sm_seq" NVLink stores to every peer as a kernel of its own, then the forward on the complete table;
+#   "sm"     pusher CTAs inside the forward SpGEMM kernel (progressive arrival, per-block waiting);
+#   "dma"    copy engines on side streams (small transfers pay ~4 us each and concurrent flows interfere).
+# Measured at 8 GPUs (profiles/r2/peer_mc8_call20.log, ms per layer, Reddit shape / 20 k-node graph):
+# multicast 0.930 / 0.245, NCCL 0.953 / 0.65, "sm" 1.012 / 0.303, "dma" 1.025 / 0.326.
+_PUSH = os.environ.get("MAXK_PEER_PUSH", "auto")
 _PUSHERS = int(os.environ.get("MAXK_PEER_PUSHERS", "592"))   # pusher CTAs (32 threads each)
 # forward cut into source-block phases (own block, the next senders, the rest: one launch each), so
 # that whole launches overlap the transfer instead of the CTAs that happen to be resident.  Measured at
@@ -153,6 +158,12 @@ def phases() -> bool:
 
 def push_mode() -> str:
     return _PUSH if _OVERLAP else "dma"
+
+
+def use_multicast(win: "PeerWindow") -> bool:
+    """The multicast all-gather for this window?  Needs a multicast address; with two ranks there is
+    nothing to replicate and the plain NVLink stores are faster (profiles/r2/peer_mc2_call19.log)."""
+    return bool(win.mc) and _MULTICAST and _PUSH in ("auto", "mc") and (win.world > 2 or _PUSH == "mc")
 
 
 def publish(win: "PeerWindow", buf: int) -> None:

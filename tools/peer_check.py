@@ -209,20 +209,18 @@ def distributed(bench: bool) -> int:
             # who moves the rows / how many pusher CTAs, forward and backward timed on their own
             fi0 = res[True][1]
             lim = peer.set_max_mb(0)          # the peer forms at every size
-            for push, pushers, ph in (("nccl", 0, 0), ("mc", 0, 0), ("sm", 592, 0), ("dma", 0, 0), ("mc", 0, 0),
-                                      ("nccl", 0, 0)):
+            for push, pushers, ph in (("nccl", 0, 0), ("mc", 0, 0), ("sm_seq", 592, 0), ("sm", 592, 0), ("dma", 0, 0),
+                                      ("auto", 0, 0), ("nccl", 0, 0)):
                 peer.set_enabled(push != "nccl")
                 peer._PHASES = bool(ph)
-                peer.set_multicast(push == "mc")
-                if push in ("sm", "dma"):
+                if push != "nccl":
                     peer._PUSH, peer._PUSHERS = push, pushers or peer._PUSHERS
                 tf = timed(lambda: mdist.sharded_forward(sd, si, ptr, idx, val, n_rows, d))
                 tb = timed(lambda: mdist.sharded_backward(dy, fi0, ptr, idx, val, n_rows, d))
                 ts = timed(step)
                 if rank == 0:
                     print(f"  {name} [{push} {pushers} phases={ph}]: fwd {tf:.3f}  bwd {tb:.3f}  fwd+bwd {ts:.3f} ms", flush=True)
-            peer._PUSH, peer._PUSHERS, peer._PHASES = "sm", 592, False
-            peer.set_multicast(True)
+            peer._PUSH, peer._PUSHERS, peer._PHASES = "auto", 592, False
             peer.set_max_mb(lim)
             peer.set_enabled(True)
         o0, f0, b0 = res[False]
