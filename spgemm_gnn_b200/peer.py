@@ -122,7 +122,7 @@ def set_multicast(on: bool) -> bool:
 def multicast(group=None) -> bool:
     """Do the windows of this process group come with a multicast address?  Probed once with a small
     symmetric allocation (a collective: every rank calls it at the same point) and agreed on by all ranks."""
-    if not (_MULTICAST and available(group)):
+    if not (_MULTICAST and available(group)) or dist.get_world_size(group) < 2:
         return False
     if not _mc_state["probed"]:
         _mc_state["probed"] = True
@@ -531,7 +531,7 @@ def reduce_scatter(win: PeerWindow, offset: int, rows: int, k: int, grid: int = 
         raise RuntimeError("peer reduce-scatter blocks must be multiples of 16 bytes")
     out = torch.empty((rows, k), dtype=torch.float32, device=win.device)
     with torch.cuda.device(win.device):
-        if win.mc and _MULTICAST and win.world > 2:    # summed by the switch: one reduced load per element
+        if win.mc and _MULTICAST and (win.world > 2 or _PUSH == "mc"):   # summed by the switch: one reduced load per element
             # (two ranks: one remote load per element either way, and the plain loads measured 3 % faster)
             rc = _lib.lib().mk_peer_reduce_scatter_mc(win.ptrs, win.mc, win.world, win.rank, int(offset), block,
                                                       out.data_ptr(), grid, _TIMEOUT_MS, _stream())

@@ -20,8 +20,8 @@ def _free_port() -> str:
         return str(s.getsockname()[1])
 
 
-def _run(cmd, timeout=600):
-    env = dict(os.environ, MAXK_PEER_TIMEOUT_MS="20000")
+def _run(cmd, timeout=600, **extra_env):
+    env = dict(os.environ, MAXK_PEER_TIMEOUT_MS="20000", **extra_env)
     p = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                        timeout=timeout)
     out = p.stdout.decode()
@@ -50,4 +50,15 @@ def test_sharded_path_through_peer_windows_world1(built_lib):
 def test_sharded_path_through_peer_windows_two_gpus(built_lib):
     out = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                 "--master-addr", "127.0.0.1", "--master-port", _free_port(), "tools/peer_check.py", "dist", "--stress"])
+    assert "dist peer check: OK" in out
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_multicast_forms_two_gpus(built_lib):
+    """The NVLink multicast forms (symmetric-memory windows, mk_peer_push_mc, mk_peer_reduce_scatter_mc) forced
+    at two ranks: forward bit-equal to the NCCL form, backward to summation order.  On a box without
+    multicast the windows fall back to CUDA IPC and the run checks the unicast forms again."""
+    out = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                "--master-addr", "127.0.0.1", "--master-port", _free_port(), "tools/peer_check.py", "dist", "--stress"],
+               MAXK_PEER_PUSH="mc")
     assert "dist peer check: OK" in out
