@@ -474,37 +474,45 @@ def flickr_record(mk, k, d, device):
     # the same iteration captured once in a CUDA graph and replayed, to separate launch overhead from GPU
     # time (measured: 7.83 ms replayed against 8.03 ms eager -- the iteration is bound by its dense fp32
     # GEMMs, 89,250 x 500 x 256 and 6 x 89,250 x 256 x 256 forward, twice that backward, not by launches)
-    gpu_graph_ms = None
+    gpu_graph_ms = gpu_graph_tf32_ms = None
+    tf32_was = torch.backends.cuda.matmul.allow_tf32
     try:
         def graph_iter():
             model.zero_grad(set_to_none=False)
             F.cross_entropy(model(g, feats), labels).backward()
 
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                graph_iter()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        cg = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(cg):
-            graph_iter()
-        for _ in range(3):
-            cg.replay()
-        torch.cuda.synchronize()
-        tg = []
-        for _ in range(10):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            cg.replay()
-            b.record()
+        def graphed_ms():
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    graph_iter()
+            torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            tg.append(a.elapsed_time(b))
-        gpu_graph_ms = statistics.median(tg)
-        del cg
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                graph_iter()
+            for _ in range(3):
+                cg.replay()
+            torch.cuda.synchronize()
+            tg = []
+            for _ in range(10):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                cg.replay()
+                b.record()
+                torch.cuda.synchronize()
+                tg.append(a.elapsed_time(b))
+            del cg
+            return statistics.median(tg)
+
+        gpu_graph_ms = graphed_ms()
+        torch.backends.cuda.matmul.allow_tf32 = True     # what the reference sets on its GPU (maxk_gnn_dgl.py:30)
+        gpu_graph_tf32_ms = graphed_ms()
     except Exception as exc:  # noqa: BLE001 -- the eager figure stands
         sys.stderr.write(f"flickr record: CUDA-graph timing skipped ({type(exc).__name__}: {exc})\n")
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32_was
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -530,9 +538,11 @@ def flickr_record(mk, k, d, device):
     return {"graph": f"flickr-shaped synthetic graph, {n} nodes, {e} stored entries",
             "model": f"MaxK-SAGE 3x{d}, k={k}, in {in_feats}, classes {classes}, LayerNorm, no dropout, forward+backward",
             "gpu_ms_per_iter": gpu_ms, "gpu_graph_ms_per_iter": gpu_graph_ms,
+            "gpu_graph_tf32_ms_per_iter": gpu_graph_tf32_ms,
             "gpu_note": "fp32 GEMMs (TF32 off, like the CPU arm); gpu_ms_per_iter: eager launches; "
                         "gpu_graph_ms_per_iter: the same iteration replayed from one CUDA graph (equal: the "
-                        "iteration is bound by the dense GEMMs, not by launches)",
+                        "iteration is bound by the dense GEMMs, not by launches); gpu_graph_tf32_ms_per_iter: "
+                        "with TF32 GEMMs, as the reference sets them on its GPU (maxk_gnn_dgl.py:30)",
             "cpu_ms_per_iter": cpu_ms, "cpu_cores": cores,
             "gpu_edges_per_s": 2.0 * layers * e / (gpu_ms * 1e-3),
             "cpu_edges_per_s": 2.0 * layers * e / (cpu_ms * 1e-3),
