@@ -75,9 +75,9 @@ def build(force: bool = False, verbose: bool = False, defs=(), out: str = None) 
                                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     failed = False
     for src, p in procs:
-        out = p.communicate()[0].decode()
+        log = p.communicate()[0].decode()
         if p.returncode != 0 or verbose:
-            sys.stderr.write(f"--- {src}\n{out}\n")
+            sys.stderr.write(f"--- {src}\n{log}\n")
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
