@@ -180,7 +180,7 @@ struct FwdPhase {
 // `split` (nullable): per CSR row, the position in idx of the first stored entry whose column is
 // >= rank*rows_per_rank.  A record then walks [split, end) first and [begin, split) second, i.e.
 // the source blocks in the order rank, rank+1, ..., world-1, 0, ..., rank-1 -- the order in which
-// mk_peer_bank_push makes them arrive.  The summation order of a row is fixed either way.
+// the pushes (peer.cu, push_rows) make them arrive.  The summation order of a row is fixed either way.
 template <int K, int U, bool WAIT, bool PACKED = false>
 __global__ void __launch_bounds__(32)
 spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,

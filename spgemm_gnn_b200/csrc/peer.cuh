@@ -18,11 +18,11 @@
 //      enqueued before the collective has completed (stream order), so its copy may be written
 //      (all-gather) / read (reduce-scatter) by the peers.
 //   2. A block waits for ready[q] >= e before it touches rank q's copy.
-//   3. COMPLETE form (mk_peer_allgather, mk_peer_reduce_scatter): after its part a block fences
+//   3. COMPLETE form (mk_peer_reduce_scatter, mk_peer_reduce_scatter_mc): after its part a block fences
 //      (system scope) and takes a ticket; the block that takes the last one stores done = e into
 //      every peer's header, waits for done[q] >= e from every peer, and publishes epoch = e.  When
 //      the kernel has finished, this rank's copy is complete / no longer read by anybody.
-//      PROGRESSIVE form (mk_peer_bank_push): the sender visits the destinations one after the other
+//      PROGRESSIVE form (push_rows: mk_peer_push_sm, pusher CTAs of the forward): the sender visits the destinations one after the other
 //      (rank, rank-1, rank-2, ...); the block that finishes step s last stores done = e into THAT
 //      destination's header, nobody waits for the peers, and the last block publishes epoch = e.
 //      The consumer (the forward SpGEMM, banked.cu) checks done[q] before it reads rank q's rows and
