@@ -466,7 +466,11 @@ static int launch_fwd_banked(const mk_part* parts, int64_t num_parts, const int*
 #else
     constexpr int U = K >= 64 ? 2 : (K == 32 ? 4 : 8);
 #endif
+#ifdef MK_FWD_EXTRA_SMEM   // measurement knob: what fewer resident CTAs (a third copy of the cells) would cost
+    const size_t smem = static_cast<size_t>(32) * rows * 4 + MK_FWD_EXTRA_SMEM;
+#else
     const size_t smem = static_cast<size_t>(32) * rows * 4;
+#endif
     if (fw.hdr != nullptr) {
         auto kern = spgemm_fwd_banked_kernel<K, U, true, PACKED>;
         if (smem > 48 * 1024)
