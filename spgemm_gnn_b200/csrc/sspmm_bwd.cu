@@ -408,7 +408,11 @@ static int launch_bwd_k(const mk_part* parts, int64_t num_parts, const int* idx,
     constexpr int U = (K / 4 >= 8) ? 8 : (K / 4);
 #endif
     const int dpad = (d + 3) & ~3;
+#ifdef MK_BWD_EXTRA_SMEM   // measurement knob: FEWER resident CTAs (the request path is the bound, not latency)
+    const size_t smem = static_cast<size_t>(dpad) * 4 * MK_BWD_WARPS + MK_BWD_EXTRA_SMEM;
+#else
     const size_t smem = static_cast<size_t>(dpad) * 4 * MK_BWD_WARPS;
+#endif
     if (smem > 200 * 1024) return MK_EUNSUPPORTED;
     auto kern = K <= 32 ? sspmm_bwd_kernel_occ32<K, IdxT, U> : sspmm_bwd_kernel<K, IdxT, U>;
     if (smem > 48 * 1024)
