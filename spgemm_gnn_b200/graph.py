@@ -134,6 +134,10 @@ class CSRGraph:
           `GraphConv(norm='both')`, used at `utils/models.py:252`).
         * `'right'`: deg_in(i)^-1 -- same numbers as `'mean'`.
         * `'sum'` / `'none'`: 1.0 (GIN, `utils/models.py:375`).
+        * `'reference_gcn'`: deg_out(j)^-1/2 * deg_in(j)^-1/2 -- BOTH normalisations on the source node,
+          which is what the reference's own `MaxKGCNConv` computes (`utils/maxk_layers.py:315-318`
+          scales the features by deg_out^-1/2, `:372-376` weights every edge with `norm_right[idx]` =
+          deg_in^-1/2 of the SOURCE), unlike the `GraphConv(norm='both')` it trains with.
         """
         w = self._cache.get(("w", kind))
         if w is not None:
@@ -148,6 +152,10 @@ class CSRGraph:
             di = self.in_degrees().clamp(min=1).to(torch.float32).pow(-0.5)
             do = self.out_degrees().clamp(min=1).to(torch.float32).pow(-0.5)
             w = di[self.row_ids()] * do[self.indices.to(torch.int64)]
+        elif kind == "reference_gcn":
+            di = self.in_degrees().clamp(min=1).to(torch.float32).pow(-0.5)
+            do = self.out_degrees().clamp(min=1).to(torch.float32).pow(-0.5)
+            w = (di * do)[self.indices.to(torch.int64)]
         else:
             raise ValueError(f"unknown edge weight kind {kind!r}")
         w = w.contiguous()

@@ -346,11 +346,18 @@ class MaxKSAGEConv(nn.Module):
 
 class MaxKGCNConv(nn.Module):
     """D_in^-1/2 A D_out^-1/2 MaxK(feat W) + b (utils/maxk_layers.py:300-324, 370-390); both
-    normalisations are folded into the per-edge weights once per graph."""
+    normalisations are folded into the per-edge weights once per graph.
+
+    `norm='both'` follows `dglnn.GraphConv(norm='both')` -- the layer the reference TRAINS with
+    (utils/models.py:252).  The reference's own MaxKGCNConv class puts both degree factors on the
+    source node instead (A D_out^-1/2 D_in^-1/2, utils/maxk_layers.py:315-318, 372-376);
+    `reference_norm=True` reproduces that class exactly (edge weights `'reference_gcn'`), for users who
+    need its numbers rather than GraphConv's."""
 
     def __init__(self, in_feats, out_feats, norm="both", weight=True, bias=True,
-                 allow_zero_in_degree=False, maxk=32):
+                 allow_zero_in_degree=False, maxk=32, reference_norm=False):
         super().__init__()
+        self.reference_norm = bool(reference_norm)
         if norm not in ("none", "both", "right"):
             raise ValueError(f"Unsupported norm: {norm}")
         self.in_feats = in_feats
@@ -389,7 +396,8 @@ class MaxKGCNConv(nn.Module):
                 raise ValueError("Graph has nodes with zero in-degree")
         if self.weight is not None:
             feat = torch.mm(feat, self.weight)
-        output = maxk_aggregate(graph, feat, self.maxk, self.norm)
+        kind = "reference_gcn" if (self.reference_norm and self.norm == "both") else self.norm
+        output = maxk_aggregate(graph, feat, self.maxk, kind)
         if self.bias is not None:
             output = output + self.bias
         return output

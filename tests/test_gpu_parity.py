@@ -451,6 +451,14 @@ def test_reference_layer_call_sites_through_the_cuda_path(mk, golden_layers):
         # the golden output is float32 from float64 sums: half an ulp of y on top of the kernel bar
         assert_rel(out + dev(np.broadcast_to(add, y.shape).astype(np.float32)), y.astype(np.float64),
                    bound + 0.01 * np.abs(y), name)
+        if name == "gcn_both":
+            # the reference's MaxKGCNConv as a whole (both degree factors on the source node): this repo's
+            # `reference_gcn` edge weights applied to the un-scaled MaxK output give the layer's output
+            g = CSRGraph(args[0], args[1])
+            do = g.out_degrees().clamp(min=1).float().pow(0.5)            # undo the feature scaling of :315-318
+            raw = (args[3] * do[:, None]).contiguous()
+            agg = aggregate_cbsr(g, raw, args[4], "reference_gcn", c["d"])
+            assert torch.allclose(agg, out, rtol=2e-6, atol=1e-7)
         if name.startswith("sage"):   # the layer's own graph code builds the same weights (a-7)
             g = CSRGraph(args[0], args[1])
             kind = "sum" if name == "sage_sum" else "mean"

@@ -202,3 +202,21 @@ def test_from_dgl_builds_the_in_edge_csr_and_caches_it():
     assert from_dgl(g) is c and from_dgl(c) is c
     assert c.in_degrees().tolist() == [3, 2, 0, 1, 0]
     assert isinstance(c, CSRGraph)
+
+
+def test_reference_gcn_weights_are_the_reference_layers_own(golden_layers):
+    """`edge_weights('reference_gcn')`: what the reference's MaxKGCNConv applies in total to an edge --
+    its recorded per-edge weight `norm_right[idx]` (deg_in of the SOURCE, utils/maxk_layers.py:372-376)
+    times the deg_out^-1/2 it folds into the features (:315-318) -- on the graph of the golden call."""
+    import torch
+    from spgemm_gnn_b200.graph import CSRGraph
+    z = golden_layers
+    g = CSRGraph(torch.from_numpy(z["gcn_both_call_ptr"].astype(np.int32)),
+                 torch.from_numpy(z["gcn_both_call_idx"].astype(np.int32)))
+    idx = z["gcn_both_call_idx"].astype(np.int64)
+    do = g.out_degrees().clamp(min=1).float().pow(-0.5).numpy()
+    want = z["gcn_both_call_val"].astype(np.float32) * do[idx]
+    got = g.edge_weights("reference_gcn").numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=0)
+    # and it is not GraphConv's 'both' unless the graph is regular
+    assert not np.allclose(g.edge_weights("both").numpy(), got)
