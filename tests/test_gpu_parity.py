@@ -458,7 +458,7 @@ def test_reference_layer_call_sites_through_the_cuda_path(mk, golden_layers):
             do = g.out_degrees().clamp(min=1).float().pow(0.5)            # undo the feature scaling of :315-318
             raw = (args[3] * do[:, None]).contiguous()
             agg = aggregate_cbsr(g, raw, args[4], "reference_gcn", c["d"])
-            assert torch.allclose(agg, out, rtol=2e-6, atol=1e-7)
+            assert float((agg - out).abs().max()) <= 1e-5 * float(out.abs().max())
         if name.startswith("sage"):   # the layer's own graph code builds the same weights (a-7)
             g = CSRGraph(args[0], args[1])
             kind = "sum" if name == "sage_sum" else "mean"
