@@ -47,7 +47,10 @@ _BWD_MAX_NZ = int(os.environ.get("MAXK_BWD_MAX_NZ", "0"))      # 0: same as the 
 # of on a straggling 1024-entry one.  The row-ordered list stays what the fold of multi-record rows uses.
 _EXEC_SORTED = os.environ.get("MAXK_EXEC_ORDER", "1") != "0"
 _BANKED = os.environ.get("MAXK_BANKED", "1") != "0"
-_BANKED_MIN_RECORD = 96   # mean stored entries per work record below which banking does not pay
+# mean stored entries per work record below which banking does not pay: every record zeroes and folds
+# 8 KB of cells, which 50 entries do not amortise (products shape, k = 32: 5.72 ms plain, 8.70 ms banked;
+# Flickr shape 0.079 / 0.138 ms -- profiles/r2/banked_short_records_call26.log)
+_BANKED_MIN_RECORD = int(os.environ.get("MAXK_BANKED_MIN_RECORD", "96"))
 _PACKED = os.environ.get("MAXK_PACKED", "1") != "0"   # k = 8, 16: banked + packed 8-byte entries
 # experimental backward: this many of the 4 neighbours of a warp step (k = 32) reduce through the TMA
 # unit (csrc/sspmm_bwd.cu, mk_sspmm_bwd_tma; measured slower); 0 = the shipped kernel
