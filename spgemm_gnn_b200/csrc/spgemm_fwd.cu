@@ -185,6 +185,10 @@ __device__ __forceinline__ void load_entries<1, uint16_t>(const float* __restric
     cv[0] = __ldg(ip);
 }
 
+#ifndef MK_FWD_VEC_GROUP_BANKS
+#define MK_FWD_VEC_GROUP_BANKS 1
+#endif
+
 template <int K, int EPL, typename IdxT, int U>
 __global__ void __launch_bounds__(32)
 spgemm_fwd_vec_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
@@ -200,12 +204,29 @@ spgemm_fwd_vec_kernel(const mk_part* __restrict__ parts, const int* __restrict__
     const int g = lane / LPN;
     const int t = lane % LPN;
     const mk_part rec = parts[blockIdx.x];
+#if MK_FWD_VEC_GROUP_BANKS
+    // Group-private BANKS instead of group-private copies laid end to end: column c of group g lives in
+    // bank LPN*g + c % LPN of row c / LPN, so the four (G) neighbours of a warp step can never collide
+    // with one another and a step costs the largest bank load INSIDE a group (LPN entries into LPN
+    // banks: ~3.0 on average for the maximum over G = 4 groups) instead of 32 entries into 32 banks
+    // (3.6).  Same shared memory, no banking pass, no assignment -- for the short-record shapes where
+    // mk_cbsr_bank + the two-cell kernel do not pay.
+    constexpr int LOG_BG = LPN >= 32 ? 5 : LPN >= 16 ? 4 : LPN >= 8 ? 3 : LPN >= 4 ? 2 : LPN >= 2 ? 1 : 0;
+    static_assert((1 << LOG_BG) == LPN, "lanes per neighbour must be a power of two");
+    const int rows = (dpad + LPN - 1) >> LOG_BG;
+    const int cells = rows << 5;
+    auto cell = [](int c) { return ((c >> LOG_BG) << 5) + (c & (LPN - 1)); };
+    float* __restrict__ my = acc + LPN * g;
+#else
+    const int cells = G * dpad;
+    auto cell = [](int c) { return c; };
+    float* __restrict__ my = acc + g * dpad;
+#endif
 
-    for (int c = lane * 4; c < G * dpad; c += 128)
+    for (int c = lane * 4; c < cells; c += 128)
         *reinterpret_cast<float4*>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
 
-    float* __restrict__ my = acc + g * dpad;
     const unsigned gmask = (LPN >= 32 ? kFull : ((1u << (LPN & 31)) - 1u)) << (g * LPN);
     const int end = rec.loc + rec.len;
     for (int base = rec.loc; base < end; base += 32) {
@@ -237,7 +258,7 @@ spgemm_fwd_vec_kernel(const mk_part* __restrict__ parts, const int* __restrict__
                 if (ok[u]) {  // uniform over the lanes of a group
 #pragma unroll
                     for (int q = 0; q < EPL; ++q)
-                        if (dv[u][q] != 0.0f) my[cv[u][q]] += vv[u] * dv[u][q];
+                        if (dv[u][q] != 0.0f) my[cell(cv[u][q])] += vv[u] * dv[u][q];
                     accum_fence_group(gmask);
                 }
                 accum_fence_warp();
@@ -249,12 +270,22 @@ spgemm_fwd_vec_kernel(const mk_part* __restrict__ parts, const int* __restrict__
     float* __restrict__ o = rec.slot < 0 ? out + static_cast<int64_t>(rec.row) * d
                                          : partial + static_cast<int64_t>(rec.slot) * d;
     for (int c = lane * 4; c < d; c += 128) {
+#if MK_FWD_VEC_GROUP_BANKS
+        const float* __restrict__ base = acc + cell(c);   // LPN >= 4: the four columns share a row segment
+        float4 s = *reinterpret_cast<const float4*>(base);
+#pragma unroll
+        for (int q = 1; q < G; ++q) {
+            const float4 a = *reinterpret_cast<const float4*>(base + LPN * q);
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        }
+#else
         float4 s = *reinterpret_cast<const float4*>(acc + c);
 #pragma unroll
         for (int q = 1; q < G; ++q) {
             const float4 a = *reinterpret_cast<const float4*>(acc + q * dpad + c);
             s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
         }
+#endif
         st_stream_f4(o + c, s);
     }
 }
@@ -390,7 +421,12 @@ static int launch_fwd_vec(const mk_part* parts, int64_t num_parts, const int* id
 #else
     constexpr int U = (EPL >= 4) ? 4 : (32 / G >= 8 ? 8 : 32 / G);  // <= 32 / G steps per slice
 #endif
+#if MK_FWD_VEC_GROUP_BANKS
+    constexpr int LPN = K / EPL;
+    const size_t smem = static_cast<size_t>((((d + 3) & ~3) + LPN - 1) / LPN) * 32 * 4;
+#else
     const size_t smem = static_cast<size_t>(G) * d * 4;
+#endif
     if (smem > 200 * 1024) return MK_EUNSUPPORTED;
     auto kern = spgemm_fwd_vec_kernel<K, EPL, IdxT, U>;
     if (smem > 48 * 1024)

@@ -537,7 +537,7 @@ def spgemm_forward(ptr, idx, val, sp_data, sp_index, num_nodes, num_edges, dim_s
 # not fit L2: "auto" = when n_src * k * 4 bytes exceed _BWD_TILED_MIN_MB, "0" / "1" force it off / on.
 _BWD_TILED = os.environ.get("MAXK_BWD_TILED", "auto")
 _BWD_TILED_MIN_MB = int(os.environ.get("MAXK_BWD_TILED_MIN_MB", "112"))
-_BWD_TILE_MB = int(os.environ.get("MAXK_BWD_TILE_MB", "64"))     # slice of dXs one column block covers
+_BWD_TILE_MB = int(os.environ.get("MAXK_BWD_TILE_MB", "96"))     # slice of dXs one column block covers (products shape, k = 32: 5.70 ms at 64, 5.34 at 80-96, 5.49 at 112-128, 6.22 at 160; profiles/r2/bwd_tile_sizes_call27.log)
 _blkptr_cache = {}
 
 
