@@ -185,8 +185,14 @@ __device__ __forceinline__ void load_entries<1, uint16_t>(const float* __restric
     cv[0] = __ldg(ip);
 }
 
+// Measurement variant (off): group-private BANKS instead of group-private copies laid end to end.  On
+// paper a step then costs the largest bank load inside a group (~3.0) instead of 32 entries into 32
+// banks (3.6); measured on a B200 it is SLOWER on every short-record shape
+// (profiles/r2/fwd_vec_group_banks_call28.log: products 5.69 -> 6.55 ms, Flickr 0.079 -> 0.111, Yelp
+// 0.90 -> 1.14): eight sorted-row entries that land in eight banks collide more often than in 32, and
+// the maximum over four groups is no better than one draw of 32 into 32.
 #ifndef MK_FWD_VEC_GROUP_BANKS
-#define MK_FWD_VEC_GROUP_BANKS 1
+#define MK_FWD_VEC_GROUP_BANKS 0
 #endif
 
 template <int K, int EPL, typename IdxT, int U>
@@ -205,12 +211,7 @@ spgemm_fwd_vec_kernel(const mk_part* __restrict__ parts, const int* __restrict__
     const int t = lane % LPN;
     const mk_part rec = parts[blockIdx.x];
 #if MK_FWD_VEC_GROUP_BANKS
-    // Group-private BANKS instead of group-private copies laid end to end: column c of group g lives in
-    // bank LPN*g + c % LPN of row c / LPN, so the four (G) neighbours of a warp step can never collide
-    // with one another and a step costs the largest bank load INSIDE a group (LPN entries into LPN
-    // banks: ~3.0 on average for the maximum over G = 4 groups) instead of 32 entries into 32 banks
-    // (3.6).  Same shared memory, no banking pass, no assignment -- for the short-record shapes where
-    // mk_cbsr_bank + the two-cell kernel do not pay.
+    // column c of group g lives in bank LPN*g + c % LPN of row c / LPN (see the note at the macro)
     constexpr int LOG_BG = LPN >= 32 ? 5 : LPN >= 16 ? 4 : LPN >= 8 ? 3 : LPN >= 4 ? 2 : LPN >= 2 ? 1 : 0;
     static_assert((1 << LOG_BG) == LPN, "lanes per neighbour must be a power of two");
     const int rows = (dpad + LPN - 1) >> LOG_BG;
