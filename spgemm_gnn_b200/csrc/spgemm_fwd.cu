@@ -189,8 +189,7 @@ __device__ __forceinline__ void load_entries<1, uint16_t>(const float* __restric
 // paper a step then costs the largest bank load inside a group (~3.0) instead of 32 entries into 32
 // banks (3.6); measured on a B200 it is SLOWER on every short-record shape
 // (profiles/r2/fwd_vec_group_banks_call28.log: products 5.69 -> 6.55 ms, Flickr 0.079 -> 0.111, Yelp
-// 0.90 -> 1.14): eight sorted-row entries that land in eight banks collide more often than in 32, and
-// the maximum over four groups is no better than one draw of 32 into 32.
+// 0.90 -> 1.14).  Not profiled further; the balls-into-bins estimate alone does not decide this kernel.
 #ifndef MK_FWD_VEC_GROUP_BANKS
 #define MK_FWD_VEC_GROUP_BANKS 0
 #endif
