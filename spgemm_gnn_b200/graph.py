@@ -307,6 +307,56 @@ def shaped_graph(name: str, *, scale: float = 1.0, seed: int = 97, device="cpu")
     return synthetic_graph(n, e, seed=seed, device=device)
 
 
+def permute(g: CSRGraph, perm: torch.Tensor) -> CSRGraph:
+    """The same graph under the node relabelling new = perm[old] (A' = P A P^T).  Parallel edges are
+    kept, neighbours come out ascending.  Node data moves with `x_new[perm] = x_old`."""
+    n = g.num_nodes()
+    if g.num_src not in (None, n):
+        raise ValueError("permute wants a square graph")
+    perm = perm.to(device=g.device, dtype=torch.int64)
+    if perm.numel() != n:
+        raise ValueError("perm must have one entry per node")
+    key, _ = torch.sort(perm[g.row_ids()] * n + perm[g.indices.to(torch.int64)])
+    d = torch.div(key, n, rounding_mode="floor")
+    ptr = torch.zeros(n + 1, dtype=torch.int64, device=key.device)
+    ptr[1:] = torch.cumsum(torch.bincount(d, minlength=n), 0)
+    out = CSRGraph(ptr.to(torch.int32), (key - d * n).to(torch.int32).contiguous())
+    out._cache["symmetric"] = g._cache.get("symmetric", False)
+    return out
+
+
+def reorder(g: CSRGraph, method: str = "rcm") -> Tuple[CSRGraph, torch.Tensor]:
+    """Locality-improving node order for graphs that HAVE locality (co-purchase, social, road
+    graphs; the uniform-random synthetic shapes have none to find).  Returns `(graph, perm)` with
+    new = perm[old], like `dist.random_relabel`.
+
+    "rcm": reverse Cuthill-McKee on the symmetrised pattern (scipy) -- neighbours get nearby ids, so
+           the CBSR rows one CSR row gathers, and the `dXs` rows it reduces into, share cache lines
+           and L2 residency; contiguous nnz-balanced shards (`row_partition_bounds`) then also cut
+           few edges.
+    "degree": descending in-degree -- the hub rows every CTA keeps gathering sit together at the
+           head of the table (and the work records come out longest first without a second copy).
+    Neither changes any result beyond the relabelling (tests/test_host.py)."""
+    n = g.num_nodes()
+    if method == "degree":
+        order = torch.argsort(g.in_degrees().to(torch.int64), descending=True, stable=True)
+    elif method == "rcm":
+        import numpy as np
+        import scipy.sparse as sp
+        from scipy.sparse.csgraph import reverse_cuthill_mckee
+        ptr = g.indptr.cpu().numpy().astype(np.int64)
+        idx = g.indices.cpu().numpy()
+        a = sp.csr_matrix((np.ones(idx.shape[0], dtype=np.int8), idx, ptr), shape=(n, n))
+        order = torch.from_numpy(np.ascontiguousarray(
+            reverse_cuthill_mckee(a, symmetric_mode=bool(g._cache.get("symmetric", False))).astype(np.int64)))
+    else:
+        raise ValueError(f"unknown reorder method {method!r}")
+    order = order.to(g.device)                      # order[new] = old
+    perm = torch.empty(n, dtype=torch.int64, device=g.device)
+    perm[order] = torch.arange(n, dtype=torch.int64, device=g.device)
+    return permute(g, perm), perm
+
+
 def row_partition_bounds(indptr: torch.Tensor, world: int) -> list:
     """nnz-balanced contiguous row ranges, one per rank (balance by
     nnz, not rows).  Returns world+1 row offsets."""
@@ -347,6 +397,8 @@ __all__ = [
     "synthetic_graph",
     "shaped_graph",
     "row_partition_bounds",
+    "permute",
+    "reorder",
     "index_dtype_for",
     "ceil_div",
 ]

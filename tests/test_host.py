@@ -220,3 +220,44 @@ def test_reference_gcn_weights_are_the_reference_layers_own(golden_layers):
     np.testing.assert_allclose(got, want, rtol=1e-6, atol=0)
     # and it is not GraphConv's 'both' unless the graph is regular
     assert not np.allclose(g.edge_weights("both").numpy(), got)
+
+
+def test_reorder_is_a_relabelling_and_rcm_restores_locality():
+    """`graph.reorder`: the permuted graph is P A P^T (the oracle's forward commutes with it), RCM brings a
+    shuffled banded graph back to a narrow band, "degree" puts the rows in descending-degree order."""
+    rng = np.random.default_rng(5)
+    n, half = 600, 6
+    r = np.repeat(np.arange(n), 2 * half + 1)
+    c = r + np.tile(np.arange(-half, half + 1), n)
+    ok = (c >= 0) & (c < n)
+    band = G.from_edges(torch.from_numpy(r[ok]), torch.from_numpy(c[ok]), n, symmetric=True)
+    shuffle = torch.from_numpy(rng.permutation(n))
+    g = G.permute(band, shuffle)
+    assert g.num_edges() == band.num_edges()
+
+    def bandwidth(h):
+        return int((h.row_ids() - h.indices.to(torch.int64)).abs().max())
+
+    assert bandwidth(band) == half and bandwidth(g) > n // 2
+    g_rcm, perm = G.reorder(g, "rcm")
+    assert bandwidth(g_rcm) <= 2 * half + 1
+    assert sorted(perm.tolist()) == list(range(n))
+
+    k, d = 4, 16
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    for h, p in ((g_rcm, perm), G.reorder(g, "degree")):
+        p = p.numpy()
+        x_new = np.empty_like(x)
+        x_new[p] = x
+        sd0, si0 = mo.maxk_cbsr(x, k)
+        sd1, si1 = mo.maxk_cbsr(x_new, k)
+        out0 = mo.spgemm_fwd(g.indptr.numpy(), g.indices.numpy(), g.edge_weights("mean").numpy(),
+                                 sd0, si0, d)
+        out1 = mo.spgemm_fwd(h.indptr.numpy(), h.indices.numpy(), h.edge_weights("mean").numpy(),
+                                 sd1, si1, d)
+        np.testing.assert_allclose(out1[p], out0, rtol=1e-6, atol=1e-7)
+    g_deg, _ = G.reorder(g, "degree")
+    deg = g_deg.in_degrees()
+    assert bool((deg[:-1] >= deg[1:]).all())
+    with pytest.raises(ValueError):
+        G.reorder(g, "nope")
