@@ -118,17 +118,28 @@ topk_cbsr_reg_kernel(const float* __restrict__ x, int64_t n, int d, int k,
     }
 }
 
-// Any D (<= 49152): the keys live in shared memory, same algorithm with strided loops.
-template <typename IdxT>
+// Any D: same algorithm with strided loops.  STAGED: the keys live in shared memory (D <= 49152);
+// otherwise (up to the 65536 columns a uint16 id can name) every pass re-derives them from the row,
+// which the first pass left in L2.
+template <typename IdxT, bool STAGED>
 __global__ void __launch_bounds__(32)
 topk_cbsr_smem_kernel(const float* __restrict__ x, int64_t n, int d, int k,
                       float* __restrict__ sp_data, IdxT* __restrict__ sp_index) {
-    extern __shared__ uint32_t skey[];
+    extern __shared__ uint32_t skey_buf[];
     const int lane = lane_id();
     for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
         const float* __restrict__ xr = x + row * d;
-        for (int c = lane; c < d; c += 32) skey[c] = order_key(ld_stream_f1(xr + c));
-        __syncwarp();
+        struct Keys {
+            const uint32_t* s;
+            const float* g;
+            __device__ __forceinline__ uint32_t operator[](int c) const {
+                return STAGED ? s[c] : order_key(__ldg(g + c));
+            }
+        } skey{skey_buf, xr};
+        if (STAGED) {
+            for (int c = lane; c < d; c += 32) skey_buf[c] = order_key(ld_stream_f1(xr + c));
+            __syncwarp();
+        }
         uint32_t thr = 0;
         bool exact = false;
         for (int bit = 31; bit >= 0; --bit) {
@@ -201,15 +212,20 @@ static int launch_topk(const float* x, int64_t n, int d, int k, float* sp_data, 
     if (d <= 512) return launch_reg<4, IdxT>(x, n, d, k, sp_data, sp_index, st);
     if (d <= 768) return launch_reg<6, IdxT>(x, n, d, k, sp_data, sp_index, st);
     if (d <= 1024) return launch_reg<8, IdxT>(x, n, d, k, sp_data, sp_index, st);
-    if (d > 49152) return MK_EUNSUPPORTED;
+    const unsigned blocks = static_cast<unsigned>(n < 148 * 32 ? n : 148 * 32);
+    if (d > 49152) {
+        topk_cbsr_smem_kernel<IdxT, false><<<blocks, 32, 0, st>>>(x, n, d, k, sp_data,
+                                                                  static_cast<IdxT*>(sp_index));
+        MK_LAUNCH_CHECK("topk_cbsr_smem_kernel");
+        return MK_OK;
+    }
     const size_t smem = static_cast<size_t>(d) * 4;
     if (smem > 48 * 1024)
-        MK_CUDA_TRY(cudaFuncSetAttribute(topk_cbsr_smem_kernel<IdxT>,
+        MK_CUDA_TRY(cudaFuncSetAttribute(topk_cbsr_smem_kernel<IdxT, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
-    const unsigned blocks = static_cast<unsigned>(n < 148 * 32 ? n : 148 * 32);
-    topk_cbsr_smem_kernel<IdxT><<<blocks, 32, smem, st>>>(x, n, d, k, sp_data,
-                                                          static_cast<IdxT*>(sp_index));
+    topk_cbsr_smem_kernel<IdxT, true><<<blocks, 32, smem, st>>>(x, n, d, k, sp_data,
+                                                                static_cast<IdxT*>(sp_index));
     MK_LAUNCH_CHECK("topk_cbsr_smem_kernel");
     return MK_OK;
 }

@@ -45,7 +45,7 @@ def assert_rel(got, want64, bound, what):
 TOPK_CASES = [(257, 256, 32), (100, 256, 8), (100, 256, 16), (64, 256, 64), (33, 256, 256),
               (50, 64, 8), (50, 32, 32), (40, 96, 1), (37, 100, 7), (31, 130, 20),
               (40, 384, 16), (20, 512, 32), (20, 768, 64), (12, 1024, 32), (9, 1500, 40),
-              (5, 4100, 33), (1, 256, 32)]
+              (5, 4100, 33), (1, 256, 32), (3, 49152, 40), (3, 50000, 33), (2, 65536, 64)]
 
 
 @pytest.mark.parametrize("n,d,k", TOPK_CASES)
@@ -266,7 +266,7 @@ def test_golden_vectors_through_the_cuda_path(mk, golden):
 
 
 @pytest.mark.parametrize("n,d,k", [(100, 256, 32), (33, 100, 7), (20, 384, 16), (7, 1500, 40), (5, 9000, 33),
-                                   (3, 49152, 64)])
+                                   (3, 49152, 64), (2, 51204, 9), (2, 65536, 40)])
 def test_scatter_and_gather(mk, n, d, k):
     from oracle import maxk_oracle as mo
     rng = np.random.default_rng(d)
