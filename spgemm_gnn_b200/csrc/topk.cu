@@ -118,6 +118,147 @@ topk_cbsr_reg_kernel(const float* __restrict__ x, int64_t n, int d, int k,
     }
 }
 
+// Second mapping of the same algorithm (the default): lane-CONTIGUOUS columns -- lane l holds columns
+// [l*EPL, (l+1)*EPL), EPL = NV4*4 -- so ascending column order is (lane, element) order and ONE warp
+// prefix sum ranks every kept entry (the strided mapping above needs one per 128 columns); the kept
+// entries are compacted through shared memory and leave as coalesced row stores instead of 2*EPL
+// predicated scalar stores with 64-bit address arithmetic each.  Rows come in with 256-bit loads
+// (LDG.E.256) when they are 32-byte aligned.  Same search, same tie rule, same output.
+template <int NV4, typename IdxT, int VECW>
+__global__ void __launch_bounds__(256)
+topk_cbsr_lane_kernel(const float* __restrict__ x, int64_t n, int d, int k,
+                      float* __restrict__ sp_data, IdxT* __restrict__ sp_index) {
+    extern __shared__ __align__(16) unsigned char stage[];  // [warps][k] floats, then [warps][k] ids
+    constexpr int EPL = NV4 * 4;
+    const int w = threadIdx.x >> 5;
+    const int nw = blockDim.x >> 5;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * nw + w;
+    if (row >= n) return;
+    const int lane = lane_id();
+    const float* __restrict__ xr = x + row * d;
+    const int cb = lane * EPL;
+
+    float v[EPL];
+    uint32_t key[EPL];
+#pragma unroll
+    for (int j = 0; j < NV4; ++j) {
+        const int c0 = cb + 4 * j;
+        if (VECW == 8 && (j & 1) == 1 && c0 + 3 < d) continue;  // second half of the 256-bit load below
+        if (VECW == 8 && (j & 1) == 0 && j + 1 < NV4 && c0 + 7 < d) {
+            asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(v[4 * j + 0]), "=f"(v[4 * j + 1]), "=f"(v[4 * j + 2]), "=f"(v[4 * j + 3]),
+                           "=f"(v[4 * j + 4]), "=f"(v[4 * j + 5]), "=f"(v[4 * j + 6]), "=f"(v[4 * j + 7])
+                         : "l"(xr + c0));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) key[4 * j + i] = order_key(v[4 * j + i]);
+        } else if (VECW >= 4 && c0 + 3 < d) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(xr + c0));  // neighbours share sectors: via L1
+            v[4 * j + 0] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) key[4 * j + i] = order_key(v[4 * j + i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool in = c0 + i < d;
+                v[4 * j + i] = in ? __ldg(xr + (in ? c0 + i : 0)) : 0.0f;
+                key[4 * j + i] = in ? order_key(v[4 * j + i]) : 0u;  // below every real key
+            }
+        }
+    }
+
+    // A lower bound of the answer that costs a handful of instructions: every lane holds at least j keys
+    // >= its own j-th largest, so at least 32*j >= k keys of the row are >= the smallest of those over the
+    // lanes (j = 1 for k <= 32, 2 for k <= 64).  Candidates not above the bound are accepted without counting.
+    uint32_t lb = 0;
+    if (k <= 32) {
+        uint32_t m1 = key[0];
+#pragma unroll
+        for (int e = 1; e < EPL; ++e) m1 = max(m1, key[e]);
+        lb = __reduce_min_sync(kFull, m1);
+    } else if (k <= 64 && EPL >= 2) {
+        uint32_t m1 = max(key[0], key[1]), m2 = min(key[0], key[1]);
+#pragma unroll
+        for (int e = 2; e < EPL; ++e) {
+            m2 = max(m2, min(m1, key[e]));
+            m1 = max(m1, key[e]);
+        }
+        lb = __reduce_min_sync(kFull, m2);
+    }
+
+    // largest T with #{key >= T} >= k
+    uint32_t thr = 0;
+    bool exact = false;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = thr | (1u << bit);
+        if (cand <= lb) { thr = cand; continue; }
+        const uint32_t ncand = 0u - cand;
+        int c = 0;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) count_ge(c, key[e], ncand);
+        c = __reduce_add_sync(kFull, c);
+        if (c >= k) {
+            thr = cand;
+            if (c == k) { exact = true; break; }
+        }
+    }
+
+    uint32_t selmask = 0;  // bit e: element e is kept
+    if (exact) {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) selmask |= (key[e] >= thr ? 1u : 0u) << e;
+    } else {
+        // more than k keys are >= thr: all keys > thr are kept, the lowest-column ties fill up
+        int gt = 0, eq = 0;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            gt += (key[e] > thr) ? 1 : 0;
+            eq += (key[e] == thr) ? 1 : 0;
+        }
+        const int need = k - __reduce_add_sync(kFull, gt);
+        int rank = warp_incl_scan(eq, lane) - eq;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            if (key[e] > thr) {
+                selmask |= 1u << e;
+            } else if (key[e] == thr) {
+                if (rank < need) selmask |= 1u << e;
+                ++rank;
+            }
+        }
+    }
+
+    // ascending-column slot of every kept element; the row is assembled in shared memory
+    float* __restrict__ sf = reinterpret_cast<float*>(stage) + w * k;
+    IdxT* __restrict__ si = reinterpret_cast<IdxT*>(stage + static_cast<size_t>(nw) * k * 4) + w * k;
+    const int cnt = __popc(selmask);
+    const int pos = warp_incl_scan(cnt, lane) - cnt;
+    // predicated stores, no branches: two running shared-memory addresses advance past every kept entry
+    uint32_t pa = static_cast<uint32_t>(__cvta_generic_to_shared(sf + pos));
+    uint32_t pb = static_cast<uint32_t>(__cvta_generic_to_shared(si + pos));
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+        if (sizeof(IdxT) == 1)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t@p st.shared.f32 [%0], %2;\n\t"
+                         "@p st.shared.u8 [%1], %3;\n\t@p add.u32 %0, %0, 4;\n\t@p add.u32 %1, %1, 1;\n\t}"
+                         : "+r"(pa), "+r"(pb)
+                         : "f"(v[e]), "r"(cb + e), "r"(selmask & (1u << e))
+                         : "memory");
+        else
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t@p st.shared.f32 [%0], %2;\n\t"
+                         "@p st.shared.u16 [%1], %3;\n\t@p add.u32 %0, %0, 4;\n\t@p add.u32 %1, %1, 2;\n\t}"
+                         : "+r"(pa), "+r"(pb)
+                         : "f"(v[e]), "r"(cb + e), "r"(selmask & (1u << e))
+                         : "memory");
+    }
+    __syncwarp();
+    float* __restrict__ od = sp_data + row * k;
+    IdxT* __restrict__ oi = sp_index + row * k;
+    for (int t = lane; t < k; t += 32) {
+        od[t] = sf[t];
+        oi[t] = si[t];
+    }
+}
+
 // Any D: same algorithm with strided loops.  STAGED: the keys live in shared memory (D <= 49152);
 // otherwise (up to the 65536 columns a uint16 id can name) every pass re-derives them from the row,
 // which the first pass left in L2.
@@ -203,9 +344,41 @@ static int launch_reg(const float* x, int64_t n, int d, int k, float* sp_data, v
     return MK_OK;
 }
 
+template <int NV4, typename IdxT>
+static int launch_lane(const float* x, int64_t n, int d, int k, float* sp_data, void* sp_index,
+                       cudaStream_t st) {
+    // 8 rows per CTA while the 8 staging rows (6 bytes per kept entry) stay within 48 KB
+    const int warps = static_cast<size_t>(k) * 8 * 8 <= 48 * 1024 ? 8 : 4;
+    const size_t smem = static_cast<size_t>(warps) * k * (4 + sizeof(IdxT));
+    const int64_t blocks = (n + warps - 1) / warps;
+    if (blocks > 0x7fffffffLL) return MK_EUNSUPPORTED;
+    const bool a16 = (d % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0);
+    const bool a32 = (d % 8 == 0) && (reinterpret_cast<uintptr_t>(x) % 32 == 0) && NV4 % 2 == 0;
+    IdxT* oi = static_cast<IdxT*>(sp_index);
+    const unsigned g = static_cast<unsigned>(blocks), b = static_cast<unsigned>(warps * 32);
+    if (a32)
+        topk_cbsr_lane_kernel<NV4, IdxT, 8><<<g, b, smem, st>>>(x, n, d, k, sp_data, oi);
+    else if (a16)
+        topk_cbsr_lane_kernel<NV4, IdxT, 4><<<g, b, smem, st>>>(x, n, d, k, sp_data, oi);
+    else
+        topk_cbsr_lane_kernel<NV4, IdxT, 0><<<g, b, smem, st>>>(x, n, d, k, sp_data, oi);
+    MK_LAUNCH_CHECK("topk_cbsr_lane_kernel");
+    return MK_OK;
+}
+
 template <typename IdxT>
 static int launch_topk(const float* x, int64_t n, int d, int k, float* sp_data, void* sp_index,
                        cudaStream_t st) {
+    // MAXK_TOPK_STRIDED=1: the round-1 mapping (columns strided over the lanes), kept for A/B runs
+    static const bool strided = [] { const char* e = getenv("MAXK_TOPK_STRIDED"); return e && e[0] == '1'; }();
+    if (!strided) {
+        if (d <= 128) return launch_lane<1, IdxT>(x, n, d, k, sp_data, sp_index, st);
+        if (d <= 256) return launch_lane<2, IdxT>(x, n, d, k, sp_data, sp_index, st);
+        if (d <= 384) return launch_lane<3, IdxT>(x, n, d, k, sp_data, sp_index, st);
+        if (d <= 512) return launch_lane<4, IdxT>(x, n, d, k, sp_data, sp_index, st);
+        if (d <= 768) return launch_lane<6, IdxT>(x, n, d, k, sp_data, sp_index, st);
+        if (d <= 1024) return launch_lane<8, IdxT>(x, n, d, k, sp_data, sp_index, st);
+    }
     if (d <= 128) return launch_reg<1, IdxT>(x, n, d, k, sp_data, sp_index, st);
     if (d <= 256) return launch_reg<2, IdxT>(x, n, d, k, sp_data, sp_index, st);
     if (d <= 384) return launch_reg<3, IdxT>(x, n, d, k, sp_data, sp_index, st);
