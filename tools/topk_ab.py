@@ -1,5 +1,5 @@
 """MaxK top-k kernel timing on the Reddit row count (A/B: MAXK_TOPK_STRIDED=1 selects the round-1 mapping).
-usage: python tools/topk_ab.py [label]"""
+usage: python tools/topk_ab.py [label [D:k]]"""
 import os
 import sys
 
@@ -13,7 +13,11 @@ def main():
     label = sys.argv[1] if len(sys.argv) > 1 else os.environ.get("MAXK_TOPK_STRIDED", "0")
     n = 232965
     gen = torch.Generator(device="cuda").manual_seed(97)
-    for d, ks in ((256, (8, 16, 32, 64)), (128, (32,)), (384, (32,)), (512, (32,)), (1024, (64,)), (250, (32,))):
+    shapes = ((256, (8, 16, 32, 64)), (128, (32,)), (384, (32,)), (512, (32,)), (1024, (64,)), (250, (32,)))
+    if len(sys.argv) > 2:                    # "256:32" -- one shape only (the ncu target)
+        d_, k_ = sys.argv[2].split(":")
+        shapes = ((int(d_), (int(k_),)),)
+    for d, ks in shapes:
         x = torch.randn(n, d, device="cuda", generator=gen)
         for k in ks:
             for _ in range(3):
