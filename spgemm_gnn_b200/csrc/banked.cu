@@ -16,6 +16,12 @@
 #include "epilogue.cuh"
 #include "peer.cuh"
 
+// Which widths prefetch the epilogue's h_self row at CTA start (-DMK_EPI_PREFETCH_MASK=<or of k> to vary it).
+#ifndef MK_EPI_PREFETCH_MASK
+#define MK_EPI_PREFETCH_MASK (8 | 32)
+#endif
+#define MK_EPI_PREFETCH(K) (((MK_EPI_PREFETCH_MASK) & (K)) != 0)
+
 namespace mk {
 
 // Loads of a lane's CAP consecutive entries.  CG = false: read-only path (ld.global.nc), the
@@ -181,8 +187,19 @@ struct FwdPhase {
 // >= rank*rows_per_rank.  A record then walks [split, end) first and [begin, split) second, i.e.
 // the source blocks in the order rank, rank+1, ..., world-1, 0, ..., rank-1 -- the order in which
 // the pushes (peer.cu, push_rows) make them arrive.  The summation order of a row is fixed either way.
-template <int K, int U, bool WAIT, bool PACKED = false>
-__global__ void __launch_bounds__(32)
+// EPI: the f-3 epilogue variant (its own instantiation: the 16 registers of the prefetched h_self row would
+// otherwise be carried through the accumulation loop of every launch -- that alone moved the k = 16 forward
+// from 2.14 to 2.39 ms, profiles/r2/k16_bisect_call35.log).
+// -DMK_FWD_MINBLOCKS=n: a resident-CTA hint for ptxas (measurement knob).  Measured, forward ms at k = 8 / 16 / 32 /
+// 64 (profiles/r2/fwd_minblocks_call37.log): no hint 1.521 / 2.138 / 2.870 / 5.979 (shipped); 25: 1.508 / 2.706 / 2.872 /
+// 6.053; 32: 1.509 / 2.537 / 2.884 / 6.098; 1 or 20: 1.554 / 2.401 / 2.967 / 6.192.
+#ifdef MK_FWD_MINBLOCKS
+#define MK_FWD_BOUNDS __launch_bounds__(32, MK_FWD_MINBLOCKS)
+#else
+#define MK_FWD_BOUNDS __launch_bounds__(32)
+#endif
+template <int K, int U, bool WAIT, bool PACKED = false, bool EPI = false, bool PF = false>
+__global__ void MK_FWD_BOUNDS
 spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restrict__ idx,
                          const float* __restrict__ val, const float* __restrict__ bk_data,
                          const uint16_t* __restrict__ bk_slot, float* __restrict__ out,
@@ -214,12 +231,19 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
 
     // f-3 epilogue: this row's h_self, asked for now and consumed when the row is finished (the load's
     // latency would otherwise sit at the end of every CTA)
-    float4 hs[4];
-    if (ep.gamma != nullptr && ep.h_self != nullptr && rec.slot < 0) {
-        const float* __restrict__ hrow = ep.h_self + static_cast<int64_t>(rec.row) * d;
+    // (EPI: epilogue code compiled in, still switched by ep.gamma at run time; PF: with the prefetch.  Measured per
+    // width, profiles/r2/epi_prefetch_call36.log: the prefetch pays at k = 8 and 32 -- 1.593 -> 1.550, 2.933 -> 2.899 ms
+    // -- and costs at k = 16, whose 8-neighbour step already fills the register file, and at k = 64 -- 2.216 -> 2.537,
+    // 5.923 -> 5.972 ms; there the row is loaded when it is needed.)
+    constexpr bool PREFETCH_SELF = EPI && PF;
+    [[maybe_unused]] float4 hs[PREFETCH_SELF ? 4 : 1];
+    if constexpr (PREFETCH_SELF) {
+        if (ep.gamma != nullptr && ep.h_self != nullptr && rec.slot < 0) {
+            const float* __restrict__ hrow = ep.h_self + static_cast<int64_t>(rec.row) * d;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j * 128 + lane * 4 < d) hs[j] = ld_stream_f4(hrow + j * 128 + lane * 4);
+            for (int j = 0; j < 4; ++j)
+                if (j * 128 + lane * 4 < d) hs[j] = ld_stream_f4(hrow + j * 128 + lane * 4);
+        }
     }
 
     // which source blocks have arrived (bit q); refreshed only while something is missing
@@ -350,12 +374,20 @@ spgemm_fwd_banked_kernel(const mk_part* __restrict__ parts, const int* __restric
     __syncwarp();
     float* __restrict__ o = rec.slot < 0 ? out + static_cast<int64_t>(rec.row) * d
                                          : partial + static_cast<int64_t>(rec.slot) * d;
-    if (ep.gamma != nullptr && rec.slot < 0) {
-        // f-3: the finished row goes straight into y = LayerNorm(h_self + row + bias) * gamma + beta
-        // (and z, mean, rstd for the backward) -- no dense round trip of the aggregated row
-        fwd_epilogue_row(ep, [&](int c) { return *reinterpret_cast<const float4*>(acc + c); },
-                         [&](int c) { return hs[c >> 7]; }, out, rec.row, d, lane);
-        return;
+    if constexpr (EPI) {
+        if (ep.gamma != nullptr && rec.slot < 0) {
+            // f-3: the finished row goes straight into y = LayerNorm(h_self + row + bias) * gamma + beta
+            // (and z, mean, rstd for the backward) -- no dense round trip of the aggregated row
+            if constexpr (PREFETCH_SELF) {
+                fwd_epilogue_row(ep, [&](int c) { return *reinterpret_cast<const float4*>(acc + c); },
+                                 [&](int c) { return hs[c >> 7]; }, out, rec.row, d, lane);
+            } else {
+                const float* __restrict__ hrow = ep.h_self + static_cast<int64_t>(rec.row) * d;
+                fwd_epilogue_row(ep, [&](int c) { return *reinterpret_cast<const float4*>(acc + c); },
+                                 [&](int c) { return ld_stream_f4(hrow + c); }, out, rec.row, d, lane);
+            }
+            return;
+        }
     }
     if (ph.accumulate && rec.slot < 0) {  // later phase: on top of what the earlier ones wrote
         for (int c = lane * 4; c < d; c += 128) {
@@ -472,7 +504,8 @@ static int launch_fwd_banked(const mk_part* parts, int64_t num_parts, const int*
     const size_t smem = static_cast<size_t>(32) * rows * 4;
 #endif
     if (fw.hdr != nullptr) {
-        auto kern = spgemm_fwd_banked_kernel<K, U, true, PACKED>;
+        // (the multi-GPU form keeps the instantiation its 2- to 8-GPU measurements were taken with)
+        auto kern = spgemm_fwd_banked_kernel<K, U, true, PACKED, true, true>;
         if (smem > 48 * 1024)
             MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem)));
@@ -481,12 +514,28 @@ static int launch_fwd_banked(const mk_part* parts, int64_t num_parts, const int*
         kern<<<static_cast<unsigned>(grid), 32, smem, st>>>(parts, idx, val, bk_data, bk_slot, out,
                                                             partial, d, rows, split, fw, ph, ep);
     } else {
-        auto kern = spgemm_fwd_banked_kernel<K, U, false, PACKED>;
-        if (smem > 48 * 1024)
-            MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem)));
-        kern<<<static_cast<unsigned>(num_parts), 32, smem, st>>>(parts, idx, val, bk_data, bk_slot, out,
-                                                                 partial, d, rows, split, fw, ph, ep);
+        // Which instantiation runs.  With the epilogue: prefetch where it pays (above).  Without: the kernel
+        // that carries the epilogue's code and registers is, as ptxas schedules it, the faster PLAIN forward at
+        // k = 8 / 32 / 64 (1.495 / 2.856 / 5.82 ms against 1.521 / 2.870 / 5.98) and the slower one at k = 16 (2.39
+        // against 2.14 ms: profiles/r2/k16_bisect_call35.log, epi_prefetch_call36.log) -- so each width gets its own.
+        auto go = [&](auto kern) -> int {
+            if (smem > 48 * 1024)
+                MK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(smem)));
+            kern<<<static_cast<unsigned>(num_parts), 32, smem, st>>>(parts, idx, val, bk_data, bk_slot, out,
+                                                                     partial, d, rows, split, fw, ph, ep);
+            return MK_OK;
+        };
+        int rc;
+        if (ep.gamma != nullptr) {
+            rc = go(spgemm_fwd_banked_kernel<K, U, false, PACKED, true, MK_EPI_PREFETCH(K)>);
+        } else {
+            if constexpr (K == 16)
+                rc = go(spgemm_fwd_banked_kernel<K, U, false, PACKED, false, false>);
+            else
+                rc = go(spgemm_fwd_banked_kernel<K, U, false, PACKED, true, true>);
+        }
+        if (rc != MK_OK) return rc;
     }
     MK_LAUNCH_CHECK("spgemm_fwd_banked_kernel");
     return MK_OK;

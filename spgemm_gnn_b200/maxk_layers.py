@@ -187,12 +187,13 @@ class MaxKAggregateLNFunction(Function):
 def maxk_aggregate_add_norm(graph: CSRGraph, h_neigh: torch.Tensor, h_self, bias, norm, k: int,
                             weight_kind: str) -> torch.Tensor:
     """`norm(h_self + aggregate(MaxK(h_neigh)) + bias)` -- with the epilogue inside the forward SpGEMM
-    where that exists (single GPU, banked or packed forward, affine LayerNorm over <= 512 columns),
-    the separate kernels otherwise."""
+    where that exists and pays (single GPU, banked or packed forward, affine LayerNorm over <= 512 columns,
+    k <= 32: at k = 64 the separate kernels measured faster, 5.765 against 5.916 ms on the Reddit shape,
+    profiles/r2/fwd_per_width_call38.log), the separate kernels otherwise."""
     d = h_neigh.shape[1]
     if (FUSED_LN_EPILOGUE and getattr(graph, "world", 1) == 1 and h_neigh.is_cuda and h_neigh.dim() == 2
             and h_neigh.dtype == torch.float32 and isinstance(norm, nn.LayerNorm) and norm.elementwise_affine
-            and norm.bias is not None and len(norm.normalized_shape) == 1 and d % 4 == 0 and d <= 512
+            and norm.bias is not None and len(norm.normalized_shape) == 1 and d % 4 == 0 and d <= 512 and k <= 32
             and h_neigh.shape[0] == graph.num_src == graph.num_nodes() and maxk_kernels.banked_supported(k, d)):
         n, e = graph.num_nodes(), graph.num_edges()
         part = maxk_kernels.partition(graph.indptr, n)
