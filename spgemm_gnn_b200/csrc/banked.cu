@@ -21,6 +21,10 @@
 #define MK_EPI_PREFETCH_MASK (8 | 32)
 #endif
 #define MK_EPI_PREFETCH(K) (((MK_EPI_PREFETCH_MASK) & (K)) != 0)
+// Which widths run their PLAIN forward on the instantiation without the epilogue's code (see launch_fwd_banked).
+#ifndef MK_FWD_PLAIN_BARE_MASK
+#define MK_FWD_PLAIN_BARE_MASK 16
+#endif
 
 namespace mk {
 
@@ -496,7 +500,9 @@ static int launch_fwd_banked(const mk_part* parts, int64_t num_parts, const int*
 #ifdef MK_FWD_U
     constexpr int U = MK_FWD_U;
 #else
-    constexpr int U = K >= 64 ? 2 : (K == 32 ? 4 : 8);
+    // neighbour steps in flight, measured per width (profiles/r2/fwd_unroll_call39.log; forward ms at U = 2 / 4 / 8:
+    // k = 8: 1.894 / 1.581 / 1.493, k = 16: 2.339 / 2.042 / 2.138, k = 32: 2.977 / 2.857 / 3.867, k = 64: 5.806 / 6.222 / 11.7)
+    constexpr int U = K >= 64 ? 2 : (K >= 16 ? 4 : 8);
 #endif
 #ifdef MK_FWD_EXTRA_SMEM   // measurement knob: what fewer resident CTAs (a third copy of the cells) would cost
     const size_t smem = static_cast<size_t>(32) * rows * 4 + MK_FWD_EXTRA_SMEM;
@@ -530,7 +536,7 @@ static int launch_fwd_banked(const mk_part* parts, int64_t num_parts, const int*
         if (ep.gamma != nullptr) {
             rc = go(spgemm_fwd_banked_kernel<K, U, false, PACKED, true, MK_EPI_PREFETCH(K)>);
         } else {
-            if constexpr (K == 16)
+            if constexpr ((MK_FWD_PLAIN_BARE_MASK & K) != 0)
                 rc = go(spgemm_fwd_banked_kernel<K, U, false, PACKED, false, false>);
             else
                 rc = go(spgemm_fwd_banked_kernel<K, U, false, PACKED, true, true>);
