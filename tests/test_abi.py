@@ -49,6 +49,30 @@ def test_library_is_sm100a_and_has_no_torch_dependency(built_lib):
     assert "torch" not in needed and "c10" not in needed and "libcudart" not in needed
 
 
+def _sass(built_lib, mangled_prefix):
+    """SASS text of every kernel of the library whose mangled name starts with the prefix."""
+    names = subprocess.check_output(["cuobjdump", "-elf", built_lib]).decode()
+    import re
+    funs = sorted(set(re.findall(r"\.text\.(" + re.escape(mangled_prefix) + r"\w*)", names)))
+    assert funs, mangled_prefix
+    return "".join(subprocess.check_output(["cuobjdump", "-sass", "-fun", f, built_lib]).decode() for f in funs[:1])
+
+
+def test_sass_carries_the_instructions_the_design_names(built_lib):
+    """DESIGN.md section 5 by mnemonic: the lane-contiguous top-k loads rows with 256-bit loads, bounds the search
+    with a warp minimum and stages entries with 64-bit shared stores; the backward reduces with four-wide float
+    reductions in L2; the forward never uses a float atomic; the multicast exchange uses the switch."""
+    topk = _sass(built_lib, "_ZN2mk21topk_cbsr_lane_kernelILi2EhLi8ELb1E")
+    assert "LDG.E.NA.ENL2.256" in topk or ".256" in topk
+    assert "CREDUX.MIN" in topk and "STS.64" in topk and "REDUX.SUM" in topk
+    bwd = _sass(built_lib, "_ZN2mk22sspmm_bwd_kernel_occ32ILi32Eh")
+    assert "REDG.E.ADD.F32x4" in bwd or "RED.E.ADD.F32x4" in bwd
+    fwd = _sass(built_lib, "_ZN2mk24spgemm_fwd_banked_kernelILi32ELi4ELb0ELb0E")
+    assert "ATOM" not in fwd and "RED." not in fwd and "LDS" in fwd and "STS" in fwd
+    mc = _sass(built_lib, "_ZN2mk29peer_reduce_scatter_mc_kernel")
+    assert "LDGMC" in mc and "ADD.F32x4" in mc
+
+
 def test_version_and_error_strings(built_lib):
     L = _lib.lib()
     assert L.mk_version() == 202
