@@ -58,16 +58,21 @@ __device__ __forceinline__ void bank_assign(ColF col, uint8_t* __restrict__ my_d
         }
     }
 
-    // ---- members of every bank
-    Mask member[8];
-#pragma unroll
-    for (int x = 0; x < 8; ++x) member[x] = 0;
+    // ---- members of every bank, bit-sliced: the three bits of every entry's bank as masks over the entries,
+    //      then bank x = the entries whose three bits spell x (3 K + 16 operations instead of 24 K)
+    Mask bit0 = 0, bit1 = 0, bit2 = 0;
 #pragma unroll
     for (int e = 0; e < K; ++e) {
         const int cls = ((choice >> e) & 1) ? ((col(e) >> 3) & 7) : (col(e) & 7);
-#pragma unroll
-        for (int x = 0; x < 8; ++x) member[x] |= static_cast<Mask>(cls == x ? 1 : 0) << e;
+        bit0 |= static_cast<Mask>(cls & 1) << e;
+        bit1 |= static_cast<Mask>((cls >> 1) & 1) << e;
+        bit2 |= static_cast<Mask>((cls >> 2) & 1) << e;
     }
+    const Mask all = static_cast<Mask>(K >= 64 ? ~0ull : ((1ull << (K & 63)) - 1ull));
+    Mask member[8];
+#pragma unroll
+    for (int x = 0; x < 8; ++x)
+        member[x] = ((x & 1) ? bit0 : ~bit0) & ((x & 2) ? bit1 : ~bit1) & ((x & 4) ? bit2 : ~bit2) & all;
 
     // ---- positions: step q takes one entry of every non-empty bank, then tops up from the
     //      fullest banks; lane t of a group reads positions [CAP*t, CAP*t + CAP)
