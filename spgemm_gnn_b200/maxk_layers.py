@@ -35,6 +35,66 @@ FUSED_LN_EPILOGUE = os.environ.get("MAXK_FUSED_LN", "1") != "0"
 
 
 # ---------------------------------------------------------------------------------------
+# Linear layers: torch GEMMs (the contract of this tier), with ONE change in the backward.  The weight
+# gradient dW = dY^T X reduces over all N nodes into an out x in matrix of a few tiles (256 x 256: four
+# 128 x 128 tiles for 148 SMs), and cuBLAS runs it as such: 0.209 ms at N = 232,965 against 0.083 ms for the
+# forward GEMM of the same size.  Cut into SPLITK_CHUNKS row blocks -- one batched GEMM, then a sum of the
+# partial matrices -- it takes 0.094 ms (608 inputs: 0.462 -> 0.171 ms; products shape: 1.88 -> 0.71 ms;
+# profiles/r2/dw_gemm_probe_call53.log), ~1.1 ms of a 32 ms MaxK-SAGE epoch on the Reddit shape.  Same
+# module, same parameters and state dict as nn.Linear; MAXK_SPLITK_DW=0 restores autograd's own form.
+# ---------------------------------------------------------------------------------------
+SPLITK_DW = os.environ.get("MAXK_SPLITK_DW", "1") != "0"
+SPLITK_MIN_ROWS = 8192
+
+
+def weight_grad(grad_out: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dW [out, in] = grad_out^T x for 2-D row-major operands, row-blocked when the reduction is long."""
+    n = grad_out.shape[0]
+    if not (SPLITK_DW and grad_out.is_cuda and n >= SPLITK_MIN_ROWS):
+        return grad_out.t().mm(x)
+    chunks = 32 if n >= (1 << 20) else 16
+    rows = n // chunks
+    main = rows * chunks
+    g = grad_out.contiguous()
+    xc = x.contiguous()
+    dw = torch.bmm(g[:main].view(chunks, rows, g.shape[1]).transpose(1, 2),
+                   xc[:main].view(chunks, rows, xc.shape[1])).sum(0)
+    if main < n:
+        dw = dw + g[main:].t().mm(xc[main:])
+    return dw
+
+
+class _LinearFunction(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, weight = ctx.saved_tensors
+        gx = grad_out.mm(weight) if ctx.needs_input_grad[0] else None
+        gw = weight_grad(grad_out, x) if ctx.needs_input_grad[1] else None
+        gb = grad_out.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
+    """`F.linear(x, weight, bias)` whose backward forms dW with `weight_grad`."""
+    if x.dim() != 2 or not x.is_cuda or not SPLITK_DW:
+        return torch.nn.functional.linear(x, weight, bias)
+    return _LinearFunction.apply(x, weight, bias)
+
+
+class Linear(nn.Linear):
+    """nn.Linear (same parameters, initialisation and state dict) on `linear` above."""
+
+    def forward(self, x):
+        return linear(x, self.weight, self.bias)
+
+
+# ---------------------------------------------------------------------------------------
 # autograd Functions
 # ---------------------------------------------------------------------------------------
 class MaxKFunction(Function):
@@ -319,8 +379,8 @@ class MaxKSAGEConv(nn.Module):
         self.out_feats = out_feats
         self.aggregator_type = aggregator_type
         self.maxk = maxk
-        self.fc_self = nn.Linear(in_feats, out_feats, bias=False)
-        self.fc_neigh = nn.Linear(in_feats, out_feats, bias=False)
+        self.fc_self = Linear(in_feats, out_feats, bias=False)
+        self.fc_neigh = Linear(in_feats, out_feats, bias=False)
         self.norm = norm
         if norm is not None and isinstance(norm, type):
             self.norm = norm(out_feats)
@@ -417,8 +477,8 @@ class MaxKGINConv(nn.Module):
             self.eps = nn.Parameter(torch.zeros(1))
         else:
             self.register_buffer("eps", torch.zeros(1))
-        self.mlp = nn.Sequential(nn.Linear(in_feats, out_feats), nn.ReLU(),
-                                 nn.Linear(out_feats, out_feats))
+        self.mlp = nn.Sequential(Linear(in_feats, out_feats), nn.ReLU(),
+                                 Linear(out_feats, out_feats))
         self.maxk_fn = MaxKFunction.apply
         self.reset_parameters()
 

@@ -24,9 +24,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 import torch.nn.init as init
-from torch.nn import Linear
-
-from .maxk_layers import (CBSRToDenseFunction, MaxKCBSRFunction, MaxKFunction, MaxKGCNConv,
+from .maxk_layers import (CBSRToDenseFunction, Linear, linear, MaxKCBSRFunction, MaxKFunction, MaxKGCNConv,
                           MaxKGINConv, MaxKSAGEConv, _dense_aggregate, add_layer_norm, aggregate_cbsr)
 
 
@@ -74,7 +72,7 @@ def aligned_linear(lin: nn.Linear, x: torch.Tensor) -> torch.Tensor:
         return lin(x)
     w = F.pad(lin.weight, (0, extra_in, 0, extra_out))
     b = None if lin.bias is None else F.pad(lin.bias, (0, extra_out))
-    y = F.linear(x, w, b)
+    y = linear(x, w, b)
     return y if extra_out == 0 else y[:, :lin.out_features]
 
 
@@ -89,8 +87,8 @@ class _SAGEConvMean(nn.Module):
     def __init__(self, in_feats, out_feats, feat_drop=0.0, norm=None):
         super().__init__()
         self.feat_drop = nn.Dropout(feat_drop)
-        self.fc_self = nn.Linear(in_feats, out_feats, bias=False)
-        self.fc_neigh = nn.Linear(in_feats, out_feats, bias=False)
+        self.fc_self = Linear(in_feats, out_feats, bias=False)
+        self.fc_neigh = Linear(in_feats, out_feats, bias=False)
         self.bias = nn.Parameter(torch.zeros(out_feats))
         self.norm = norm
         gain = nn.init.calculate_gain("relu")

@@ -283,3 +283,35 @@ def test_flickr_shape_first_step_against_cpu_reference():
         gr = rg[pn].grad
         rel = float((p.grad.cpu().double() - gr).norm() / (gr.norm() + 1e-30))
         assert rel <= 1e-2, (pn, rel)      # dominated by the flipped rows (measured 3e-3)
+
+
+def test_row_blocked_weight_gradient_is_the_linear_layers_gradient():
+    """`maxk_layers.Linear`: nn.Linear with dW formed from row blocks (one batched GEMM + a sum).  Same output, same
+    dX and bias gradient bit for bit, dW equal to autograd's form within fp32 summation-order noise -- with fp32 GEMMs
+    pinned (tolerance 2e-6 of max |dW|), for a row count with a remainder and for one below the blocking threshold."""
+    from spgemm_gnn_b200 import maxk_layers as ML
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        for n, fin, fout, bias in ((20011, 96, 64, True), (70001, 40, 48, False), (500, 32, 16, True)):
+            ref = torch.nn.Linear(fin, fout, bias=bias).cuda()
+            ours = ML.Linear(fin, fout, bias=bias).cuda()
+            ours.load_state_dict(ref.state_dict())
+            x = torch.randn(n, fin, device="cuda", generator=gen)
+            gy = torch.randn(n, fout, device="cuda", generator=gen)
+            xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+            ya, yb = ref(xa), ours(xb)
+            assert torch.equal(ya, yb)
+            ya.backward(gy)
+            yb.backward(gy)
+            assert torch.equal(xa.grad, xb.grad)
+            if bias:
+                assert torch.equal(ref.bias.grad, ours.bias.grad)
+            scale = float(ref.weight.grad.abs().max())
+            assert float((ref.weight.grad - ours.weight.grad).abs().max()) <= 2e-6 * scale
+            if n < ML.SPLITK_MIN_ROWS:       # below the threshold the layer IS autograd's form
+                assert torch.equal(ref.weight.grad, ours.weight.grad)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
