@@ -32,8 +32,15 @@ namespace mk {
 // table is complete before the kernel starts.  CG = true: L2-coherent loads (ld.global.cg) for the
 // forward that runs while peers are still storing other rows of the table over NVLink (the L1 hit
 // rate of these gathers is 0.15 % -- profiles/r1_final_* -- so nothing is lost).
+// -DMK_TAB_NOALLOC: the complete-table gathers with L1::no_allocate instead of the default read-only path
+// (measurement knob).  Their L1 hit rate is 0.15 %, and still the no-allocate form is much SLOWER: forward at k = 8 /
+// 16 / 32 / 64 1.459 / 2.005 / 2.816 / 5.758 ms as shipped, 1.537 / 2.161 / 3.454 / 9.411 ms without allocation
+// (profiles/r2/tab_noalloc_call57.log).
 template <bool CG>
 __device__ __forceinline__ float4 ld_tab_f4(const float* p) {
+#ifdef MK_TAB_NOALLOC
+    if (!CG) return ld_stream_f4(p);
+#endif
     if (!CG) return __ldg(reinterpret_cast<const float4*>(p));
     float4 r;
     asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
@@ -55,6 +62,13 @@ __device__ __forceinline__ float ld_tab_f1(const float* p) {
 }
 template <bool CG>
 __device__ __forceinline__ uint4 ld_tab_u4(const void* p) {
+#ifdef MK_TAB_NOALLOC
+    if (!CG) {
+        uint4 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+        return r;
+    }
+#endif
     if (!CG) return __ldg(reinterpret_cast<const uint4*>(p));
     uint4 r;
     asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -62,6 +76,13 @@ __device__ __forceinline__ uint4 ld_tab_u4(const void* p) {
 }
 template <bool CG>
 __device__ __forceinline__ uint2 ld_tab_u2(const void* p) {
+#ifdef MK_TAB_NOALLOC
+    if (!CG) {
+        uint2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+        return r;
+    }
+#endif
     if (!CG) return __ldg(reinterpret_cast<const uint2*>(p));
     uint2 r;
     asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
