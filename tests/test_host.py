@@ -261,3 +261,25 @@ def test_reorder_is_a_relabelling_and_rcm_restores_locality():
     assert bool((deg[:-1] >= deg[1:]).all())
     with pytest.raises(ValueError):
         G.reorder(g, "nope")
+
+
+def test_linear_is_nn_linear_with_the_same_state_dict_and_cpu_gradients():
+    """`maxk_layers.Linear` / `weight_grad`: on the CPU (and below the row threshold) it IS nn.Linear -- same
+    parameter names, same outputs, same gradients bit for bit; the row-blocked form is a CUDA-only path."""
+    from spgemm_gnn_b200 import maxk_layers as ML
+    torch.manual_seed(3)
+    ref = torch.nn.Linear(12, 7)
+    ours = ML.Linear(12, 7)
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    ours.load_state_dict(ref.state_dict())
+    x = torch.randn(50, 12)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = ref(xa), ours(xb)
+    assert torch.equal(ya, yb)
+    g = torch.randn(50, 7)
+    ya.backward(g)
+    yb.backward(g)
+    assert torch.equal(xa.grad, xb.grad) and torch.equal(ref.weight.grad, ours.weight.grad)
+    assert torch.equal(ref.bias.grad, ours.bias.grad)
+    assert torch.equal(ML.weight_grad(g, x), g.t().mm(x))
+    assert isinstance(ours, torch.nn.Linear)
